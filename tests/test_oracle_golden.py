@@ -1,0 +1,96 @@
+"""Pins the CPU oracle (oracle/dvc_oracle.py) against outputs of the unmodified reference.
+
+The golden vectors were produced by oracle/gen_golden.py importing /root/reference; these tests
+run everywhere (no GPU, no reference needed).  ``test_live_reference_*`` additionally re-runs the
+reference when the checkout is present (build container only).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import dvc_oracle as O
+from oracle import ref_shim
+
+INTER = ["estmv", "mvfeature", "quant_mv", "mv_hat", "warpframe", "prediction", "feature", "z", "z_hat",
+         "sigma", "feat_hat", "recon_res", "recon"]
+SCALARS = ["mse", "warploss", "interloss", "bpp_feature", "bpp_z", "bpp_mv", "bpp"]
+
+
+def _check_pframe(sd, gold):
+    out, cap = O.pframe_forward(sd, gold["cur"], gold["ref"], capture=True)
+    for name in INTER:
+        a, b = cap[name], gold[name]
+        assert a.shape == b.shape, name
+        if name in ("quant_mv", "z_hat", "feat_hat"):
+            mism = (a != b).float().mean().item()
+            assert mism <= 1e-4, (name, mism)
+        else:
+            err = (a - b).abs().max().item()
+            scale = max(1.0, b.abs().max().item())
+            assert err <= 2e-4 * scale, (name, err, scale)
+    assert (out[0] - gold["clipped"]).abs().max().item() <= 1e-4
+    for i, name in enumerate(SCALARS, start=1):
+        a, b = float(out[i]), float(gold[name])
+        assert abs(a - b) <= 1e-4 * max(abs(b), 1e-3), (name, a, b)
+
+
+def test_oracle_matches_reference_pframe_64(state_dict, golden_pframe_64):
+    _check_pframe(state_dict, golden_pframe_64)
+
+
+def test_oracle_matches_reference_pframe_128(state_dict, golden_pframe_128):
+    _check_pframe(state_dict, golden_pframe_128)
+
+
+def test_oracle_matches_reference_gop(state_dict, golden_gop_64):
+    rows, rec = O.gop_forward(state_dict, golden_gop_64["frames"])
+    g = golden_gop_64["rows"]  # [mse, warploss, interloss, bpp_f, bpp_z, bpp_mv, bpp, psnr]
+    assert (rec - golden_gop_64["recon"]).abs().max().item() <= 1e-2
+    for i, (bpp, psnr, mse) in enumerate(rows):
+        assert abs(bpp - g[i, 6].item()) <= 0.005 * g[i, 6].item()
+        assert abs(psnr - g[i, 7].item()) <= 0.02
+
+
+def test_oracle_ops(golden_ops):
+    g = golden_ops
+    assert (O.flow_warp(g["warp_img"], g["warp_flow"]) - g["warp_out"]).abs().max() <= 1e-5
+    z = O.flow_warp(g["warp_img"], torch.zeros_like(g["warp_flow"]))
+    assert (z - g["warp_zero_flow_out"]).abs().max() <= 1e-5
+    # zero flow is NOT the identity
+    assert (z - g["warp_img"]).abs().max() > 1e-3
+    assert (O.upsample2x_bilinear(g["up_in"], False) - g["up_half_pixel"]).abs().max() <= 1e-6
+    assert (O.upsample2x_bilinear(g["up_in"], True) - g["up_align_corners"]).abs().max() <= 1e-5
+    assert torch.equal(O.avg_pool2(g["up_in"]), g["pool_out"])
+    sd = {"g.beta": g["gdn_beta"], "g.gamma": g["gdn_gamma"]}
+    assert (O.gdn(sd, "g", g["gdn_in"]) - g["gdn_out"]).abs().max() <= 1e-5
+    assert (O.gdn(sd, "g", g["gdn_in"], inverse=True) - g["igdn_out"]).abs().max() <= 1e-4
+
+
+def test_oracle_bit_estimators(state_dict, golden_ops):
+    g = golden_ops
+    hi = O.bit_estimator_cdf(state_dict, "bitEstimator_z", g["be_q"] + 0.5)
+    lo = O.bit_estimator_cdf(state_dict, "bitEstimator_z", g["be_q"] - 0.5)
+    assert (hi - g["be_cdf_hi"]).abs().max() <= 1e-6
+    assert (lo - g["be_cdf_lo"]).abs().max() <= 1e-6
+    _, prob = O.laplace_bits(g["lap_q"], g["lap_sigma"])
+    assert (prob - g["lap_prob"]).abs().max() <= 1e-6
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+def test_live_reference_real_spynet_weights():
+    """Same check against the live reference with its real SpyNet .npy weights (|w|max ~ 5)."""
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    torch.manual_seed(0)
+    model = ref_shim.build_reference_model(None)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    fr = synthetic_gop(64, 64, gop=2, gop_id=5)[:, 0]
+    out_ref, cap_ref = ref_shim.run_reference_with_capture(model, fr[1:2], fr[0:1])
+    out, cap = O.pframe_forward(sd, fr[1:2], fr[0:1], capture=True)
+    for name in ("estmv", "mv_hat", "prediction", "recon"):
+        err = (cap[name] - cap_ref[name]).abs().max().item()
+        assert err <= 2e-4 * max(1.0, cap_ref[name].abs().max().item()), (name, err)
+    for name in ("quant_mv", "z_hat", "feat_hat"):
+        assert (cap[name] != cap_ref[name]).float().mean().item() <= 1e-4
+    assert abs(float(out[7]) - float(out_ref[7])) <= 1e-4 * float(out_ref[7])
+    assert abs(10 * math.log10(1 / float(out[1])) - 10 * math.log10(1 / float(out_ref[1]))) <= 0.02
