@@ -1,0 +1,93 @@
+"""ctypes binding of libfvc_b200.so (C ABI declared in include/fvc_b200.h).
+
+The library is the product: if it is missing, or there is no CUDA device when a compute entry
+point is called, we raise — there is no CPU or PyTorch fallback on this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfvc_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fvc_b200.h")
+
+ACT_NONE, ACT_RELU, ACT_LRELU01, ACT_EXP = 0, 1, 2, 3
+IMPL_SIMT, IMPL_TC = 0, 1
+
+_lib = None
+
+_f = C.c_void_p   # device float*
+_i = C.c_int
+_l = C.c_int64
+_s = C.c_void_p   # cudaStream_t
+
+_SIGNATURES = {
+    "fvc_version": (C.c_int, []),
+    "fvc_last_error": (C.c_char_p, []),
+    "fvc_avg_pool2": (_i, [_f, _f, _i, _i, _i, _s]),
+    "fvc_upsample2x_bilinear": (_i, [_f, _f, _i, _i, _i, _i, C.c_float, _s]),
+    "fvc_flow_warp": (_i, [_f, _f, _f, _i, _i, _i, _i, _s]),
+    "fvc_conv2d": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _s]),
+    "fvc_gdn": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _s]),
+    "fvc_quant_bits_factorized": (_i, [_f, C.POINTER(C.c_void_p), _f, _f, _i, _i, _i, _i, _s]),
+    "fvc_quant_bits_laplace": (_i, [_f, _f, _f, _f, _l, _s]),
+    "fvc_recon_losses": (_i, [_f, _f, _f, _f, _f, _f, _l, _s]),
+    "fvc_eb_forward": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _s]),
+    "fvc_gaussian_forward": (_i, [_f, _f, _f, _f, _f, _f, _l, _s]),
+    "fvc_ctx_create": (C.c_void_p, [_i, _i, _i, _i, _i]),
+    "fvc_ctx_destroy": (None, [C.c_void_p]),
+    "fvc_ctx_set_param": (_i, [C.c_void_p, C.c_char_p, _f, _l, _s]),
+    "fvc_ctx_missing_params": (_i, [C.c_void_p]),
+    "fvc_pframe_forward": (_i, [C.c_void_p, _f, _f, _f, _f, _s]),
+    "fvc_ctx_get_tensor": (_l, [C.c_void_p, C.c_char_p, _f, _l, _s]),
+    "fvc_gop_forward_host": (_i, [C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, _s]),
+    "fvc_ctx_launch_count": (_l, [C.c_void_p]),
+    "fvc_ctx_last_conv_seconds": (C.c_double, [C.c_void_p]),
+}
+
+
+def declared_symbols():
+    """Every function include/fvc_b200.h declares (parsed from the header)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"FVC_API\s+[\w\s\*]+?\b(fvc_\w+)\s*\(", text)))
+
+
+def lib():
+    """Loads (once) and returns the shared library; raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libfvc_b200.so is not built (%s). Run `python -m fastvideocodec_b200.build`; "
+                "there is no fallback path." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+class FvcError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc is not None and rc < 0:
+        msg = lib().fvc_last_error()
+        raise FvcError("%s failed (%d): %s" % (what or "libfvc_b200 call", rc, (msg or b"").decode()))
+    return rc
+
+
+def stream_ptr():
+    """Raw cudaStream_t of torch's current stream (so calls compose with torch ordering)."""
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())

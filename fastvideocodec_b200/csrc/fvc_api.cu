@@ -1,0 +1,228 @@
+// C ABI: op-level entry points (one per reference op; see include/fvc_b200.h).
+#include <vector>
+#include <cstring>
+#include <algorithm>
+
+#include "fvc_kernels.cuh"
+
+using namespace fvc;
+
+namespace {
+
+struct TmpPool {  // stream-ordered temporaries, released on scope exit
+    cudaStream_t s;
+    std::vector<void*> ptrs;
+    explicit TmpPool(cudaStream_t st) : s(st) {}
+    template <typename T>
+    int get(T** p, size_t bytes) {
+        void* q = nullptr;
+        FVC_CUDA(cudaMallocAsync(&q, bytes ? bytes : 16, s));
+        ptrs.push_back(q);
+        *p = reinterpret_cast<T*>(q);
+        return 0;
+    }
+    ~TmpPool() {
+        for (void* p : ptrs) cudaFreeAsync(p, s);
+    }
+};
+
+int pad_c(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : 128); }
+
+int have_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device (%s); libfvc_b200 has no CPU fallback", cudaGetErrorString(e));
+        return FVC_ERR_CUDA;
+    }
+    return 0;
+}
+#define NEED_DEVICE() do { int _r = have_device(); if (_r) return _r; } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int fvc_avg_pool2(const float* x, float* y, int planes, int H, int W, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(x && y && planes >= 0 && H >= 0 && W >= 0 && (H % 2 == 0) && (W % 2 == 0));
+    return launch_avg_pool2_planar(x, y, planes, H, W, (cudaStream_t)stream);
+}
+
+int fvc_upsample2x_bilinear(const float* x, float* y, int planes, int H, int W, int align_corners, float scale,
+                            void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(x && y && planes >= 0 && H >= 0 && W >= 0);
+    return launch_upsample2x_planar(x, y, planes, H, W, align_corners, scale, (cudaStream_t)stream);
+}
+
+int fvc_flow_warp(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(img && flow && out && B >= 0 && C >= 0 && H >= 2 && W >= 2);
+    return launch_flow_warp_nchw(img, flow, out, B, C, H, W, (cudaStream_t)stream);
+}
+
+int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W, int Cout,
+               int k, int stride, int transposed, int act, int impl, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(x && w && bias && y);
+    FVC_ARG(B >= 1 && Cin >= 1 && Cin <= 128 && Cout >= 1 && Cout <= 128 && (k == 1 || k == 3 || k == 5 || k == 7));
+    FVC_ARG(stride == 1 || stride == 2);
+    FVC_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0) || transposed);
+    cudaStream_t s = (cudaStream_t)stream;
+    ConvLayer L;
+    make_conv_layer(L, Cin, Cout, k, stride, transposed);
+    int Ho = transposed ? H * stride : H / stride, Wo = transposed ? W * stride : W / stride;
+    TmpPool tmp(s);
+    ActT in;
+    in.B = B; in.H = H; in.W = W; in.Cp = pad_c(Cin); in.parity = (!transposed && stride == 2) ? 1 : 0;
+    if (tmp.get(&in.p, act_bytes(B, H, W, in.Cp))) return FVC_ERR_CUDA;
+    int rc = launch_nchw_to_act(x, in, Cin, 0, s);
+    if (rc) return rc;
+    float* out_nhwc = nullptr;
+    if (tmp.get(&out_nhwc, (size_t)B * Ho * Wo * Cout * 4)) return FVC_ERR_CUDA;
+    Epilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.bias = bias;
+    ep.act = act;
+    ep.out_f32 = out_nhwc;
+    if (impl == FVC_IMPL_TC) {
+        if (!tc_supported(L, in.Cp)) {
+            set_error("fvc_conv2d: shape not supported by the tcgen05 engine");
+            return FVC_ERR_ARG;
+        }
+        TcPlan* plan = nullptr;
+        rc = tc_plan_create(L, w, in, Ho, Wo, ep, &plan, s);
+        if (rc) return rc;
+        rc = tc_plan_launch(plan, s);
+        if (rc == 0) rc = (cudaStreamSynchronize(s) == cudaSuccess) ? 0 : cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
+        tc_plan_destroy(plan);
+        if (rc) return rc;
+    } else {
+        SimtWeights sw;
+        rc = simt_pack_weights(L, w, in.Cp, std::max(pad_c(Cout), 32), &sw, s);
+        if (rc) return rc;
+        rc = launch_conv_simt(L, sw, in, Ho, Wo, ep, s);
+        cudaStreamSynchronize(s);
+        cudaFree(sw.w);
+        if (rc) return rc;
+    }
+    return launch_nhwc_to_nchw(out_nhwc, y, B, Cout, Ho, Wo, s);
+}
+
+int fvc_gdn(const float* x, const float* beta, const float* gamma, float* y, int B, int C, int H, int W,
+            int inverse, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(x && beta && gamma && y && C >= 8 && C <= 64 && C % 8 == 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    TmpPool tmp(s);
+    ActT in, out;
+    in.B = B; in.H = H; in.W = W; in.Cp = pad_c(C); in.parity = 0;
+    out = in;
+    float *be = nullptr, *ge = nullptr;
+    if (tmp.get(&in.p, act_bytes(B, H, W, in.Cp)) || tmp.get(&out.p, act_bytes(B, H, W, in.Cp)) ||
+        tmp.get(&be, C * 4) || tmp.get(&ge, (size_t)C * C * 4))
+        return FVC_ERR_CUDA;
+    int rc = launch_nchw_to_act(x, in, C, 0, s);
+    if (!rc) rc = launch_gdn_reparam(beta, gamma, be, ge, C, s);
+    if (!rc) rc = launch_gdn_act(in, C, be, ge, inverse, out, s);
+    if (!rc) rc = launch_act_to_nchw(out, C, y, s);
+    return rc;
+}
+
+int fvc_quant_bits_factorized(const float* x, const float* const* params, float* q_out, float* bits_out, int B,
+                              int C, int H, int W, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(x && params && bits_out && B >= 0 && C >= 1 && H >= 0 && W >= 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    TmpPool tmp(s);
+    float* partials = nullptr;
+    if (tmp.get(&partials, (size_t)bits_max_blocks() * 4)) return FVC_ERR_CUDA;
+    FactorizedParams prm;
+    for (int i = 0; i < 11; ++i) {
+        FVC_ARG(params[i] != nullptr);
+        prm.p[i] = params[i];
+    }
+    ActT none;
+    memset(&none, 0, sizeof(none));
+    int nb = 0;
+    if ((int64_t)B * C * H * W == 0) {
+        FVC_CUDA(cudaMemsetAsync(bits_out, 0, 4, s));
+        return 0;
+    }
+    int rc = launch_quant_bits_factorized(x, 0, B, C, H * W, prm, q_out, none, partials, &nb, s);
+    if (rc) return rc;
+    return launch_reduce_partials(partials, nb, 1, 1.0, bits_out, s);
+}
+
+int fvc_quant_bits_laplace(const float* x, const float* sigma, float* q_out, float* bits_out, int64_t n,
+                           void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(x && sigma && bits_out && n >= 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        FVC_CUDA(cudaMemsetAsync(bits_out, 0, 4, s));
+        return 0;
+    }
+    TmpPool tmp(s);
+    float* partials = nullptr;
+    if (tmp.get(&partials, (size_t)bits_max_blocks() * 4)) return FVC_ERR_CUDA;
+    ActT none;
+    memset(&none, 0, sizeof(none));
+    int nb = 0;
+    int rc = launch_quant_bits_laplace(x, sigma, n, 1, q_out, none, partials, &nb, s);
+    if (rc) return rc;
+    return launch_reduce_partials(partials, nb, 1, 1.0, bits_out, s);
+}
+
+int fvc_recon_losses(const float* cur, const float* pred, const float* warp, const float* res, float* clipped_out,
+                     float* means_out, int64_t n, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(cur && pred && warp && res && clipped_out && means_out && n > 0 && n % 3 == 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    TmpPool tmp(s);
+    float* partials = nullptr;
+    if (tmp.get(&partials, (size_t)148 * 8 * 3 * 4)) return FVC_ERR_CUDA;
+    int nb = 0;
+    int rc = launch_recon_losses(cur, pred, warp, res, 0, 1, (int)(n / 3), clipped_out, partials, &nb, s);
+    if (rc) return rc;
+    return launch_reduce_partials(partials, nb, 3, 1.0 / (double)n, means_out, s);
+}
+
+int fvc_eb_forward(const float* x, const float* packed_params, const float* medians, float* xhat_out, float* lik_out,
+                   float* bits_out, int B, int C, int H, int W, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(x && packed_params && medians && bits_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((int64_t)B * C * H * W == 0) {
+        FVC_CUDA(cudaMemsetAsync(bits_out, 0, 4, s));
+        return 0;
+    }
+    TmpPool tmp(s);
+    float* partials = nullptr;
+    if (tmp.get(&partials, (size_t)bits_max_blocks() * 4)) return FVC_ERR_CUDA;
+    int nb = 0;
+    int rc = launch_eb_forward(x, packed_params, medians, xhat_out, lik_out, partials, &nb, B, C, H * W, s);
+    if (rc) return rc;
+    return launch_reduce_partials(partials, nb, 1, 1.0, bits_out, s);
+}
+
+int fvc_gaussian_forward(const float* x, const float* scales, const float* means, float* xhat_out, float* lik_out,
+                         float* bits_out, int64_t n, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(x && scales && bits_out && n >= 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        FVC_CUDA(cudaMemsetAsync(bits_out, 0, 4, s));
+        return 0;
+    }
+    TmpPool tmp(s);
+    float* partials = nullptr;
+    if (tmp.get(&partials, (size_t)bits_max_blocks() * 4)) return FVC_ERR_CUDA;
+    int nb = 0;
+    int rc = launch_gaussian_forward(x, scales, means, xhat_out, lik_out, partials, &nb, n, s);
+    if (rc) return rc;
+    return launch_reduce_partials(partials, nb, 1, 1.0, bits_out, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// Shared device/host helpers for libfvc_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <algorithm>
+
+#include "../../include/fvc_b200.h"
+
+namespace fvc {
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define FVC_CUDA(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return fvc::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+#define FVC_CHECK_LAUNCH() FVC_CUDA(cudaGetLastError())
+#define FVC_ARG(cond)                                                         \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            fvc::set_error("bad argument: %s (%s:%d)", #cond, __FILE__, __LINE__); \
+            return FVC_ERR_ARG;                                               \
+        }                                                                     \
+    } while (0)
+
+extern thread_local int64_t g_launch_count;  // kernels launched by this library on this thread
+
+// ----------------------------------------------------------------------------------------------
+// Activation record format ("ACT"): NHWC, per pixel [hi: Cp bf16][lo: Cp bf16]; value = hi + lo.
+// hi = bf16_rn(v), lo = bf16_rn(v - hi): 16 significant mantissa bits, the operand precision the
+// parity contract needs; both halves feed tcgen05 kind::f16 MMAs directly.
+// parity layout (inputs of stride-2 convs): 4 planes [(y&1)*2+(x&1)][H/2][W/2][record].
+// ----------------------------------------------------------------------------------------------
+struct ActT {
+    __nv_bfloat16* p;
+    int B, H, W, Cp;
+    int parity;
+};
+
+__host__ __device__ inline size_t act_bytes(int B, int H, int W, int Cp) {
+    return (size_t)B * H * W * Cp * 2 * sizeof(__nv_bfloat16);
+}
+
+__device__ __forceinline__ size_t act_pixel_offset(const ActT& t, int b, int y, int x) {
+    size_t pix;
+    if (t.parity) {
+        int plane = ((y & 1) << 1) | (x & 1);
+        pix = (((size_t)(b * 4 + plane) * (t.H >> 1) + (y >> 1)) * (t.W >> 1) + (x >> 1));
+    } else {
+        pix = ((size_t)b * t.H + y) * t.W + x;
+    }
+    return pix * (size_t)(2 * t.Cp);
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ float act_load(const ActT& t, size_t pixoff, int c) {
+    return __bfloat162float(t.p[pixoff + c]) + __bfloat162float(t.p[pixoff + t.Cp + c]);
+}
+
+__device__ __forceinline__ void act_store(const ActT& t, size_t pixoff, int c, float v) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    t.p[pixoff + c] = hi;
+    t.p[pixoff + t.Cp + c] = lo;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// warp + block sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem32[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.f;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------------------------
+// Convolution description shared by both engines.  A layer is 1 sub-convolution (conv, or
+// stride-1 transposed conv) or 4 (stride-2 transposed conv, one per output parity phase); every
+// sub-convolution is a gather  out(q*os + ph) = sum_taps in(q*st + d_tap) * W_tap.
+// ----------------------------------------------------------------------------------------------
+#define FVC_MAX_TAPS 49
+
+struct SubConv {
+    int ntaps;
+    int py, px;                 // output phase (transposed stride 2), else 0
+    int8_t dy[FVC_MAX_TAPS];    // input offset of the tap on the (strided) q grid
+    int8_t dx[FVC_MAX_TAPS];
+    int8_t r[FVC_MAX_TAPS];     // kernel coordinates of the tap in the reference weight
+    int8_t s[FVC_MAX_TAPS];
+};
+
+struct ConvLayer {
+    int Cin, Cout, k, stride, transposed;
+    int nsub;
+    SubConv sub[4];
+    int st;   // input step on the q grid (2 for a stride-2 conv, else 1)
+    int os;   // output step (2 for a stride-2 transposed conv, else 1)
+};
+
+void make_conv_layer(ConvLayer& L, int Cin, int Cout, int k, int stride, int transposed);
+
+// Epilogue description (device-visible POD)
+struct Epilogue {
+    const float* bias;        // [Cout]
+    int act;                  // FVC_ACT_*
+    ActT res_act;             // optional residual (p == nullptr: none), same geometry as the output
+    const float* res_f32;     // optional fp32 NHWC residual [B,Hout,Wout,Cout]
+    ActT out_act;             // optional ACT output (p == nullptr: none)
+    ActT out_act_relu;        // optional second ACT output holding relu(y)
+    float* out_f32;           // optional fp32 NHWC output [B,Hout,Wout,Cout]
+    const float* gdn_beta;    // fused (I)GDN: effective beta [C], gamma [C][C]; nullptr: none
+    const float* gdn_gamma;
+    int gdn_inverse;
+};
+
+}  // namespace fvc

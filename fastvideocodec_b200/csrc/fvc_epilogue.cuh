@@ -1,0 +1,102 @@
+// Shared convolution epilogue: bias, activation, residual, output formats.  Used by both engines.
+#pragma once
+#include "fvc_common.cuh"
+
+namespace fvc {
+
+__device__ __forceinline__ void ep_load8(const __nv_bfloat16* rec, int Cp, int c0, float* v) {
+    uint4 h = *reinterpret_cast<const uint4*>(rec + c0);
+    uint4 l = *reinterpret_cast<const uint4*>(rec + Cp + c0);
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[2 * j] = __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+        v[2 * j + 1] = __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void ep_store8(__nv_bfloat16* rec, int Cp, int c0, const float* v, bool relu) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = v[2 * j], b = v[2 * j + 1];
+        if (relu) {
+            a = fmaxf(a, 0.f);
+            b = fmaxf(b, 0.f);
+        }
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(a, h0, l0);
+        split_bf16(b, h1, l1);
+        hi[j] = pack_bf16x2(h0, h1);
+        lo[j] = pack_bf16x2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(rec + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(rec + Cp + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__device__ __forceinline__ float ep_act(float v, int act) {
+    switch (act) {
+        case FVC_ACT_RELU: return fmaxf(v, 0.f);
+        case FVC_ACT_LRELU01: return v > 0.f ? v : v * 0.1f;
+        case FVC_ACT_EXP: return expf(v);
+        default: return v;
+    }
+}
+
+// v[NCH]: raw accumulators of output channels co0..co0+NCH-1 of output pixel (b,oy,ox).
+// Applies bias + activation (+ residuals) in place and writes every configured output.
+template <int NCH>
+__device__ __forceinline__ void epilogue_apply(const Epilogue& ep, int Cout, int Hout, int Wout, int b, int oy,
+                                               int ox, int co0, float* v, bool skip_bias_act = false) {
+    if (!skip_bias_act) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            int c = co0 + j;
+            v[j] = (c < Cout) ? ep_act(v[j] + ep.bias[c], ep.act) : 0.f;
+        }
+    }
+    size_t pix = ((size_t)b * Hout + oy) * Wout + ox;
+    if (ep.res_act.p) {
+        const __nv_bfloat16* rec = ep.res_act.p + act_pixel_offset(ep.res_act, b, oy, ox);
+#pragma unroll
+        for (int g = 0; g < NCH / 8; ++g) {
+            if (co0 + g * 8 < ep.res_act.Cp) {
+                float r[8];
+                ep_load8(rec, ep.res_act.Cp, co0 + g * 8, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] += r[j];
+            }
+        }
+    }
+    if (ep.res_f32) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+            if (co0 + j < Cout) v[j] += ep.res_f32[pix * Cout + co0 + j];
+    }
+    if (ep.out_f32) {
+        if ((Cout & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < NCH; j += 4)
+                if (co0 + j < Cout)
+                    *reinterpret_cast<float4*>(ep.out_f32 + pix * Cout + co0 + j) =
+                        make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+                if (co0 + j < Cout) ep.out_f32[pix * Cout + co0 + j] = v[j];
+        }
+    }
+    if (ep.out_act.p) {
+        __nv_bfloat16* rec = ep.out_act.p + act_pixel_offset(ep.out_act, b, oy, ox);
+#pragma unroll
+        for (int g = 0; g < NCH / 8; ++g)
+            if (co0 + g * 8 < ep.out_act.Cp) ep_store8(rec, ep.out_act.Cp, co0 + g * 8, v + g * 8, false);
+    }
+    if (ep.out_act_relu.p) {
+        __nv_bfloat16* rec = ep.out_act_relu.p + act_pixel_offset(ep.out_act_relu, b, oy, ox);
+#pragma unroll
+        for (int g = 0; g < NCH / 8; ++g)
+            if (co0 + g * 8 < ep.out_act_relu.Cp) ep_store8(rec, ep.out_act_relu.Cp, co0 + g * 8, v + g * 8, true);
+    }
+}
+
+}  // namespace fvc

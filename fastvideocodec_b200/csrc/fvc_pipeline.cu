@@ -1,0 +1,790 @@
+// Whole-path context: VideoCompressor.forward (reference DVC/net.py:70-220) as a stream-ordered
+// sequence of sm_100a kernels over library-owned buffers.  The context consumes the reference
+// state_dict layout directly and packs weights on the device.
+#include <map>
+#include <string>
+#include <vector>
+#include <cstdarg>
+#include <cstring>
+
+#include "fvc_kernels.cuh"
+
+namespace fvc {
+
+thread_local std::string g_err;
+thread_local int64_t g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return FVC_ERR_CUDA;
+}
+
+// ----------------------------------------------------------------------------------------------
+struct ConvRt {
+    std::string name;
+    ConvLayer L;
+    int CinP = 0;      // channel count of the input records
+    int CoutS = 0;     // padded output-channel count of the packed weights
+    int act = FVC_ACT_NONE;
+    float* w_raw = nullptr;  // device copy of the reference-layout weight
+    float* bias = nullptr;   // device [Cout]
+    bool have_w = false, have_b = false;
+    SimtWeights simt;
+    TcPlan* tc = nullptr;
+};
+
+struct GdnRt {
+    std::string name;
+    int C = 64, inverse = 0;
+    float *beta_raw = nullptr, *gamma_raw = nullptr, *beta_eff = nullptr, *gamma_eff = nullptr;
+    bool have_b = false, have_g = false;
+};
+
+struct BitEstRt {
+    std::string name;
+    int C = 0;
+    float* p[11] = {nullptr};
+    bool have[11] = {false};
+};
+
+static int pad_c(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : 128); }
+
+}  // namespace fvc
+
+using namespace fvc;
+
+struct fvc_ctx {
+    int B, H, W, levels, impl;
+    std::vector<void*> allocs;
+    std::map<std::string, ConvRt> conv;
+    std::map<std::string, GdnRt> gdn;
+    BitEstRt be_z, be_mv;
+    int64_t launches = 0;
+    bool profile = false;
+    double last_conv_seconds = -1.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
+    size_t conv_event_used = 0;
+
+    // ---- buffers ---------------------------------------------------------------------------
+    std::vector<float*> pyr1, pyr2;                 // planar pyramids, scale 1..levels-1 (scale 0 = user ptr)
+    std::vector<ActT> sx, sa1, sa2, sa3, sa4;       // per SpyNet level
+    std::vector<float*> sflow_up, sflow;            // fp32 NHWC2
+    ActT estmv_act;                                  // parity layout, input of mvEncoder.conv1
+    ActT e[8];                                       // mvEncoder activations e[1..7]
+    float* mvfeature = nullptr;                      // fp32 NHWC128
+    ActT quant_mv;
+    ActT d[8];                                       // mvDecoder activations d[1..7]
+    float* mv_hat = nullptr;                         // fp32 NHWC2
+    float* warpframe = nullptr;                      // planar
+    ActT xmc;
+    ActT wf, wt0, wc0, wc0p, wc0p_r, wt1, wc1, wc1p, wc1p_r, wt2, wc2, wc2_r, wt3, wc3, wc3u, wc3u_r, wt4, wc4,
+        wc4u, wc4u_r, wt5, wc5;
+    float* wres = nullptr;                           // fp32 NHWC3
+    float* prediction = nullptr;                     // planar
+    ActT residual;                                   // parity
+    ActT r_raw[3], r[3];                             // resEncoder (raw only for the SIMT engine)
+    float* feature = nullptr;                        // fp32 NHWC96
+    ActT featabs;
+    ActT p1, p2;
+    float* z = nullptr;                              // fp32 NHWC64
+    ActT z_hat;
+    ActT s1, s2;
+    float* sigma = nullptr;                          // fp32 NHWC96
+    ActT feat_hat;
+    ActT g_raw[3], g[3];
+    float* recon_res = nullptr;                      // fp32 NHWC3
+    float* loss_partials = nullptr;
+    float* bits_partials = nullptr;
+    int* bits_counts = nullptr;                      // device [3]
+    float* scalars = nullptr;                        // device [7] (internal copy)
+    float *stage_cur = nullptr, *stage_ref = nullptr, *stage_rec = nullptr;  // GOP driver staging
+    int stage_G = 0;
+    float* stage_frames = nullptr;
+    float* stage_scalars = nullptr;
+
+    template <typename T>
+    int alloc(T** p, size_t bytes) {
+        void* q = nullptr;
+        FVC_CUDA(cudaMalloc(&q, bytes ? bytes : 16));
+        allocs.push_back(q);
+        *p = reinterpret_cast<T*>(q);
+        return 0;
+    }
+    int alloc_act(ActT* t, int h, int w, int Cp, int parity) {
+        t->B = B; t->H = h; t->W = w; t->Cp = Cp; t->parity = parity;
+        return alloc(&t->p, act_bytes(B, h, w, Cp));
+    }
+};
+
+namespace fvc {
+
+static void add_conv(fvc_ctx* c, const std::string& name, int Cin, int Cout, int k, int stride, int transposed,
+                     int act, int CinP) {
+    ConvRt r;
+    r.name = name;
+    make_conv_layer(r.L, Cin, Cout, k, stride, transposed);
+    r.CinP = CinP;
+    r.CoutS = std::max(pad_c(Cout), 32);
+    r.act = act;
+    c->conv[name] = r;
+}
+
+static int build_layers(fvc_ctx* c) {
+    char buf[128];
+    const int sp[5][2] = {{8, 32}, {32, 64}, {64, 32}, {32, 16}, {16, 2}};
+    for (int l = 0; l < c->levels; ++l)
+        for (int i = 0; i < 5; ++i) {
+            snprintf(buf, sizeof(buf), "opticFlow.moduleBasic.%d.conv%d", l, i + 1);
+            add_conv(c, buf, sp[i][0], sp[i][1], 7, 1, 0, i < 4 ? FVC_ACT_RELU : FVC_ACT_NONE, pad_c(sp[i][0]));
+        }
+    for (int i = 1; i <= 8; ++i) {
+        snprintf(buf, sizeof(buf), "mvEncoder.conv%d", i);
+        add_conv(c, buf, i == 1 ? 2 : 128, 128, 3, (i & 1) ? 2 : 1, 0, i < 8 ? FVC_ACT_LRELU01 : FVC_ACT_NONE,
+                 i == 1 ? 32 : 128);
+    }
+    for (int i = 1; i <= 8; ++i) {
+        snprintf(buf, sizeof(buf), "mvDecoder.deconv%d", i);
+        if (i & 1) add_conv(c, buf, 128, 128, 3, 2, 1, FVC_ACT_LRELU01, 128);
+        else add_conv(c, buf, 128, i == 8 ? 2 : 128, 3, 1, 0, i < 8 ? FVC_ACT_LRELU01 : FVC_ACT_NONE, 128);
+    }
+    add_conv(c, "warpnet.feature_ext", 6, 64, 3, 1, 0, FVC_ACT_RELU, 32);
+    for (int i = 0; i < 6; ++i) {
+        snprintf(buf, sizeof(buf), "warpnet.conv%d.conv1", i);
+        add_conv(c, buf, 64, 64, 3, 1, 0, FVC_ACT_RELU, 64);  // relu2 fused into conv1's epilogue
+        snprintf(buf, sizeof(buf), "warpnet.conv%d.conv2", i);
+        add_conv(c, buf, 64, 64, 3, 1, 0, FVC_ACT_NONE, 64);
+    }
+    add_conv(c, "warpnet.conv6", 64, 3, 3, 1, 0, FVC_ACT_NONE, 64);
+    add_conv(c, "resEncoder.conv1", 3, 64, 5, 2, 0, FVC_ACT_NONE, 32);
+    add_conv(c, "resEncoder.conv2", 64, 64, 5, 2, 0, FVC_ACT_NONE, 64);
+    add_conv(c, "resEncoder.conv3", 64, 64, 5, 2, 0, FVC_ACT_NONE, 64);
+    add_conv(c, "resEncoder.conv4", 64, 96, 5, 2, 0, FVC_ACT_NONE, 64);
+    add_conv(c, "resDecoder.deconv1", 96, 64, 5, 2, 1, FVC_ACT_NONE, 128);
+    add_conv(c, "resDecoder.deconv2", 64, 64, 5, 2, 1, FVC_ACT_NONE, 64);
+    add_conv(c, "resDecoder.deconv3", 64, 64, 5, 2, 1, FVC_ACT_NONE, 64);
+    add_conv(c, "resDecoder.deconv4", 64, 3, 5, 2, 1, FVC_ACT_NONE, 64);
+    add_conv(c, "respriorEncoder.conv1", 96, 64, 3, 1, 0, FVC_ACT_RELU, 128);
+    add_conv(c, "respriorEncoder.conv2", 64, 64, 5, 2, 0, FVC_ACT_RELU, 64);
+    add_conv(c, "respriorEncoder.conv3", 64, 64, 5, 2, 0, FVC_ACT_NONE, 64);
+    add_conv(c, "respriorDecoder.deconv1", 64, 64, 5, 2, 1, FVC_ACT_RELU, 64);
+    add_conv(c, "respriorDecoder.deconv2", 64, 64, 5, 2, 1, FVC_ACT_RELU, 64);
+    add_conv(c, "respriorDecoder.deconv3", 64, 96, 3, 1, 1, FVC_ACT_EXP, 64);
+    for (int i = 1; i <= 3; ++i) {
+        GdnRt g;
+        snprintf(buf, sizeof(buf), "resEncoder.gdn%d", i);
+        g.name = buf; g.inverse = 0;
+        c->gdn[buf] = g;
+        snprintf(buf, sizeof(buf), "resDecoder.igdn%d", i);
+        g.name = buf; g.inverse = 1;
+        c->gdn[buf] = g;
+    }
+    c->be_z.name = "bitEstimator_z"; c->be_z.C = 64;
+    c->be_mv.name = "bitEstimator_mv"; c->be_mv.C = 128;
+    // device storage for parameters
+    for (auto& kv : c->conv) {
+        ConvRt& r = kv.second;
+        size_t nw = (size_t)r.L.Cin * r.L.Cout * r.L.k * r.L.k;
+        if (c->alloc(&r.w_raw, nw * sizeof(float))) return FVC_ERR_CUDA;
+        if (c->alloc(&r.bias, (size_t)r.L.Cout * sizeof(float))) return FVC_ERR_CUDA;
+    }
+    for (auto& kv : c->gdn) {
+        GdnRt& g = kv.second;
+        if (c->alloc(&g.beta_raw, 64 * 4) || c->alloc(&g.gamma_raw, 64 * 64 * 4) || c->alloc(&g.beta_eff, 64 * 4) ||
+            c->alloc(&g.gamma_eff, 64 * 64 * 4))
+            return FVC_ERR_CUDA;
+    }
+    for (BitEstRt* be : {&c->be_z, &c->be_mv})
+        for (int i = 0; i < 11; ++i)
+            if (c->alloc(&be->p[i], (size_t)be->C * 4)) return FVC_ERR_CUDA;
+    return 0;
+}
+
+static int build_buffers(fvc_ctx* c) {
+    const int B = c->B, H = c->H, W = c->W, L = c->levels;
+#define A(expr) do { if (expr) return FVC_ERR_CUDA; } while (0)
+    c->pyr1.assign(L, nullptr);
+    c->pyr2.assign(L, nullptr);
+    for (int s = 1; s < L; ++s) {
+        A(c->alloc(&c->pyr1[s], (size_t)B * 3 * (H >> s) * (W >> s) * 4));
+        A(c->alloc(&c->pyr2[s], (size_t)B * 3 * (H >> s) * (W >> s) * 4));
+    }
+    c->sx.resize(L); c->sa1.resize(L); c->sa2.resize(L); c->sa3.resize(L); c->sa4.resize(L);
+    c->sflow_up.assign(L, nullptr); c->sflow.assign(L, nullptr);
+    for (int i = 0; i < L; ++i) {
+        int h = H >> (L - 1 - i), w = W >> (L - 1 - i);
+        A(c->alloc_act(&c->sx[i], h, w, 32, 0));
+        A(c->alloc_act(&c->sa1[i], h, w, 32, 0));
+        A(c->alloc_act(&c->sa2[i], h, w, 64, 0));
+        A(c->alloc_act(&c->sa3[i], h, w, 32, 0));
+        A(c->alloc_act(&c->sa4[i], h, w, 32, 0));
+        A(c->alloc(&c->sflow_up[i], (size_t)B * h * w * 2 * 4));
+        A(c->alloc(&c->sflow[i], (size_t)B * h * w * 2 * 4));
+    }
+    A(c->alloc_act(&c->estmv_act, H, W, 32, 1));
+    // mvEncoder: conv i output at H >> ceil(i/2); parity layout when the consumer is a stride-2 conv
+    for (int i = 1; i <= 7; ++i) {
+        int sh = (i + 1) / 2;
+        A(c->alloc_act(&c->e[i], H >> sh, W >> sh, 128, (i % 2 == 0) ? 1 : 0));
+    }
+    A(c->alloc(&c->mvfeature, (size_t)B * (H / 16) * (W / 16) * 128 * 4));
+    A(c->alloc_act(&c->quant_mv, H / 16, W / 16, 128, 0));
+    for (int i = 1; i <= 7; ++i) {
+        int sh = 4 - (i + 1) / 2;  // deconv1 -> H/8, deconv2 -> H/8, deconv3 -> H/4, ...
+        A(c->alloc_act(&c->d[i], H >> sh, W >> sh, 128, 0));
+    }
+    A(c->alloc(&c->mv_hat, (size_t)B * H * W * 2 * 4));
+    A(c->alloc(&c->warpframe, (size_t)B * 3 * H * W * 4));
+    A(c->alloc_act(&c->xmc, H, W, 32, 0));
+    A(c->alloc_act(&c->wf, H, W, 64, 0));
+    A(c->alloc_act(&c->wt0, H, W, 64, 0));
+    A(c->alloc_act(&c->wc0, H, W, 64, 0));
+    A(c->alloc_act(&c->wc0p, H / 2, W / 2, 64, 0));
+    A(c->alloc_act(&c->wc0p_r, H / 2, W / 2, 64, 0));
+    A(c->alloc_act(&c->wt1, H / 2, W / 2, 64, 0));
+    A(c->alloc_act(&c->wc1, H / 2, W / 2, 64, 0));
+    A(c->alloc_act(&c->wc1p, H / 4, W / 4, 64, 0));
+    A(c->alloc_act(&c->wc1p_r, H / 4, W / 4, 64, 0));
+    A(c->alloc_act(&c->wt2, H / 4, W / 4, 64, 0));
+    A(c->alloc_act(&c->wc2, H / 4, W / 4, 64, 0));
+    A(c->alloc_act(&c->wc2_r, H / 4, W / 4, 64, 0));
+    A(c->alloc_act(&c->wt3, H / 4, W / 4, 64, 0));
+    A(c->alloc_act(&c->wc3, H / 4, W / 4, 64, 0));
+    A(c->alloc_act(&c->wc3u, H / 2, W / 2, 64, 0));
+    A(c->alloc_act(&c->wc3u_r, H / 2, W / 2, 64, 0));
+    A(c->alloc_act(&c->wt4, H / 2, W / 2, 64, 0));
+    A(c->alloc_act(&c->wc4, H / 2, W / 2, 64, 0));
+    A(c->alloc_act(&c->wc4u, H, W, 64, 0));
+    A(c->alloc_act(&c->wc4u_r, H, W, 64, 0));
+    A(c->alloc_act(&c->wt5, H, W, 64, 0));
+    A(c->alloc_act(&c->wc5, H, W, 64, 0));
+    A(c->alloc(&c->wres, (size_t)B * H * W * 3 * 4));
+    A(c->alloc(&c->prediction, (size_t)B * 3 * H * W * 4));
+    A(c->alloc_act(&c->residual, H, W, 32, 1));
+    for (int i = 0; i < 3; ++i) {
+        A(c->alloc_act(&c->r_raw[i], H >> (i + 1), W >> (i + 1), 64, 0));
+        A(c->alloc_act(&c->r[i], H >> (i + 1), W >> (i + 1), 64, 1));
+    }
+    A(c->alloc(&c->feature, (size_t)B * (H / 16) * (W / 16) * 96 * 4));
+    A(c->alloc_act(&c->featabs, H / 16, W / 16, 128, 0));
+    A(c->alloc_act(&c->p1, H / 16, W / 16, 64, 1));
+    A(c->alloc_act(&c->p2, H / 32, W / 32, 64, 1));
+    A(c->alloc(&c->z, (size_t)B * (H / 64) * (W / 64) * 64 * 4));
+    A(c->alloc_act(&c->z_hat, H / 64, W / 64, 64, 0));
+    A(c->alloc_act(&c->s1, H / 32, W / 32, 64, 0));
+    A(c->alloc_act(&c->s2, H / 16, W / 16, 64, 0));
+    A(c->alloc(&c->sigma, (size_t)B * (H / 16) * (W / 16) * 96 * 4));
+    A(c->alloc_act(&c->feat_hat, H / 16, W / 16, 128, 0));
+    for (int i = 0; i < 3; ++i) {
+        A(c->alloc_act(&c->g_raw[i], H >> (3 - i), W >> (3 - i), 64, 0));
+        A(c->alloc_act(&c->g[i], H >> (3 - i), W >> (3 - i), 64, 0));
+    }
+    A(c->alloc(&c->recon_res, (size_t)B * H * W * 3 * 4));
+    A(c->alloc(&c->loss_partials, (size_t)148 * 8 * 3 * 4));
+    A(c->alloc(&c->bits_partials, (size_t)bits_max_blocks() * 3 * 4));
+    A(c->alloc(&c->bits_counts, 3 * sizeof(int)));
+    A(c->alloc(&c->scalars, 8 * 4));
+#undef A
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+static ActT no_act() {
+    ActT t;
+    t.p = nullptr; t.B = t.H = t.W = t.Cp = t.parity = 0;
+    return t;
+}
+static Epilogue make_ep(const ConvRt& r) {
+    Epilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.bias = r.bias;
+    ep.act = r.act;
+    ep.res_act = no_act();
+    ep.out_act = no_act();
+    ep.out_act_relu = no_act();
+    return ep;
+}
+
+static int run_conv(fvc_ctx* c, const std::string& name, ActT in, int Hout, int Wout, Epilogue ep,
+                    cudaStream_t s) {
+    auto it = c->conv.find(name);
+    if (it == c->conv.end()) {
+        set_error("unknown layer %s", name.c_str());
+        return FVC_ERR_STATE;
+    }
+    ConvRt& r = it->second;
+    if (!r.have_w || !r.have_b) {
+        set_error("parameters of %s not set", name.c_str());
+        return FVC_ERR_STATE;
+    }
+    ep.bias = r.bias;
+    ep.act = r.act;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) {
+        if (c->conv_event_used == c->conv_events.size()) {
+            cudaEvent_t a, b;
+            FVC_CUDA(cudaEventCreate(&a));
+            FVC_CUDA(cudaEventCreate(&b));
+            c->conv_events.push_back({a, b});
+        }
+        e0 = c->conv_events[c->conv_event_used].first;
+        e1 = c->conv_events[c->conv_event_used].second;
+        c->conv_event_used++;
+        FVC_CUDA(cudaEventRecord(e0, s));
+    }
+    int rc;
+    if (c->impl == FVC_IMPL_TC && tc_supported(r.L, r.CinP)) {
+        if (!r.tc) {
+            rc = tc_plan_create(r.L, r.w_raw, in, Hout, Wout, ep, &r.tc, s);
+            if (rc) return rc;
+        }
+        rc = tc_plan_launch(r.tc, s);
+    } else {
+        if (ep.gdn_beta) {
+            set_error("fused GDN requested on the SIMT engine (%s)", name.c_str());
+            return FVC_ERR_STATE;
+        }
+        rc = launch_conv_simt(r.L, r.simt, in, Hout, Wout, ep, s);
+    }
+    if (rc) return rc;
+    if (c->profile) FVC_CUDA(cudaEventRecord(e1, s));
+    return 0;
+}
+
+// conv followed by (I)GDN: fused in the tcgen05 engine, two kernels in the SIMT engine
+static int run_conv_gdn(fvc_ctx* c, const std::string& conv, const std::string& gdn, ActT in, ActT raw, ActT out,
+                        cudaStream_t s) {
+    GdnRt& g = c->gdn[gdn];
+    if (!g.have_b || !g.have_g) {
+        set_error("parameters of %s not set", gdn.c_str());
+        return FVC_ERR_STATE;
+    }
+    ConvRt& r = c->conv[conv];
+    Epilogue ep = make_ep(r);
+    if (c->impl == FVC_IMPL_TC && tc_supported(r.L, r.CinP)) {
+        ep.out_act = out;
+        ep.gdn_beta = g.beta_eff;
+        ep.gdn_gamma = g.gamma_eff;
+        ep.gdn_inverse = g.inverse;
+        return run_conv(c, conv, in, out.H, out.W, ep, s);
+    }
+    ep.out_act = raw;
+    int rc = run_conv(c, conv, in, out.H, out.W, ep, s);
+    if (rc) return rc;
+    return launch_gdn_act(raw, g.C, g.beta_eff, g.gamma_eff, g.inverse, out, s);
+}
+
+static int res_block(fvc_ctx* c, int idx, ActT x_relu, ActT x_skip, ActT tmp, ActT out, ActT out_relu,
+                     cudaStream_t s) {
+    char n1[64], n2[64];
+    snprintf(n1, sizeof(n1), "warpnet.conv%d.conv1", idx);
+    snprintf(n2, sizeof(n2), "warpnet.conv%d.conv2", idx);
+    Epilogue ep = make_ep(c->conv[n1]);
+    ep.out_act = tmp;  // relu(conv1(relu(x)))
+    int rc = run_conv(c, n1, x_relu, tmp.H, tmp.W, ep, s);
+    if (rc) return rc;
+    ep = make_ep(c->conv[n2]);
+    ep.res_act = x_skip;
+    ep.out_act = out;
+    ep.out_act_relu = out_relu;
+    return run_conv(c, n2, tmp, out.H, out.W, ep, s);
+}
+
+static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_out, float* scalars_out,
+                   cudaStream_t s) {
+    const int B = c->B, H = c->H, W = c->W, L = c->levels;
+    char nm[96];
+    int rc;
+    c->conv_event_used = 0;
+#define R(expr) do { rc = (expr); if (rc) return rc; } while (0)
+    // ---- SpyNet (endecoder.py:337-356) --------------------------------------------------------
+    const float* p1 = cur;
+    const float* p2 = ref;
+    std::vector<const float*> im1(L), im2(L);
+    im1[0] = cur; im2[0] = ref;
+    for (int sc = 1; sc < L; ++sc) {
+        R(launch_avg_pool2_planar(im1[sc - 1], c->pyr1[sc], B * 3, H >> (sc - 1), W >> (sc - 1), s));
+        R(launch_avg_pool2_planar(im2[sc - 1], c->pyr2[sc], B * 3, H >> (sc - 1), W >> (sc - 1), s));
+        im1[sc] = c->pyr1[sc];
+        im2[sc] = c->pyr2[sc];
+    }
+    (void)p1; (void)p2;
+    for (int i = 0; i < L; ++i) {
+        int sc = L - 1 - i;
+        int h = H >> sc, w = W >> sc;
+        R(launch_spynet_prep(im1[sc], im2[sc], i == 0 ? nullptr : c->sflow[i - 1], c->sx[i], c->sflow_up[i], s));
+        ActT chain_in[5] = {c->sx[i], c->sa1[i], c->sa2[i], c->sa3[i], c->sa4[i]};
+        for (int k = 0; k < 5; ++k) {
+            snprintf(nm, sizeof(nm), "opticFlow.moduleBasic.%d.conv%d", i, k + 1);
+            Epilogue ep = make_ep(c->conv[nm]);
+            if (k < 4) {
+                ep.out_act = chain_in[k + 1];
+            } else {
+                ep.res_f32 = c->sflow_up[i];
+                ep.out_f32 = c->sflow[i];
+                if (i == L - 1) ep.out_act = c->estmv_act;
+            }
+            R(run_conv(c, nm, chain_in[k], h, w, ep, s));
+        }
+    }
+    // ---- mvEncoder (analysis_mv.py:58-66) ----------------------------------------------------
+    {
+        ActT in = c->estmv_act;
+        for (int i = 1; i <= 8; ++i) {
+            snprintf(nm, sizeof(nm), "mvEncoder.conv%d", i);
+            Epilogue ep = make_ep(c->conv[nm]);
+            int sh = (i + 1) / 2;
+            if (i < 8) ep.out_act = c->e[i];
+            else ep.out_f32 = c->mvfeature;
+            R(run_conv(c, nm, in, H >> sh, W >> sh, ep, s));
+            if (i < 8) in = c->e[i];
+        }
+    }
+    int nb_mv = 0, nb_z = 0, nb_f = 0;
+    const int maxb = bits_max_blocks();
+    {
+        FactorizedParams prm;
+        for (int i = 0; i < 11; ++i) prm.p[i] = c->be_mv.p[i];
+        R(launch_quant_bits_factorized(c->mvfeature, 1, B, 128, (H / 16) * (W / 16), prm, nullptr, c->quant_mv,
+                                       c->bits_partials + 2 * maxb, &nb_mv, s));
+    }
+    // ---- mvDecoder (synthesis_mv.py:71-79) ---------------------------------------------------
+    {
+        ActT in = c->quant_mv;
+        for (int i = 1; i <= 8; ++i) {
+            snprintf(nm, sizeof(nm), "mvDecoder.deconv%d", i);
+            Epilogue ep = make_ep(c->conv[nm]);
+            int sh = 4 - (i + 1) / 2;
+            if (i < 8) ep.out_act = c->d[i];
+            else ep.out_f32 = c->mv_hat;
+            R(run_conv(c, nm, in, H >> sh, W >> sh, ep, s));
+            if (i < 8) in = c->d[i];
+        }
+    }
+    // ---- motion compensation (net.py:64-68, endecoder.py:282-296) ------------------------------
+    R(launch_mc_prep(ref, c->mv_hat, c->warpframe, c->xmc, s));
+    {
+        Epilogue ep = make_ep(c->conv["warpnet.feature_ext"]);
+        ep.out_act = c->wf;
+        R(run_conv(c, "warpnet.feature_ext", c->xmc, H, W, ep, s));
+    }
+    R(res_block(c, 0, c->wf, c->wf, c->wt0, c->wc0, no_act(), s));          // f >= 0: relu(f) == f
+    R(launch_pool_act(c->wc0, c->wc0p, c->wc0p_r, s));
+    R(res_block(c, 1, c->wc0p_r, c->wc0p, c->wt1, c->wc1, no_act(), s));
+    R(launch_pool_act(c->wc1, c->wc1p, c->wc1p_r, s));
+    R(res_block(c, 2, c->wc1p_r, c->wc1p, c->wt2, c->wc2, c->wc2_r, s));
+    R(res_block(c, 3, c->wc2_r, c->wc2, c->wt3, c->wc3, no_act(), s));
+    R(launch_upadd_act(c->wc3, c->wc1, c->wc3u, c->wc3u_r, s));
+    R(res_block(c, 4, c->wc3u_r, c->wc3u, c->wt4, c->wc4, no_act(), s));
+    R(launch_upadd_act(c->wc4, c->wc0, c->wc4u, c->wc4u_r, s));
+    R(res_block(c, 5, c->wc4u_r, c->wc4u, c->wt5, c->wc5, no_act(), s));
+    {
+        Epilogue ep = make_ep(c->conv["warpnet.conv6"]);
+        ep.out_f32 = c->wres;
+        R(run_conv(c, "warpnet.conv6", c->wc5, H, W, ep, s));
+    }
+    R(launch_mc_finish(c->wres, c->warpframe, cur, c->prediction, c->residual, s));
+    // ---- residual encoder (analysis.py:44-48) ---------------------------------------------------
+    R(run_conv_gdn(c, "resEncoder.conv1", "resEncoder.gdn1", c->residual, c->r_raw[0], c->r[0], s));
+    R(run_conv_gdn(c, "resEncoder.conv2", "resEncoder.gdn2", c->r[0], c->r_raw[1], c->r[1], s));
+    R(run_conv_gdn(c, "resEncoder.conv3", "resEncoder.gdn3", c->r[1], c->r_raw[2], c->r[2], s));
+    {
+        Epilogue ep = make_ep(c->conv["resEncoder.conv4"]);
+        ep.out_f32 = c->feature;
+        R(run_conv(c, "resEncoder.conv4", c->r[2], H / 16, W / 16, ep, s));
+    }
+    // ---- hyper-prior (analysis_prior.py:40-56, synthesis_prior.py:42-58) ------------------------
+    R(launch_nhwc_to_act(c->feature, c->featabs, 96, 1, s));
+    {
+        Epilogue ep = make_ep(c->conv["respriorEncoder.conv1"]);
+        ep.out_act = c->p1;
+        R(run_conv(c, "respriorEncoder.conv1", c->featabs, H / 16, W / 16, ep, s));
+        ep = make_ep(c->conv["respriorEncoder.conv2"]);
+        ep.out_act = c->p2;
+        R(run_conv(c, "respriorEncoder.conv2", c->p1, H / 32, W / 32, ep, s));
+        ep = make_ep(c->conv["respriorEncoder.conv3"]);
+        ep.out_f32 = c->z;
+        R(run_conv(c, "respriorEncoder.conv3", c->p2, H / 64, W / 64, ep, s));
+    }
+    {
+        FactorizedParams prm;
+        for (int i = 0; i < 11; ++i) prm.p[i] = c->be_z.p[i];
+        R(launch_quant_bits_factorized(c->z, 1, B, 64, (H / 64) * (W / 64), prm, nullptr, c->z_hat,
+                                       c->bits_partials + 1 * maxb, &nb_z, s));
+    }
+    {
+        Epilogue ep = make_ep(c->conv["respriorDecoder.deconv1"]);
+        ep.out_act = c->s1;
+        R(run_conv(c, "respriorDecoder.deconv1", c->z_hat, H / 32, W / 32, ep, s));
+        ep = make_ep(c->conv["respriorDecoder.deconv2"]);
+        ep.out_act = c->s2;
+        R(run_conv(c, "respriorDecoder.deconv2", c->s1, H / 16, W / 16, ep, s));
+        ep = make_ep(c->conv["respriorDecoder.deconv3"]);
+        ep.out_f32 = c->sigma;
+        R(run_conv(c, "respriorDecoder.deconv3", c->s2, H / 16, W / 16, ep, s));
+    }
+    R(launch_quant_bits_laplace(c->feature, c->sigma, (int64_t)B * (H / 16) * (W / 16) * 96, 96, nullptr,
+                                c->feat_hat, c->bits_partials + 0 * maxb, &nb_f, s));
+    // ---- residual decoder (synthesis.py:54-58) --------------------------------------------------
+    R(run_conv_gdn(c, "resDecoder.deconv1", "resDecoder.igdn1", c->feat_hat, c->g_raw[0], c->g[0], s));
+    R(run_conv_gdn(c, "resDecoder.deconv2", "resDecoder.igdn2", c->g[0], c->g_raw[1], c->g[1], s));
+    R(run_conv_gdn(c, "resDecoder.deconv3", "resDecoder.igdn3", c->g[1], c->g_raw[2], c->g[2], s));
+    {
+        Epilogue ep = make_ep(c->conv["resDecoder.deconv4"]);
+        ep.out_f32 = c->recon_res;
+        R(run_conv(c, "resDecoder.deconv4", c->g[2], H, W, ep, s));
+    }
+    // ---- reconstruction, distortion, rate (net.py:103-116, 207-217) -------------------------------
+    int nloss = 0;
+    R(launch_recon_losses(cur, c->prediction, c->warpframe, c->recon_res, 1, B, H * W, recon_out, c->loss_partials,
+                          &nloss, s));
+    R(launch_reduce_partials(c->loss_partials, nloss, 3, 1.0 / ((double)B * 3 * H * W), c->scalars, s));
+    R(launch_reduce_partials(c->bits_partials + 0 * maxb, nb_f, 1, 1.0, c->scalars + 3, s));
+    R(launch_reduce_partials(c->bits_partials + 1 * maxb, nb_z, 1, 1.0, c->scalars + 4, s));
+    R(launch_reduce_partials(c->bits_partials + 2 * maxb, nb_mv, 1, 1.0, c->scalars + 5, s));
+    R(launch_finalize_scalars(c->scalars, (float)((double)B * H * W), scalars_out, s));
+#undef R
+    return 0;
+}
+
+}  // namespace fvc
+
+// ==================================================================================================
+// C ABI: context
+// ==================================================================================================
+extern "C" {
+
+const char* fvc_last_error(void) { return fvc::g_err.c_str(); }
+int fvc_version(void) { return 100; }
+
+fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl) {
+    if (B < 1 || H < 64 || W < 64 || (H % 64) || (W % 64) || levels < 1 || levels > 6 ||
+        (impl != FVC_IMPL_SIMT && impl != FVC_IMPL_TC)) {
+        set_error("fvc_ctx_create: bad geometry B=%d H=%d W=%d levels=%d impl=%d (H, W must be multiples of 64)", B,
+                  H, W, levels, impl);
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("fvc_ctx_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return nullptr;
+    }
+    fvc_ctx* c = new fvc_ctx();
+    c->B = B; c->H = H; c->W = W; c->levels = levels; c->impl = impl;
+    const char* prof = getenv("FVC_PROFILE");
+    c->profile = prof && prof[0] == '1';
+    if (build_layers(c) || build_buffers(c)) {
+        fvc_ctx_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void fvc_ctx_destroy(fvc_ctx* c) {
+    if (!c) return;
+    cudaDeviceSynchronize();
+    for (auto& kv : c->conv) {
+        if (kv.second.simt.w) cudaFree(kv.second.simt.w);
+        if (kv.second.tc) tc_plan_destroy(kv.second.tc);
+    }
+    for (void* p : c->allocs) cudaFree(p);
+    for (auto& ev : c->conv_events) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    if (c->stage_frames) cudaFree(c->stage_frames);
+    if (c->stage_rec) cudaFree(c->stage_rec);
+    if (c->stage_scalars) cudaFree(c->stage_scalars);
+    delete c;
+}
+
+int fvc_ctx_set_param(fvc_ctx* c, const char* key_c, const float* data, int64_t numel, void* stream) {
+    FVC_ARG(c && key_c && data);
+    cudaStream_t s = (cudaStream_t)stream;
+    std::string key(key_c);
+    size_t dot = key.rfind('.');
+    FVC_ARG(dot != std::string::npos);
+    std::string mod = key.substr(0, dot), leaf = key.substr(dot + 1);
+    auto ci = c->conv.find(mod);
+    if (ci != c->conv.end()) {
+        ConvRt& r = ci->second;
+        if (leaf == "weight") {
+            int64_t n = (int64_t)r.L.Cin * r.L.Cout * r.L.k * r.L.k;
+            if (numel != n) { set_error("%s: expected %lld elements, got %lld", key_c, (long long)n, (long long)numel); return FVC_ERR_ARG; }
+            FVC_CUDA(cudaMemcpyAsync(r.w_raw, data, n * 4, cudaMemcpyDeviceToDevice, s));
+            int rc = simt_pack_weights(r.L, r.w_raw, r.CinP, r.CoutS, &r.simt, s);
+            if (rc) return rc;
+            if (r.tc) { tc_plan_destroy(r.tc); r.tc = nullptr; }
+            r.have_w = true;
+            return 0;
+        }
+        if (leaf == "bias") {
+            if (numel != r.L.Cout) { set_error("%s: expected %d elements", key_c, r.L.Cout); return FVC_ERR_ARG; }
+            FVC_CUDA(cudaMemcpyAsync(r.bias, data, numel * 4, cudaMemcpyDeviceToDevice, s));
+            r.have_b = true;
+            return 0;
+        }
+    }
+    auto gi = c->gdn.find(mod);
+    if (gi != c->gdn.end()) {
+        GdnRt& g = gi->second;
+        if (leaf == "beta") {
+            FVC_ARG(numel == g.C);
+            FVC_CUDA(cudaMemcpyAsync(g.beta_raw, data, numel * 4, cudaMemcpyDeviceToDevice, s));
+            g.have_b = true;
+        } else if (leaf == "gamma") {
+            FVC_ARG(numel == (int64_t)g.C * g.C);
+            FVC_CUDA(cudaMemcpyAsync(g.gamma_raw, data, numel * 4, cudaMemcpyDeviceToDevice, s));
+            g.have_g = true;
+        } else {
+            set_error("unknown parameter %s", key_c);
+            return FVC_ERR_ARG;
+        }
+        if (g.have_b && g.have_g) return launch_gdn_reparam(g.beta_raw, g.gamma_raw, g.beta_eff, g.gamma_eff, g.C, s);
+        return 0;
+    }
+    // bitEstimator_{z,mv}.f{1..4}.{h,b,a}
+    for (BitEstRt* be : {&c->be_z, &c->be_mv}) {
+        if (key.compare(0, be->name.size() + 1, be->name + ".") == 0) {
+            std::string rest = key.substr(be->name.size() + 1);  // f1.h
+            if (rest.size() == 4 && rest[0] == 'f' && rest[2] == '.') {
+                int fi = rest[1] - '1';
+                int pi = rest[3] == 'h' ? 0 : (rest[3] == 'b' ? 1 : (rest[3] == 'a' ? 2 : -1));
+                if (fi >= 0 && fi < 4 && pi >= 0 && !(fi == 3 && pi == 2)) {
+                    FVC_ARG(numel == be->C);
+                    int idx = fi * 3 + pi;
+                    FVC_CUDA(cudaMemcpyAsync(be->p[idx], data, numel * 4, cudaMemcpyDeviceToDevice, s));
+                    be->have[idx] = true;
+                    return 0;
+                }
+            }
+        }
+    }
+    set_error("unknown parameter %s", key_c);
+    return FVC_ERR_ARG;
+}
+
+int fvc_ctx_missing_params(fvc_ctx* c) {
+    if (!c) return -1;
+    int m = 0;
+    for (auto& kv : c->conv) m += (!kv.second.have_w) + (!kv.second.have_b);
+    for (auto& kv : c->gdn) m += (!kv.second.have_b) + (!kv.second.have_g);
+    for (BitEstRt* be : {&c->be_z, &c->be_mv})
+        for (int i = 0; i < 11; ++i) m += !be->have[i];
+    return m;
+}
+
+int fvc_pframe_forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_out, float* scalars_out,
+                       void* stream) {
+    FVC_ARG(c && cur && ref && recon_out && scalars_out);
+    if (fvc_ctx_missing_params(c) != 0) {
+        set_error("fvc_pframe_forward: %d parameters not set", fvc_ctx_missing_params(c));
+        return FVC_ERR_STATE;
+    }
+    int64_t before = g_launch_count;
+    int rc = forward(c, cur, ref, recon_out, scalars_out, (cudaStream_t)stream);
+    c->launches += g_launch_count - before;
+    if (rc == 0 && c->profile) {
+        FVC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        double tot = 0;
+        for (size_t i = 0; i < c->conv_event_used; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->conv_events[i].first, c->conv_events[i].second);
+            tot += ms * 1e-3;
+        }
+        c->last_conv_seconds = tot;
+    }
+    return rc;
+}
+
+int64_t fvc_ctx_launch_count(fvc_ctx* c) { return c ? c->launches : -1; }
+double fvc_ctx_last_conv_seconds(fvc_ctx* c) { return c ? c->last_conv_seconds : -1.0; }
+
+int64_t fvc_ctx_get_tensor(fvc_ctx* c, const char* name_c, float* out, int64_t capacity, void* stream) {
+    if (!c || !name_c || !out) { set_error("fvc_ctx_get_tensor: null argument"); return FVC_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    std::string n(name_c);
+    const int B = c->B, H = c->H, W = c->W;
+    const int h16 = H / 16, w16 = W / 16;
+    struct F32 { const float* p; int C, h, w; };
+    std::map<std::string, F32> f32 = {
+        {"estmv", {c->sflow[c->levels - 1], 2, H, W}}, {"mvfeature", {c->mvfeature, 128, h16, w16}},
+        {"mv_hat", {c->mv_hat, 2, H, W}},               {"feature", {c->feature, 96, h16, w16}},
+        {"z", {c->z, 64, H / 64, W / 64}},              {"sigma", {c->sigma, 96, h16, w16}},
+        {"recon_res", {c->recon_res, 3, H, W}},         {"warpnet_res", {c->wres, 3, H, W}}};
+    std::map<std::string, std::pair<ActT, int>> act = {{"quant_mv", {c->quant_mv, 128}},
+                                                       {"z_hat", {c->z_hat, 64}},
+                                                       {"feat_hat", {c->feat_hat, 96}},
+                                                       {"residual", {c->residual, 3}},
+                                                       {"warpnet_c0", {c->wc0, 64}},
+                                                       {"warpnet_c5", {c->wc5, 64}},
+                                                       {"mvenc_e1", {c->e[1], 128}},
+                                                       {"mvdec_d7", {c->d[7], 128}},
+                                                       {"resenc_r0", {c->r[0], 64}},
+                                                       {"resdec_g2", {c->g[2], 64}}};
+    std::map<std::string, const float*> planar = {{"warpframe", c->warpframe}, {"prediction", c->prediction}};
+    auto fi = f32.find(n);
+    if (fi != f32.end()) {
+        int64_t cnt = (int64_t)B * fi->second.C * fi->second.h * fi->second.w;
+        if (cnt > capacity) { set_error("capacity too small"); return FVC_ERR_ARG; }
+        int rc = launch_nhwc_to_nchw(fi->second.p, out, B, fi->second.C, fi->second.h, fi->second.w, s);
+        return rc ? rc : cnt;
+    }
+    auto ai = act.find(n);
+    if (ai != act.end()) {
+        ActT t = ai->second.first;
+        int64_t cnt = (int64_t)B * ai->second.second * t.H * t.W;
+        if (cnt > capacity) { set_error("capacity too small"); return FVC_ERR_ARG; }
+        int rc = launch_act_to_nchw(t, ai->second.second, out, s);
+        return rc ? rc : cnt;
+    }
+    auto pi = planar.find(n);
+    if (pi != planar.end()) {
+        int64_t cnt = (int64_t)B * 3 * H * W;
+        if (cnt > capacity) { set_error("capacity too small"); return FVC_ERR_ARG; }
+        if (cudaMemcpyAsync(out, pi->second, cnt * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return FVC_ERR_CUDA;
+        return cnt;
+    }
+    set_error("unknown tensor %s", name_c);
+    return FVC_ERR_ARG;
+}
+
+int fvc_gop_forward_host(fvc_ctx* c, const float* frames_host, int G, float* recon_host, float* scalars_host,
+                         void* stream) {
+    FVC_ARG(c && frames_host && scalars_host && G >= 2);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t fsz = (size_t)c->B * 3 * c->H * c->W;
+    if (c->stage_G < G) {
+        if (c->stage_frames) cudaFree(c->stage_frames);
+        if (c->stage_rec) cudaFree(c->stage_rec);
+        if (c->stage_scalars) cudaFree(c->stage_scalars);
+        FVC_CUDA(cudaMalloc(&c->stage_frames, fsz * G * 4));
+        FVC_CUDA(cudaMalloc(&c->stage_rec, fsz * (G - 1) * 4));
+        FVC_CUDA(cudaMalloc(&c->stage_scalars, (size_t)(G - 1) * 7 * 4));
+        c->stage_G = G;
+    }
+    FVC_CUDA(cudaMemcpyAsync(c->stage_frames, frames_host, fsz * G * 4, cudaMemcpyHostToDevice, s));
+    const float* prev = c->stage_frames;  // decoded I-frame (models.py:370)
+    for (int i = 1; i < G; ++i) {
+        float* rec = c->stage_rec + (size_t)(i - 1) * fsz;
+        int rc = fvc_pframe_forward(c, c->stage_frames + (size_t)i * fsz, prev, rec, c->stage_scalars + (i - 1) * 7,
+                                    stream);
+        if (rc) return rc;
+        prev = rec;  // x_prev = clipped_recon (models.py:372-375)
+    }
+    if (recon_host)
+        FVC_CUDA(cudaMemcpyAsync(recon_host, c->stage_rec, fsz * (G - 1) * 4, cudaMemcpyDeviceToHost, s));
+    FVC_CUDA(cudaMemcpyAsync(scalars_host, c->stage_scalars, (size_t)(G - 1) * 7 * 4, cudaMemcpyDeviceToHost, s));
+    FVC_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+"""Drop-in ``VideoCompressor`` — mirrors reference DVC/net.py:38-220 behind libfvc_b200.
+
+Same constructor (no arguments), same sub-module names / state_dict layout, same
+``forward(input_image, referframe, quant_noise_feature=None, quant_noise_z=None,
+quant_noise_mv=None)`` returning the reference 8-tuple
+``(clipped_recon_image, mse_loss, warploss, interloss, bpp_feature, bpp_z, bpp_mv, bpp)``,
+same attributes (``mxrange``, ``calrealbits``, ``warp_weight``, ``decoding_time``) and the
+``load_model`` / ``save_model`` helpers (net.py:18-34).  The whole forward is one call into the
+C ABI (``fvc_pframe_forward``): hand-written sm_100a kernels, no cuDNN, no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import IMPL_SIMT, IMPL_TC, check, lib, ptr, stream_ptr
+from .subnet import (Analysis_mv_net, Analysis_net, Analysis_prior_net, BitEstimator, ME_Spynet, Synthesis_mv_net,
+                     Synthesis_net, Synthesis_prior_net, Warp_net, out_channel_N, out_channel_mv)
+from .synthetic import init_state_dict
+
+
+def save_model(model, iter):
+    """reference net.py:18-19."""
+    torch.save(model.state_dict(), "./snapshot/iter{}.model".format(iter))
+
+
+def load_model(model, f):
+    """reference net.py:21-34 (same key filtering and iteration parsing)."""
+    with open(f, 'rb') as fh:
+        pretrained_dict = torch.load(fh, map_location="cpu")
+        model_dict = model.state_dict()
+        pretrained_dict = {k: v for k, v in pretrained_dict.items() if k in model_dict}
+        model_dict.update(pretrained_dict)
+        model.load_state_dict(model_dict)
+    f = str(f)
+    if f.find('iter') != -1 and f.find('.model') != -1:
+        st = f.find('iter') + 4
+        ed = f.find('.model', st)
+        return int(f[st:ed])
+    return 0
+
+
+def _default_impl():
+    v = os.environ.get("FVC_IMPL", "tc").lower()
+    return IMPL_SIMT if v in ("simt", "0") else IMPL_TC
+
+
+class _Context:
+    """One fvc_ctx per (B, H, W, device): library-owned buffers + packed weights."""
+
+    def __init__(self, model, B, H, W, device, impl):
+        self.key = (B, H, W, device, impl)
+        with torch.cuda.device(device):
+            self.handle = lib().fvc_ctx_create(B, H, W, model.opticFlow.L, impl)
+        if not self.handle:
+            raise _lib.FvcError("fvc_ctx_create failed: %s" % lib().fvc_last_error().decode())
+        self.versions = None
+        self.scalars = torch.empty(7, device=device, dtype=torch.float32)
+
+    def sync_params(self, model):
+        params = dict(model.state_dict(keep_vars=True))
+        versions = tuple((k, p.data_ptr(), p._version) for k, p in params.items())
+        if versions == self.versions:
+            return
+        s = stream_ptr()
+        for k, p in params.items():
+            t = p.detach()
+            if not t.is_cuda:
+                raise RuntimeError("VideoCompressor parameters must live on the CUDA device (call .cuda())")
+            t = t.contiguous().float()
+            check(lib().fvc_ctx_set_param(self.handle, k.encode(), ptr(t), t.numel(), s), "fvc_ctx_set_param(%s)" % k)
+        missing = lib().fvc_ctx_missing_params(self.handle)
+        if missing:
+            raise RuntimeError("%d parameters missing after upload" % missing)
+        self.versions = versions
+
+    def close(self):
+        if self.handle:
+            lib().fvc_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VideoCompressor(nn.Module):
+    def __init__(self, spynet_levels=4):
+        super().__init__()
+        self.opticFlow = ME_Spynet(spynet_levels)
+        self.mvEncoder = Analysis_mv_net()
+        self.Q = None
+        self.mvDecoder = Synthesis_mv_net()
+        self.warpnet = Warp_net()
+        self.resEncoder = Analysis_net()
+        self.resDecoder = Synthesis_net()
+        self.respriorEncoder = Analysis_prior_net()
+        self.respriorDecoder = Synthesis_prior_net()
+        self.bitEstimator_z = BitEstimator(out_channel_N)
+        self.bitEstimator_mv = BitEstimator(out_channel_mv)
+        self.warp_weight = 0
+        self.mxrange = 150
+        self.calrealbits = False
+        self.decoding_time = 0.0
+        self.impl = _default_impl()
+        self._ctxs = {}
+        # reference initialisers (xavier / constants; SpyNet: scaled default init because the
+        # pretrained .npy files are not redistributable with this package)
+        seed = int(torch.initial_seed() % (2 ** 31))
+        self.load_state_dict(init_state_dict(seed, spynet_levels), strict=True)
+
+    # -- context management -----------------------------------------------------------------
+    def _context(self, B, H, W, device):
+        key = (B, H, W, device, self.impl)
+        ctx = self._ctxs.get(key)
+        if ctx is None:
+            ctx = _Context(self, B, H, W, device, self.impl)
+            self._ctxs[key] = ctx
+        ctx.sync_params(self)
+        return ctx
+
+    def release(self):
+        for c in self._ctxs.values():
+            c.close()
+        self._ctxs = {}
+
+    def motioncompensation(self, ref, mv):
+        """reference net.py:64-68 (module-level convenience path)."""
+        from .subnet import flow_warp
+        warpframe = flow_warp(ref, mv)
+        prediction = self.warpnet(torch.cat((warpframe, ref), 1)) + warpframe
+        return prediction, warpframe
+
+    def forward(self, input_image, referframe, quant_noise_feature=None, quant_noise_z=None, quant_noise_mv=None):
+        if self.training:
+            raise NotImplementedError("training-mode (additive-noise) forward is outside the B200 inference hot "
+                                      "path; call .eval() (reference net.py:73-99 noise branch)")
+        if self.calrealbits:
+            raise NotImplementedError("calrealbits (torchac range coding, net.py:123-138) is out of scope")
+        for t in (input_image, referframe):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] == 3):
+                raise TypeError("frames must be CUDA float32 [B,3,H,W] tensors")
+        if input_image.shape != referframe.shape:
+            raise ValueError("input_image and referframe must have the same shape")
+        B, _, H, W = input_image.shape
+        if H % 64 or W % 64:
+            raise ValueError("H and W must be multiples of 64 (got %dx%d)" % (H, W))
+        cur, ref = input_image.contiguous(), referframe.contiguous()
+        with torch.cuda.device(cur.device):
+            ctx = self._context(B, H, W, cur.device)
+            t0_dec = time.perf_counter()
+            recon = torch.empty_like(cur)
+            scalars = torch.empty(7, device=cur.device, dtype=torch.float32)
+            check(lib().fvc_pframe_forward(ctx.handle, ptr(cur), ptr(ref), ptr(recon), ptr(scalars), stream_ptr()),
+                  "fvc_pframe_forward")
+        self._last_ctx = ctx
+        self.decoding_time = time.perf_counter() - t0_dec
+        s = scalars
+        return recon, s[0], s[1], s[2], s[3], s[4], s[5], s[6]
+
+    def get_intermediate(self, name):
+        """fp32 NCHW copy of a named intermediate of the last forward (tests / inspection)."""
+        ctx = self._last_ctx
+        B, H, W = ctx.key[0], ctx.key[1], ctx.key[2]
+        shapes = {"estmv": (B, 2, H, W), "mvfeature": (B, 128, H // 16, W // 16), "quant_mv": (B, 128, H // 16, W // 16),
+                  "mv_hat": (B, 2, H, W), "warpframe": (B, 3, H, W), "prediction": (B, 3, H, W),
+                  "feature": (B, 96, H // 16, W // 16), "z": (B, 64, H // 64, W // 64),
+                  "z_hat": (B, 64, H // 64, W // 64), "sigma": (B, 96, H // 16, W // 16),
+                  "feat_hat": (B, 96, H // 16, W // 16), "recon_res": (B, 3, H, W), "warpnet_res": (B, 3, H, W),
+                  "residual": (B, 3, H, W), "warpnet_c0": (B, 64, H, W), "warpnet_c5": (B, 64, H, W),
+                  "mvenc_e1": (B, 128, H // 2, W // 2), "mvdec_d7": (B, 128, H, W),
+                  "resenc_r0": (B, 64, H // 2, W // 2), "resdec_g2": (B, 64, H // 2, W // 2)}
+        out = torch.empty(shapes[name], device=ctx.key[3], dtype=torch.float32)
+        with torch.cuda.device(out.device):
+            n = lib().fvc_ctx_get_tensor(ctx.handle, name.encode(), ptr(out), out.numel(), stream_ptr())
+        check(n, "fvc_ctx_get_tensor(%s)" % name)
+        return out
+
+    def gop_forward_host(self, frames_host, want_recon=True):
+        """Closed-loop GOP from HOST frames [G,B,3,H,W] through fvc_gop_forward_host (models.py:368-383).
+
+        Returns (recon_host [G-1,B,3,H,W] or None, scalars_host [G-1,7]).  H2D/D2H copies inside.
+        """
+        G, B, _, H, W = frames_host.shape
+        dev = next(self.parameters()).device
+        with torch.cuda.device(dev):
+            ctx = self._context(B, H, W, dev)
+            rec = torch.empty((G - 1, B, 3, H, W), dtype=torch.float32, pin_memory=True) if want_recon else None
+            sc = torch.empty((G - 1, 7), dtype=torch.float32, pin_memory=True)
+            check(lib().fvc_gop_forward_host(ctx.handle, C.c_void_p(frames_host.data_ptr()), G,
+                                             C.c_void_p(rec.data_ptr()) if want_recon else C.c_void_p(0),
+                                             C.c_void_p(sc.data_ptr()), stream_ptr()), "fvc_gop_forward_host")
+        self._last_ctx = ctx
+        return rec, sc
+
+    def launch_count(self):
+        return sum(lib().fvc_ctx_launch_count(c.handle) for c in self._ctxs.values())

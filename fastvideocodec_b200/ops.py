@@ -1,0 +1,174 @@
+"""Op-level Python surface over the C ABI: one function per reference op on the hot path.
+
+Tensors are torch CUDA fp32 tensors used purely as device buffers (PyTorch is plumbing here); each
+function mirrors the reference op it replaces (same argument meaning, same result layout).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_EXP, ACT_LRELU01, ACT_NONE, ACT_RELU, IMPL_SIMT, IMPL_TC, check, lib, ptr, stream_ptr
+
+__all__ = ["avg_pool2", "upsample2x_bilinear", "flow_warp", "conv2d", "conv_transpose2d", "gdn",
+           "quant_bits_factorized", "quant_bits_laplace", "recon_losses", "eb_forward", "gaussian_forward",
+           "pack_eb_params", "ACT_NONE", "ACT_RELU", "ACT_LRELU01", "ACT_EXP", "IMPL_SIMT", "IMPL_TC"]
+
+
+def _cuda_f32(t, name):
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32):
+        raise TypeError("%s must be a CUDA float32 tensor (libfvc_b200 has no CPU path)" % name)
+    return t.contiguous()
+
+
+def avg_pool2(x):
+    """F.avg_pool2d(x, 2, 2) — reference DVC/subnet/endecoder.py:344-346."""
+    x = _cuda_f32(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, Cc, H // 2, W // 2), device=x.device, dtype=torch.float32)
+    check(lib().fvc_avg_pool2(ptr(x), ptr(y), B * Cc, H, W, stream_ptr()), "fvc_avg_pool2")
+    return y
+
+
+def upsample2x_bilinear(x, align_corners=False, scale=1.0):
+    """F.interpolate(x, 2x, 'bilinear', align_corners) * scale — endecoder.py:173-184, 353."""
+    x = _cuda_f32(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, Cc, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+    check(lib().fvc_upsample2x_bilinear(ptr(x), ptr(y), B * Cc, H, W, int(bool(align_corners)), float(scale),
+                                        stream_ptr()), "fvc_upsample2x_bilinear")
+    return y
+
+
+def flow_warp(im, flow):
+    """flow_warp(im, flow) — endecoder.py:116-119 / torch_warp 52-67."""
+    im, flow = _cuda_f32(im, "im"), _cuda_f32(flow, "flow")
+    B, Cc, H, W = im.shape
+    if tuple(flow.shape) != (B, 2, H, W):
+        raise ValueError("flow must be [B,2,H,W]")
+    out = torch.empty_like(im)
+    check(lib().fvc_flow_warp(ptr(im), ptr(flow), ptr(out), B, Cc, H, W, stream_ptr()), "fvc_flow_warp")
+    return out
+
+
+def _conv(x, weight, bias, stride, transposed, act, impl):
+    x, weight = _cuda_f32(x, "x"), _cuda_f32(weight, "weight")
+    B, Cin, H, W = x.shape
+    k = weight.shape[-1]
+    if transposed:
+        if weight.shape[0] != Cin:
+            raise ValueError("ConvTranspose2d weight must be [Cin,Cout,k,k]")
+        Cout = weight.shape[1]
+        Ho, Wo = H * stride, W * stride
+    else:
+        if weight.shape[1] != Cin:
+            raise ValueError("Conv2d weight must be [Cout,Cin,k,k]")
+        Cout = weight.shape[0]
+        Ho, Wo = H // stride, W // stride
+    if bias is None:
+        bias = torch.zeros(Cout, device=x.device, dtype=torch.float32)
+    bias = _cuda_f32(bias, "bias")
+    y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+    check(lib().fvc_conv2d(ptr(x), ptr(weight), ptr(bias), ptr(y), B, Cin, H, W, Cout, k, stride, int(transposed),
+                           int(act), int(impl), stream_ptr()), "fvc_conv2d")
+    return y
+
+
+def conv2d(x, weight, bias=None, stride=1, act=ACT_NONE, impl=IMPL_TC):
+    """nn.Conv2d(.., k, stride, padding=k//2) + activation (all convs of the DVC sub-networks)."""
+    return _conv(x, weight, bias, stride, False, act, impl)
+
+
+def conv_transpose2d(x, weight, bias=None, stride=2, act=ACT_NONE, impl=IMPL_TC):
+    """nn.ConvTranspose2d(.., k, stride, padding=k//2, output_padding=stride-1) + activation."""
+    return _conv(x, weight, bias, stride, True, act, impl)
+
+
+def gdn(x, beta, gamma, inverse=False):
+    """GDN.forward with RAW beta/gamma parameters — reference DVC/subnet/GDN.py:63-93."""
+    x, beta, gamma = _cuda_f32(x, "x"), _cuda_f32(beta, "beta"), _cuda_f32(gamma, "gamma")
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    check(lib().fvc_gdn(ptr(x), ptr(beta), ptr(gamma), ptr(y), B, Cc, H, W, int(bool(inverse)), stream_ptr()),
+          "fvc_gdn")
+    return y
+
+
+def quant_bits_factorized(x, params):
+    """round(x) and total bits under a BitEstimator — net.py:153-178 / bitEstimator.py:20-42.
+
+    ``params``: the 11 tensors f1.h f1.b f1.a f2.h f2.b f2.a f3.h f3.b f3.a f4.h f4.b (any shape
+    holding C values).  Returns (q, bits) with bits a 0-dim tensor.
+    """
+    x = _cuda_f32(x, "x")
+    B, Cc, H, W = x.shape
+    ps = [_cuda_f32(p, "param").reshape(-1) for p in params]
+    if len(ps) != 11 or any(p.numel() != Cc for p in ps):
+        raise ValueError("need 11 parameter vectors of length C")
+    arr = (C.c_void_p * 11)(*[p.data_ptr() for p in ps])
+    q = torch.empty_like(x)
+    bits = torch.empty((), device=x.device, dtype=torch.float32)
+    check(lib().fvc_quant_bits_factorized(ptr(x), arr, ptr(q), ptr(bits), B, Cc, H, W, stream_ptr()),
+          "fvc_quant_bits_factorized")
+    return q, bits
+
+
+def quant_bits_laplace(x, sigma):
+    """round(x) and total bits under Laplace(0, clamp(sigma)) — net.py:121-151."""
+    x, sigma = _cuda_f32(x, "x"), _cuda_f32(sigma, "sigma")
+    if x.shape != sigma.shape:
+        raise ValueError("x and sigma must have the same shape")
+    q = torch.empty_like(x)
+    bits = torch.empty((), device=x.device, dtype=torch.float32)
+    check(lib().fvc_quant_bits_laplace(ptr(x), ptr(sigma), ptr(q), ptr(bits), x.numel(), stream_ptr()),
+          "fvc_quant_bits_laplace")
+    return q, bits
+
+
+def recon_losses(cur, pred, warp, res):
+    """clamp(pred+res, 0, 1) and the three distortion means — net.py:103-116."""
+    cur, pred, warp, res = (_cuda_f32(t, n) for t, n in ((cur, "cur"), (pred, "pred"), (warp, "warp"), (res, "res")))
+    clipped = torch.empty_like(cur)
+    means = torch.empty(3, device=cur.device, dtype=torch.float32)
+    check(lib().fvc_recon_losses(ptr(cur), ptr(pred), ptr(warp), ptr(res), ptr(clipped), ptr(means), cur.numel(),
+                                 stream_ptr()), "fvc_recon_losses")
+    return clipped, means
+
+
+def pack_eb_params(matrices, biases, factors):
+    """Packs CompressAI EntropyBottleneck parameters (filters (3,3,3,3)) to the [C,58] layout."""
+    Cc = matrices[0].shape[0]
+    cols = []
+    for i in range(5):
+        cols.append(matrices[i].reshape(Cc, -1))
+        cols.append(biases[i].reshape(Cc, -1))
+        if i < 4:
+            cols.append(factors[i].reshape(Cc, -1))
+    packed = torch.cat(cols, 1).contiguous().float()
+    if packed.shape[1] != 58:
+        raise ValueError("expected filters (3,3,3,3): got %d values per channel" % packed.shape[1])
+    return packed
+
+
+def eb_forward(x, packed, medians):
+    """EntropyBottleneck eval forward (x_hat, likelihood, bits) — entropy_models.py:66, 74-78."""
+    x, packed, medians = _cuda_f32(x, "x"), _cuda_f32(packed, "packed"), _cuda_f32(medians, "medians")
+    B, Cc, H, W = x.shape
+    xh, lik = torch.empty_like(x), torch.empty_like(x)
+    bits = torch.empty((), device=x.device, dtype=torch.float32)
+    check(lib().fvc_eb_forward(ptr(x), ptr(packed), ptr(medians.reshape(-1)), ptr(xh), ptr(lik), ptr(bits), B, Cc, H,
+                               W, stream_ptr()), "fvc_eb_forward")
+    return xh, lik, bits
+
+
+def gaussian_forward(x, scales, means=None):
+    """GaussianConditional eval forward (x_hat, likelihood, bits) — entropy_models.py:63, 218."""
+    x, scales = _cuda_f32(x, "x"), _cuda_f32(scales, "scales")
+    mp = ptr(_cuda_f32(means, "means")) if means is not None else C.c_void_p(0)
+    xh, lik = torch.empty_like(x), torch.empty_like(x)
+    bits = torch.empty((), device=x.device, dtype=torch.float32)
+    check(lib().fvc_gaussian_forward(ptr(x), ptr(scales), mp, ptr(xh), ptr(lik), ptr(bits), x.numel(), stream_ptr()),
+          "fvc_gaussian_forward")
+    return xh, lik, bits

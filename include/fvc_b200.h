@@ -1,0 +1,155 @@
+/*
+ * fvc_b200.h — C-ABI of libfvc_b200.so: the B200 (sm_100a) implementation of the DVC P-frame
+ * coding hot path of bochen-sysnet/FastVideoCodec.
+ *
+ * The reference has no FFI: its seam is the Python nn.Module API (DVC/net.py::VideoCompressor).
+ * This library sits directly below that seam; fastvideocodec_b200/_lib.py binds it with ctypes
+ * (INTEGRATION.md shows the stub).  Each entry point cites the reference code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense fp32 NCHW exactly as the reference holds them, unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are
+ *     stream-ordered and never synchronise unless stated;
+ *   - return 0 on success, <0 on error; fvc_last_error() gives the thread-local message;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with FVC_ERR_CUDA.
+ */
+#ifndef FVC_B200_H_
+#define FVC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FVC_API __attribute__((visibility("default")))
+#else
+#define FVC_API
+#endif
+
+#define FVC_OK 0
+#define FVC_ERR_ARG (-1)
+#define FVC_ERR_CUDA (-2)
+#define FVC_ERR_STATE (-3)
+
+/* activation codes for fvc_conv2d */
+#define FVC_ACT_NONE 0
+#define FVC_ACT_RELU 1
+#define FVC_ACT_LRELU01 2 /* LeakyReLU(0.1) — analysis_mv.py:17 */
+#define FVC_ACT_EXP 3     /* synthesis_prior.py:57 */
+
+/* convolution engines */
+#define FVC_IMPL_SIMT 0 /* fp32 CUDA-core implicit GEMM (checker / bring-up path) */
+#define FVC_IMPL_TC 1   /* tcgen05 + TMEM + TMA, split-bf16 x3 with fp32 accumulate */
+
+FVC_API int fvc_version(void);
+FVC_API const char* fvc_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Op-level entry points (each mirrors one reference op; used by the parity tests and by
+ * fastvideocodec_b200.ops).
+ * ------------------------------------------------------------------------------------------- */
+
+/* F.avg_pool2d(x, 2, 2) — endecoder.py:344-346, AvgPool2d endecoder.py:273,275.
+ * x: [planes,H,W] -> y: [planes,H/2,W/2]. */
+FVC_API int fvc_avg_pool2(const float* x, float* y, int planes, int H, int W, void* stream);
+
+/* F.interpolate(x, (2H,2W), mode='bilinear', align_corners) * scale — endecoder.py:173-184, 353.
+ * x: [planes,H,W] -> y: [planes,2H,2W]. */
+FVC_API int fvc_upsample2x_bilinear(const float* x, float* y, int planes, int H, int W, int align_corners,
+                            float scale, void* stream);
+
+/* flow_warp / torch_warp — endecoder.py:52-67, 116-119 (grid_sample bilinear, border,
+ * align_corners=False on an align_corners=True style grid).
+ * img: [B,C,H,W], flow: [B,2,H,W] (ch0 = x, ch1 = y) -> out: [B,C,H,W]. */
+FVC_API int fvc_flow_warp(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+
+/* nn.Conv2d(Cin,Cout,k,stride,padding=k//2) [transposed=0; weight [Cout,Cin,k,k]] or
+ * nn.ConvTranspose2d(Cin,Cout,k,stride,padding=k//2,output_padding=stride-1)
+ * [transposed=1; weight [Cin,Cout,k,k]], + bias, + activation.  stride in {1,2}.
+ * x: [B,Cin,H,W] -> y: [B,Cout,Ho,Wo] with Ho = H/stride (conv) or H*stride (transposed).
+ * impl selects the engine (FVC_IMPL_*). */
+FVC_API int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W,
+               int Cout, int k, int stride, int transposed, int act, int impl, void* stream);
+
+/* GDN.forward — GDN.py:63-93.  beta: [C], gamma: [C,C] are the RAW parameters (the lower bounds
+ * and the square-minus-pedestal reparametrisation of GDN.py:73-79 are applied inside). */
+FVC_API int fvc_gdn(const float* x, const float* beta, const float* gamma, float* y, int B, int C, int H, int W,
+            int inverse, void* stream);
+
+/* round + BitEstimator likelihood + clamp-log2 sum — net.py:76/91, 153-178, 181-205,
+ * bitEstimator.py:20-42.  params: 11 device pointers to [C] vectors in the order
+ * f1.h f1.b f1.a f2.h f2.b f2.a f3.h f3.b f3.a f4.h f4.b.
+ * x: [B,C,H,W] -> q_out: [B,C,H,W] (torch.round(x)), bits_out: one float (total bits). */
+FVC_API int fvc_quant_bits_factorized(const float* x, const float* const* params, float* q_out, float* bits_out,
+                              int B, int C, int H, int W, void* stream);
+
+/* round + Laplace(0, clamp(sigma,1e-5,1e10)) likelihood + clamp-log2 sum — net.py:100, 121-151. */
+FVC_API int fvc_quant_bits_laplace(const float* x, const float* sigma, float* q_out, float* bits_out, int64_t n,
+                           void* stream);
+
+/* recon = pred + res; clipped = clamp(recon,0,1); sums_out[3] = mean((recon-cur)^2),
+ * mean((warp-cur)^2), mean((pred-cur)^2) — net.py:103-116.  All [n] fp32. */
+FVC_API int fvc_recon_losses(const float* cur, const float* pred, const float* warp, const float* res,
+                     float* clipped_out, float* means_out, int64_t n, void* stream);
+
+/* CompressAI-compatible likelihoods used by entropy_models.py:55-68, 202-219 (RecProbModel,
+ * MeanScaleHyperPriors) + get_estimate_bits (74-78).  Parity at this boundary is UNPINNED
+ * (CompressAI is not vendored by the reference).
+ * fvc_eb_forward: EntropyBottleneck eval forward with filters (3,3,3,3):
+ *   matrices/biases/factors: packed per channel, medians: [C].
+ *   x: [B,C,H,W] -> xhat_out, lik_out: [B,C,H,W]; bits_out: sum clamp(-log2(lik+1e-5),0,50). */
+FVC_API int fvc_eb_forward(const float* x, const float* packed_params, const float* medians, float* xhat_out,
+                   float* lik_out, float* bits_out, int B, int C, int H, int W, void* stream);
+/* fvc_gaussian_forward: GaussianConditional eval forward (scale_bound 0.11, likelihood_bound 1e-9). */
+FVC_API int fvc_gaussian_forward(const float* x, const float* scales, const float* means, float* xhat_out,
+                         float* lik_out, float* bits_out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-path context: VideoCompressor.forward — net.py:70-220.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fvc_ctx fvc_ctx;
+
+/* Creates a context for frames [B,3,H,W]; H and W must be multiples of 64.
+ * levels = SpyNet pyramid depth (reference: 4, endecoder.py:318).  impl = FVC_IMPL_*. */
+FVC_API fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl);
+FVC_API void fvc_ctx_destroy(fvc_ctx* ctx);
+
+/* Hands one reference state_dict entry (key as in SURVEY 8b, e.g. "mvEncoder.conv3.weight") to the
+ * context.  The data is read (and packed) inside the call, stream-ordered; the caller keeps
+ * ownership.  numel is checked against the expected shape. */
+FVC_API int fvc_ctx_set_param(fvc_ctx* ctx, const char* key, const float* data, int64_t numel, void* stream);
+/* Number of keys still missing (0 = ready). */
+FVC_API int fvc_ctx_missing_params(fvc_ctx* ctx);
+
+/* One P-frame.  cur, ref: [B,3,H,W] in [0,1].  recon_out: [B,3,H,W] (clamped reconstruction =
+ * next reference).  scalars_out: 7 floats = mse_loss, warploss, interloss, bpp_feature, bpp_z,
+ * bpp_mv, bpp (net.py:220).  Stream-ordered, no host synchronisation. */
+FVC_API int fvc_pframe_forward(fvc_ctx* ctx, const float* cur, const float* ref, float* recon_out, float* scalars_out,
+                       void* stream);
+
+/* Copies a named intermediate of the last fvc_pframe_forward as fp32 NCHW (testing/inspection):
+ * estmv mvfeature quant_mv mv_hat warpframe prediction feature z z_hat sigma feat_hat recon_res.
+ * Returns the element count, or <0. */
+FVC_API int64_t fvc_ctx_get_tensor(fvc_ctx* ctx, const char* name, float* out, int64_t capacity, void* stream);
+
+/* Closed-loop GOP from HOST memory — models.py:368-383 (parallel_compression, 'DVC-pretrained'):
+ * frames_host: [G,B,3,H,W] (pinned or pageable), frame 0 is the decoded I-frame.
+ * recon_host: [G-1,B,3,H,W] or NULL.  scalars_host: [G-1,7].  Copies H2D, runs G-1 P-frames,
+ * copies results D2H and synchronises the stream before returning. */
+FVC_API int fvc_gop_forward_host(fvc_ctx* ctx, const float* frames_host, int G, float* recon_host, float* scalars_host,
+                         void* stream);
+
+/* Launch statistics since creation: kernels launched by this library through ctx. */
+FVC_API int64_t fvc_ctx_launch_count(fvc_ctx* ctx);
+/* Dominant-kernel timing hook for bench.py: seconds spent in convolution kernels during the last
+ * fvc_pframe_forward when FVC_PROFILE=1 was set at create time (uses CUDA events; else -1). */
+FVC_API double fvc_ctx_last_conv_seconds(fvc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVC_B200_H_ */

@@ -1,0 +1,191 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, fails loudly
+without a GPU, the host-side mirrors keep the reference interface, and the N>1 path (GOP sharding +
+statistics reduce) works with world_size 2 over gloo."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import __graft_entry__ as g
+    g.build()
+    from fastvideocodec_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    syms = built_lib.declared_symbols()
+    assert len(syms) >= 20
+    handle = ctypes.CDLL(built_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(handle, s), s
+    # the ctypes table binds exactly the header's functions
+    assert sorted(built_lib._SIGNATURES) == syms
+    assert built_lib.lib().fvc_version() >= 100
+
+
+def test_library_has_no_libcuda_load_dependency(built_lib):
+    out = subprocess.run(["ldd", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libcudart" not in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_call_fails_loudly_without_gpu(built_lib):
+    lib = built_lib.lib()
+    buf = (ctypes.c_float * 16)()
+    rc = lib.fvc_avg_pool2(ctypes.cast(buf, ctypes.c_void_p), ctypes.cast(buf, ctypes.c_void_p), 1, 2, 2, None)
+    assert rc == -2
+    assert b"no CPU fallback" in lib.fvc_last_error()
+    assert not lib.fvc_ctx_create(1, 64, 64, 4, 0)
+    with pytest.raises(TypeError):
+        from fastvideocodec_b200 import ops
+        ops.avg_pool2(torch.zeros(1, 1, 2, 2))  # CPU tensor: rejected, never silently computed
+
+
+def test_ctx_create_rejects_bad_geometry(built_lib):
+    lib = built_lib.lib()
+    assert not lib.fvc_ctx_create(1, 720, 1280, 4, 0)  # 720 is not a multiple of 64
+    assert b"multiples of 64" in lib.fvc_last_error()
+
+
+def test_state_dict_layout_matches_reference(state_dict):
+    from fastvideocodec_b200 import VideoCompressor
+    m = VideoCompressor()
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == sorted(state_dict.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(state_dict[k].shape), k
+    assert sum(v.numel() for v in sd.values()) == 4754064
+    from oracle import ref_shim
+    if ref_shim.available():
+        ref = ref_shim.build_reference_model(None)
+        rsd = ref.state_dict()
+        assert sorted(rsd.keys()) == sorted(sd.keys())
+        for k in rsd:
+            assert tuple(rsd[k].shape) == tuple(sd[k].shape), k
+        ref.load_state_dict(sd, strict=True)  # ours loads into the reference
+        m.load_state_dict(rsd, strict=True)   # and the reference's into ours
+
+
+def test_module_surface():
+    from fastvideocodec_b200 import VideoCompressor
+    m = VideoCompressor()
+    for attr in ("opticFlow", "mvEncoder", "mvDecoder", "warpnet", "resEncoder", "resDecoder", "respriorEncoder",
+                 "respriorDecoder", "bitEstimator_z", "bitEstimator_mv", "mxrange", "calrealbits", "warp_weight",
+                 "decoding_time"):
+        assert hasattr(m, attr)
+    assert m.mxrange == 150 and m.calrealbits is False
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))
+    m.eval()
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))  # CPU tensors are rejected, no fallback
+
+
+def test_load_model_filters_keys_and_parses_iter(tmp_path, state_dict):
+    from fastvideocodec_b200 import VideoCompressor, load_model
+    m = VideoCompressor()
+    sd = dict(state_dict)
+    sd["not.a.key"] = torch.zeros(3)
+    f = tmp_path / "iter1234.model"
+    torch.save(sd, f)
+    assert load_model(m, str(f)) == 1234
+    assert torch.equal(m.state_dict()["mvEncoder.conv3.weight"], state_dict["mvEncoder.conv3.weight"])
+    g = tmp_path / "2048.model"
+    torch.save(sd, g)
+    assert load_model(m, str(g)) == 0
+
+
+def test_synthetic_is_deterministic():
+    from fastvideocodec_b200.synthetic import init_state_dict, synthetic_gop
+    a, b = init_state_dict(3), init_state_dict(3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    f, g = synthetic_gop(64, 128, 3, 7), synthetic_gop(64, 128, 3, 7)
+    assert torch.equal(f, g) and f.shape == (3, 1, 3, 64, 128)
+    assert float(f.min()) >= 0 and float(f.max()) <= 1
+
+
+def test_shard_gops_partitions_exactly():
+    from fastvideocodec_b200 import shard_gops
+    for world in (1, 2, 4, 8):
+        seen = sorted(g for r in range(world) for g in shard_gops(64, r, world))
+        assert seen == list(range(64))
+        assert max(len(shard_gops(64, r, world)) for r in range(world)) == 64 // world
+    assert shard_gops(3, 3, 4) == []  # ragged: a rank can own nothing
+    with pytest.raises(ValueError):
+        shard_gops(4, 2, 2)
+
+
+class _FakeCodec(torch.nn.Module):
+    """Stands in for VideoCompressor to test the GOP driver's host logic on CPU."""
+    r = 1024
+
+    def forward(self, x, ref):
+        rec = 0.5 * (x + ref)
+        mse = torch.mean((rec - x) ** 2)
+        one = torch.tensor(0.25)
+        return rec, mse, mse * 2, mse * 3, one, one / 4, one / 2, one + one / 4 + one / 2
+
+
+def test_parallel_compression_matches_reference_aggregation():
+    from fastvideocodec_b200 import parallel_compression
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    data = synthetic_gop(64, 64, gop=4, gop_id=1)[:, 0]
+    out = parallel_compression(None, _FakeCodec(), data.clone())
+    x_hat, loss, img_loss, be_loss, be_res_loss, psnr, psnr_list = out[:7]
+    assert x_hat.shape == (3, 3, 64, 64) and len(out) == 11
+    # closed loop: frame i is predicted from the previous reconstruction (models.py:372-375)
+    prev = data[0:1]
+    psnrs = []
+    for i in range(1, 4):
+        prev = 0.5 * (data[i:i + 1] + prev)
+        psnrs.append(float(10 * torch.log10(1 / torch.mean((prev - data[i:i + 1]) ** 2))))
+        assert torch.allclose(x_hat[i - 1:i], prev)
+    assert abs(psnr - sum(psnrs) / 3) < 1e-4 and abs(be_loss - 0.4375) < 1e-6
+    assert all(abs(a - b) < 1e-4 for a, b in zip(psnr_list, psnrs))
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from fastvideocodec_b200 import shard_gops, stats_vector, reduce_stats, summarize
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rows = []
+for g in shard_gops(5, rank, world):           # 5 GOPs over 2 ranks: ragged split 3 / 2
+    for t in range(3):
+        mse = 1e-3 * (1 + g + t)
+        rows.append([mse, 0, 0, 0, 0, 0, 0.1 * (g + 1)])
+tot = reduce_stats(stats_vector(rows))
+s = summarize(tot)
+if rank == 0:
+    print("RESULT", s["frames"], "%%.6f" %% s["bpp"], "%%.6f" %% s["psnr"])
+dist.destroy_process_group()
+"""
+
+
+def test_stats_reduce_world_size_2_gloo(tmp_path):
+    """N>1 path on CPU: shard by GOP, all_reduce(SUM) of the statistics vector over gloo."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = [ln for ln in outs[0][0].splitlines() if ln.startswith("RESULT")][0].split()
+    import math
+    rows = [(1e-3 * (1 + g + t), 0.1 * (g + 1)) for g in range(5) for t in range(3)]
+    assert int(line[1]) == 15
+    assert abs(float(line[2]) - sum(b for _, b in rows) / 15) < 1e-6
+    assert abs(float(line[3]) - sum(10 * math.log10(1 / m) for m, _ in rows) / 15) < 1e-4
