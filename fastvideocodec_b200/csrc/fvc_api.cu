@@ -133,8 +133,13 @@ int fvc_gdn(const float* x, const float* beta, const float* gamma, float* y, int
 int fvc_quant_bits_factorized(const float* x, const float* const* params, float* q_out, float* bits_out, int B,
                               int C, int H, int W, void* stream) {
     NEED_DEVICE();
-    FVC_ARG(x && params && bits_out && B >= 0 && C >= 1 && H >= 0 && W >= 0);
+    FVC_ARG(params && bits_out && B >= 0 && C >= 1 && H >= 0 && W >= 0);
     cudaStream_t s = (cudaStream_t)stream;
+    if ((int64_t)B * C * H * W == 0) {
+        FVC_CUDA(cudaMemsetAsync(bits_out, 0, 4, s));
+        return 0;
+    }
+    FVC_ARG(x != nullptr);
     TmpPool tmp(s);
     float* partials = nullptr;
     if (tmp.get(&partials, (size_t)bits_max_blocks() * 4)) return FVC_ERR_CUDA;
@@ -158,12 +163,13 @@ int fvc_quant_bits_factorized(const float* x, const float* const* params, float*
 int fvc_quant_bits_laplace(const float* x, const float* sigma, float* q_out, float* bits_out, int64_t n,
                            void* stream) {
     NEED_DEVICE();
-    FVC_ARG(x && sigma && bits_out && n >= 0);
+    FVC_ARG(bits_out && n >= 0);
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) {
         FVC_CUDA(cudaMemsetAsync(bits_out, 0, 4, s));
         return 0;
     }
+    FVC_ARG(x && sigma);
     TmpPool tmp(s);
     float* partials = nullptr;
     if (tmp.get(&partials, (size_t)bits_max_blocks() * 4)) return FVC_ERR_CUDA;
