@@ -84,6 +84,7 @@ int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int 
     Epilogue ep;
     memset(&ep, 0, sizeof(ep));
     ep.bias = bias;
+    ep.acc_scale = 1.f;
     ep.act = act;
     ep.out_f32 = out_nhwc;
     if (impl == FVC_IMPL_TC) {

@@ -67,8 +67,8 @@ k_quant_bits_factorized(const float* __restrict__ x, int nhwc, int B, int C, int
         if (q_act.p) {
             // geometry of q_act equals the latent grid; pix indexes [B,H,W] row-major
             size_t off = (size_t)pix * (size_t)(2 * q_act.Cp);
-            __nv_bfloat16 hi, lo;
-            split_bf16(q, hi, lo);
+            e16 hi, lo;
+            split16(q, hi, lo);
             q_act.p[off + c] = hi;
             q_act.p[off + q_act.Cp + c] = lo;
         }
@@ -88,8 +88,8 @@ __global__ void k_zero_pad_channels(ActT t, int C) {
     if (i >= n) return;
     int c = C + (int)(i % pad);
     size_t off = (size_t)(i / pad) * (size_t)(2 * t.Cp);
-    t.p[off + c] = __float2bfloat16_rn(0.f);
-    t.p[off + t.Cp + c] = __float2bfloat16_rn(0.f);
+    t.p[off + c] = 0;
+    t.p[off + t.Cp + c] = 0;
 }
 static int zero_pad(ActT t, int C, cudaStream_t s) {
     if (!t.p || t.Cp == C) return 0;
@@ -133,8 +133,8 @@ k_quant_bits_laplace(const float* __restrict__ x, const float* __restrict__ sigm
         if (q_act.p) {
             int c = (int)(i % C);
             size_t off = (size_t)(i / C) * (size_t)(2 * q_act.Cp);
-            __nv_bfloat16 hi, lo;
-            split_bf16(q, hi, lo);
+            e16 hi, lo;
+            split16(q, hi, lo);
             q_act.p[off + c] = hi;
             q_act.p[off + q_act.Cp + c] = lo;
         }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -34,19 +35,51 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 extern thread_local int64_t g_launch_count;  // kernels launched by this library on this thread
 
 // ----------------------------------------------------------------------------------------------
-// Activation record format ("ACT"): NHWC, per pixel [hi: Cp bf16][lo: Cp bf16]; value = hi + lo.
-// hi = bf16_rn(v), lo = bf16_rn(v - hi): 16 significant mantissa bits, the operand precision the
-// parity contract needs; both halves feed tcgen05 kind::f16 MMAs directly.
+// Activation record format ("ACT"): NHWC, per pixel [hi: Cp x 16 bit][lo: Cp x 16 bit]; value = hi + lo,
+// hi = rn16(v), lo = rn16(v - hi).  Both halves feed tcgen05 kind::f16 MMAs directly.
+//   FVC_SPLIT_FP16=1 (default): IEEE half pairs, 22 significant bits (abs floor 3e-8, |v| clamped to
+//                               65504) - the precision the parity gates need (measured);
+//   FVC_SPLIT_FP16=0          : bfloat16 pairs, 16 significant bits, fp32 range.
 // parity layout (inputs of stride-2 convs): 4 planes [(y&1)*2+(x&1)][H/2][W/2][record].
 // ----------------------------------------------------------------------------------------------
+#ifndef FVC_SPLIT_FP16
+#define FVC_SPLIT_FP16 1
+#endif
+typedef uint16_t e16;  // one 16-bit storage element of a record (half or bfloat16 bits)
+
+__device__ __forceinline__ e16 f2e(float v) {
+#if FVC_SPLIT_FP16
+    return __half_as_ushort(__float2half_rn(v));
+#else
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+#endif
+}
+__device__ __forceinline__ float e2f(e16 h) {
+#if FVC_SPLIT_FP16
+    return __half2float(__ushort_as_half(h));
+#else
+    return __uint_as_float((uint32_t)h << 16);
+#endif
+}
+// two packed elements (low half = first) -> floats
+__device__ __forceinline__ void e2f2(uint32_t u, float& a, float& b) {
+#if FVC_SPLIT_FP16
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+    a = f.x; b = f.y;
+#else
+    a = __uint_as_float(u << 16);
+    b = __uint_as_float(u & 0xffff0000u);
+#endif
+}
+
 struct ActT {
-    __nv_bfloat16* p;
+    e16* p;
     int B, H, W, Cp;
     int parity;
 };
 
 __host__ __device__ inline size_t act_bytes(int B, int H, int W, int Cp) {
-    return (size_t)B * H * W * Cp * 2 * sizeof(__nv_bfloat16);
+    return (size_t)B * H * W * Cp * 2 * sizeof(e16);
 }
 
 __device__ __forceinline__ size_t act_pixel_offset(const ActT& t, int b, int y, int x) {
@@ -60,25 +93,26 @@ __device__ __forceinline__ size_t act_pixel_offset(const ActT& t, int b, int y, 
     return pix * (size_t)(2 * t.Cp);
 }
 
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+__device__ __forceinline__ void split16(float v, e16& hi, e16& lo) {
+#if FVC_SPLIT_FP16
+    v = fminf(fmaxf(v, -65504.f), 65504.f);  // keep hi finite (NaN passes through)
+#endif
+    hi = f2e(v);
+    lo = f2e(v - e2f(hi));
 }
 
 __device__ __forceinline__ float act_load(const ActT& t, size_t pixoff, int c) {
-    return __bfloat162float(t.p[pixoff + c]) + __bfloat162float(t.p[pixoff + t.Cp + c]);
+    return e2f(t.p[pixoff + c]) + e2f(t.p[pixoff + t.Cp + c]);
 }
 
 __device__ __forceinline__ void act_store(const ActT& t, size_t pixoff, int c, float v) {
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
+    e16 hi, lo;
+    split16(v, hi, lo);
     t.p[pixoff + c] = hi;
     t.p[pixoff + t.Cp + c] = lo;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
+__device__ __forceinline__ uint32_t pack16x2(e16 a, e16 b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
 // warp + block sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0
 __device__ __forceinline__ float warp_sum(float v) {
@@ -130,6 +164,7 @@ void make_conv_layer(ConvLayer& L, int Cin, int Cout, int k, int stride, int tra
 // Epilogue description (device-visible POD)
 struct Epilogue {
     const float* bias;        // [Cout]
+    float acc_scale;          // accumulators are multiplied by this before the bias (1/weight scale)
     int act;                  // FVC_ACT_*
     ActT res_act;             // optional residual (p == nullptr: none), same geometry as the output
     const float* res_f32;     // optional fp32 NHWC residual [B,Hout,Wout,Cout]

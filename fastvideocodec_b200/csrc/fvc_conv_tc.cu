@@ -1,12 +1,770 @@
-// placeholder until the tcgen05 engine lands (next commit)
+// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (sm_100a).
+//
+// GEMM view: M = 128 output pixels (a 16x8 sub-tile), N = output channels, K = taps x input channels.
+//   * A (activations) is never im2col'ed.  A CTA loads ONE halo'ed input patch [PH][PW][128 B] per
+//     128-byte record segment with a single 5-D TMA box (zero fill outside the image = conv
+//     padding) and every filter tap is just a different start address into that patch: the 8-row
+//     core groups of the UMMA K-major SWIZZLE_128B layout are 8 consecutive pixels of one image
+//     row (128 B pitch) and successive groups are successive image rows (SBO = PW*128 B).
+//   * B (weights) is a pre-packed bf16 stream in exactly the order the K loop consumes it, pulled
+//     by 2-D TMA boxes through a multi-stage mbarrier ring.
+//   * Precision: activations and weights are hi/lo bf16 pairs; each product is issued as
+//     a_hi*w_hi + a_hi*w_lo + a_lo*w_hi on kind::f16 MMAs with fp32 accumulation in TMEM
+//     (>= 16 operand mantissa bits, the parity contract of SURVEY 7.2-1).
+//   * S sub-tiles (S*N accumulator columns in TMEM) share every weight stage, cutting the weight
+//     traffic per pixel S-fold; stride-2 convs read the four parity planes of a parity-planar
+//     input; stride-2 transposed convs run as 4 output-phase sub-convolutions.
+//   * Accumulation: tcgen05 adds into its fp32 TMEM accumulator with TRUNCATION (measured: relative
+//     bias -4.9e-8 per MMA in the chain, -2.9e-5 after the 588 MMAs of a 7x7x64 filter; see
+//     tools/tc_bias.py and DESIGN.md).  So TMEM only ever holds SHORT chains (<= ~24 MMAs, a group
+//     of taps): two partial-accumulator buffers ping-pong, and 16 accumulator warps drain each
+//     finished partial with tcgen05.ld and add it to a running sum in registers in fp32
+//     round-to-nearest, overlapped with the MMAs of the next group.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..19 =
+//     accumulator/epilogue warps (drain -> running sum -> bias/activation/residual -> hi/lo split
+//     -> global).  Persistent over tiles.
+#include <cuda.h>
+#include <vector>
+#include <cstring>
+#include <cmath>
+
 #include "fvc_kernels.cuh"
+#include "fvc_epilogue.cuh"
+
 namespace fvc {
-struct TcPlan { int dummy; };
-bool tc_supported(const ConvLayer&, int) { return false; }
-int tc_plan_create(const ConvLayer&, const float*, ActT, int, int, const Epilogue&, TcPlan**, cudaStream_t) {
-    set_error("tcgen05 engine not built");
+
+// ----------------------------------------------------------------------------------------------
+// device tables
+// ----------------------------------------------------------------------------------------------
+#define TC_MAX_PASS 16
+#define TC_MAX_TAPS 64
+#define TC_THREADS 640
+
+struct TcPass {
+    int8_t seg, plane;     // record segment (128 B unit) and parity plane (0 for stride-1 inputs)
+    int8_t oy, ox;         // patch origin relative to the tile's q origin (input grid of that plane)
+    int16_t tap_first, ntaps;
+    int8_t nbt, ks0, ks1;  // weight tiles per tap and their k-step counts (16 channels per k-step)
+    int8_t gtaps;          // taps per accumulation group (one TMEM chain, drained to registers)
+};
+struct TcSub {
+    int pass_first, npass, py, px;
+    uint32_t btile_first;
+    int ngroups;           // accumulation groups per tile
+};
+struct alignas(64) TcParams {
+    CUtensorMap mapA;
+    CUtensorMap mapB;
+    TcSub sub[4];
+    TcPass pass[TC_MAX_PASS];
+    int32_t tap_off[TC_MAX_TAPS];  // byte offset of the tap's window inside the patch
+    int nsub, S, SX, N, PW, PH, nst, CT;   // CT = S*N accumulator columns per partial buffer
+    int Hq, Wq, tiles_x, tiles_y, B, os, Hout, Wout, Cout, nchunks;
+    uint32_t patch_bytes, patch_tx, btile_bytes, tmem_cols, idesc;
+    int planes;       // 1 or 4 (parity-planar input)
+    int bo_mode;      // 0: base_offset field = 0, 1: (addr >> 7) & 7
+    Epilogue ep;
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("fvc tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+                   bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, int bo_mode) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);                 // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                   // leading byte offset (ignored, K-major swizzled)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;        // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                                   // descriptor version 1 (Blackwell)
+    if (bo_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;    // base offset, bits [49,52)
+    d |= (uint64_t)2 << 61;                                   // SWIZZLE_128B
+    return d;
+}
+
+// ----------------------------------------------------------------------------------------------
+// (tile, pass) iterator shared by the producer and the MMA issuer
+// ----------------------------------------------------------------------------------------------
+struct PassIter {
+    int tile, pass;     // current tile id, pass index inside the tile's sub-convolution
+    int b, sub, ty, tx;
+    __device__ __forceinline__ void decode(const TcParams& P) {
+        int t = tile;
+        tx = t % P.tiles_x; t /= P.tiles_x;
+        ty = t % P.tiles_y; t /= P.tiles_y;
+        sub = t % P.nsub;
+        b = t / P.nsub;
+    }
+    __device__ __forceinline__ bool valid(int ntiles) const { return tile < ntiles; }
+    __device__ __forceinline__ void next(const TcParams& P, int stride) {
+        if (++pass >= P.sub[sub].npass) {
+            pass = 0;
+            tile += stride;
+            decode(P);
+        }
+    }
+};
+
+template <int NCH>   // 8-column chunks of the running sum each accumulator thread owns (CT/4 = 8*NCH)
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment: SWIZZLE_128B atoms
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t patch0 = base;                                   // 2 patch sets
+    const uint32_t bst0 = base + 2 * P.patch_bytes;                 // nst weight stages
+    const uint32_t bars = bst0 + P.nst * P.btile_bytes;             // mbarriers (8 B each)
+    const uint32_t bar_pfull = bars, bar_pempty = bars + 16;        // [2] each
+    const uint32_t bar_bfull = bars + 32, bar_bempty = bars + 32 + 8 * 8;   // [nst <= 8] each
+    const uint32_t bar_afull = bars + 32 + 16 * 8, bar_aempty = bar_afull + 16;  // partial buffers [2] each
+    const uint32_t tmem_slot = bar_aempty + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_pfull + 8 * i, 1);
+            mbar_init(bar_pempty + 8 * i, 1);
+            mbar_init(bar_afull + 8 * i, 1);
+            mbar_init(bar_aempty + 8 * i, 16);  // one arrive per accumulator warp
+        }
+        for (int i = 0; i < P.nst; ++i) {
+            mbar_init(bar_bfull + 8 * i, 1);
+            mbar_init(bar_bempty + 8 * i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"(P.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ================================ TMA producer ==========================================
+        if (lane == 0) {
+            PassIter cur, nxt;
+            cur.tile = blockIdx.x; cur.pass = 0; cur.decode(P);
+            uint32_t gp = 0;       // global pass counter (patch ring position)
+            uint32_t gb = 0;       // global weight-stage counter
+            auto issue_patch = [&](const PassIter& it, uint32_t g) {
+                const TcPass& ps = P.pass[P.sub[it.sub].pass_first + it.pass];
+                const uint32_t set = g & 1u, ph = (g >> 1) & 1u;
+                mbar_wait(bar_pempty + 8 * set, ph ^ 1u);
+                mbar_expect_tx(bar_pfull + 8 * set, P.patch_tx);
+                int x0 = it.tx * 8 * P.SX + ps.ox, y0 = it.ty * 16 + ps.oy;
+                tma_load_5d(patch0 + set * P.patch_bytes, &P.mapA, bar_pfull + 8 * set, 0, ps.seg, x0, y0,
+                            it.b * P.planes + ps.plane);
+            };
+            if (cur.valid(ntiles)) issue_patch(cur, gp);
+            while (cur.valid(ntiles)) {
+                const TcSub& sb = P.sub[cur.sub];
+                const TcPass& ps = P.pass[sb.pass_first + cur.pass];
+                // weight tiles of this pass: contiguous in the stream
+                uint32_t bt = sb.btile_first;
+                for (int q = 0; q < cur.pass; ++q) {
+                    const TcPass& pq = P.pass[sb.pass_first + q];
+                    bt += (uint32_t)pq.ntaps * pq.nbt;
+                }
+                const int nb = ps.ntaps * ps.nbt;
+                nxt = cur;
+                nxt.next(P, gridDim.x);
+                const int pref = min(P.nst - 1, nb - 1);
+                for (int i = 0; i < nb; ++i) {
+                    if (i == pref && nxt.valid(ntiles)) issue_patch(nxt, gp + 1);
+                    const uint32_t st = gb % P.nst, ph = (gb / P.nst) & 1u;
+                    mbar_wait(bar_bempty + 8 * st, ph ^ 1u);
+                    mbar_expect_tx(bar_bfull + 8 * st, P.btile_bytes);
+                    tma_load_2d(bst0 + st * P.btile_bytes, &P.mapB, bar_bfull + 8 * st, 0, (int)((bt + i) * P.N));
+                    ++gb;
+                }
+                ++gp;
+                cur = nxt;
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer =============================================
+        if (lane == 0) {
+            PassIter cur;
+            cur.tile = blockIdx.x; cur.pass = 0; cur.decode(P);
+            uint32_t gp = 0, gb = 0, gg = 0;   // pass, weight-stage and accumulation-group counters
+            const uint32_t sbo = (uint32_t)P.PW * 128u;
+            while (cur.valid(ntiles)) {
+                const TcSub& sb = P.sub[cur.sub];
+                const TcPass& ps = P.pass[sb.pass_first + cur.pass];
+                const uint32_t set = gp & 1u;
+                mbar_wait(bar_pfull + 8 * set, (gp >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t pbase = patch0 + set * P.patch_bytes;
+                for (int t0 = 0; t0 < ps.ntaps; t0 += ps.gtaps) {
+                    const int t1 = min(t0 + (int)ps.gtaps, (int)ps.ntaps);
+                    // partial buffer must have been drained by the accumulator warps
+                    const uint32_t pb = gg & 1u;
+                    mbar_wait(bar_aempty + 8 * pb, ((gg >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    for (int t = t0; t < t1; ++t) {
+                        const uint32_t toff = (uint32_t)P.tap_off[ps.tap_first + t];
+                        for (int j = 0; j < ps.nbt; ++j) {
+                            const uint32_t st = gb % P.nst;
+                            mbar_wait(bar_bfull + 8 * st, (gb / P.nst) & 1u);
+                            tc_fence_after();
+                            const uint32_t bbase = bst0 + st * P.btile_bytes;
+                            const int ks = j == 0 ? ps.ks0 : ps.ks1;
+                            const bool first = (t == t0 && j == 0);
+                            for (int s = 0; s < P.S; ++s) {
+                                const uint32_t abase = pbase + toff + (uint32_t)s * 8u * 128u;
+                                const uint32_t dcol = tmem_base + pb * P.CT + s * P.N;
+                                for (int k = 0; k < ks; ++k) {
+                                    uint64_t ad = make_desc(abase + k * 32u, sbo, P.bo_mode);
+                                    uint64_t bd = make_desc(bbase + k * 32u, 1024u, 0);
+                                    tc_mma(dcol, ad, bd, P.idesc, (first && k == 0) ? 0u : 1u);
+                                }
+                            }
+                            tc_commit(bar_bempty + 8 * st);   // frees the weight stage when these MMAs retire
+                            ++gb;
+                        }
+                    }
+                    tc_commit(bar_afull + 8 * pb);            // short chain complete -> accumulator warps
+                    ++gg;
+                }
+                tc_commit(bar_pempty + 8 * set);              // patch set reusable
+                ++gp;
+                cur.next(P, gridDim.x);
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================= accumulator / epilogue warps (16) =================================
+        const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+        const int part = (warp - 4) >> 2;                 // which quarter of the CT columns
+        const int row = quarter * 32 + lane;              // accumulator row = pixel inside the sub-tile
+        const int th = row >> 3, tw = row & 7;
+        const uint32_t colbase = (uint32_t)part * (uint32_t)(NCH * 8);
+        uint32_t gg = 0;
+        float run[NCH * 8];
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int t = tile;
+            const int tx = t % P.tiles_x; t /= P.tiles_x;
+            const int ty = t % P.tiles_y; t /= P.tiles_y;
+            const int sub = t % P.nsub;
+            const int b = t / P.nsub;
+            const int ng = P.sub[sub].ngroups;
+            for (int g = 0; g < ng; ++g, ++gg) {
+                const uint32_t pb = gg & 1u;
+                mbar_wait(bar_afull + 8 * pb, (gg >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pb * P.CT + colbase;
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    float v[8];
+                    tc_ld8(taddr + i * 8, reinterpret_cast<uint32_t*>(v));
+                    tc_wait_ld();
+                    if (g == 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) run[i * 8 + q] = v[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) run[i * 8 + q] += v[q];   // fp32 round-to-nearest
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
+            }
+            // ---- epilogue from registers ----
+            const int qy = ty * 16 + th;
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                const int col = (int)colbase + i * 8;
+                const int s = col / P.N, c0 = col - s * P.N;
+                const int qx = (tx * P.SX + s) * 8 + tw;
+                if (qy < P.Hq && qx < P.Wq)
+                    epilogue_apply<8>(P.ep, P.Cout, P.Hout, P.Wout, b, qy * P.os + P.sub[sub].py,
+                                      qx * P.os + P.sub[sub].px, c0, run + i * 8);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols)
+                     : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// weight stream packing
+// ----------------------------------------------------------------------------------------------
+struct BTileInfo {
+    int8_t r, s;       // kernel tap
+    uint8_t kind;      // 0: hi(c0..c0+63)  1: lo(c0..c0+63)  2: [hi(0..31) | hi(0..31)]  3: [lo(0..31) | 0]
+    uint8_t c0;
+};
+__global__ void k_absmax(const float* __restrict__ w, size_t n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float m = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) *out = m;
+    }
+}
+
+__global__ void k_tc_pack(const float* __restrict__ w, e16* __restrict__ out, const BTileInfo* __restrict__ info,
+                          int ntiles, int N, int Cin, int Cout, int k, int transposed, float wscale) {
+    size_t n = (size_t)ntiles * N * 64;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int col = (int)(i & 63);
+    int row = (int)((i >> 6) % N);
+    int tile = (int)(i / ((size_t)N * 64));
+    BTileInfo bi = info[tile];
+    int ci;
+    bool lo;
+    bool zero = false;
+    if (bi.kind <= 1) {
+        ci = bi.c0 + col;
+        lo = bi.kind == 1;
+    } else if (bi.kind == 2) {
+        ci = col & 31;
+        lo = false;
+    } else {
+        ci = col & 31;
+        lo = true;
+        zero = col >= 32;
+    }
+    float v = 0.f;
+    if (!zero && ci < Cin && row < Cout) {
+        v = transposed ? w[(((size_t)ci * Cout + row) * k + bi.r) * k + bi.s]
+                       : w[(((size_t)row * Cin + ci) * k + bi.r) * k + bi.s];
+    }
+    v *= wscale;  // power of two: exact
+    e16 hi = f2e(v);
+    out[i] = lo ? f2e(v - e2f(hi)) : hi;
+}
+
+// ----------------------------------------------------------------------------------------------
+// host: plan
+// ----------------------------------------------------------------------------------------------
+struct TcPlan {
+    TcParams P;
+    e16* wstream = nullptr;
+    size_t smem = 0;
+    int grid = 0;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+bool tc_supported(const ConvLayer& L, int CinP) {
+    if (!(CinP == 32 || CinP == 64 || CinP == 128)) return false;
+    if (L.k > 7 || L.Cout > 128) return false;
+    return true;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, int Wout, const Epilogue& ep,
+                   TcPlan** out, cudaStream_t s) {
+    FVC_ARG(tc_supported(L, in.Cp));
+    FVC_ARG(ep.gdn_beta == nullptr);
+    FVC_ARG((L.st == 2) == (in.parity != 0));
+    PFN_encodeTiled encode = get_encode();
+    if (!encode) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return FVC_ERR_CUDA;
+    }
+    TcPlan* plan = new TcPlan();
+    TcParams& P = plan->P;
+    memset(&P, 0, sizeof(P));
+    const int Cp = in.Cp;
+    // output channels covered by the MMA: every channel of an ACT output record must be written
+    int chans = L.Cout;
+    if (ep.out_act.p) chans = std::max(chans, ep.out_act.Cp);
+    if (ep.out_act_relu.p) chans = std::max(chans, ep.out_act_relu.Cp);
+    const int N = std::max(16, cdiv(chans, 16) * 16);   // MMA N: every channel of an output record is produced
+    P.N = N;
+    P.nchunks = 0;
+    P.Cout = L.Cout;
+    P.nsub = L.nsub;
+    P.os = L.os;
+    P.Hout = Hout; P.Wout = Wout;
+    P.Hq = Hout / L.os; P.Wq = Wout / L.os;
+    P.B = in.B;
+    P.planes = (L.st == 2) ? 4 : 1;
+    P.bo_mode = env_int("FVC_TC_BO_MODE", 0);
+    P.ep = ep;
+
+    // ---- passes: (segment, plane) x taps ---------------------------------------------------------
+    struct HostTap { int ey, ex, r, s; };
+    std::vector<BTileInfo> binfo;
+    int npass = 0, ntapent = 0;
+    int gymin = 127, gymax = -127, gxmin = 127, gxmax = -127;   // extents over all (sub, plane) groups
+    struct Group { int sub, plane; std::vector<HostTap> taps; int eymin, exmin, eymax, exmax; int tap_first; };
+    std::vector<Group> groups;
+    for (int si = 0; si < L.nsub; ++si) {
+        const SubConv& S = L.sub[si];
+        for (int pl = 0; pl < P.planes; ++pl) {
+            Group g;
+            g.sub = si; g.plane = pl; g.tap_first = 0;
+            g.eymin = g.exmin = 127; g.eymax = g.exmax = -127;
+            for (int t = 0; t < S.ntaps; ++t) {
+                int dy = S.dy[t], dx = S.dx[t];
+                int ey = dy, ex = dx;
+                if (L.st == 2) {
+                    int py = dy & 1, px = dx & 1;
+                    if (py * 2 + px != pl) continue;
+                    ey = (dy - py) / 2; ex = (dx - px) / 2;
+                }
+                g.taps.push_back({ey, ex, S.r[t], S.s[t]});
+                g.eymin = std::min(g.eymin, ey); g.eymax = std::max(g.eymax, ey);
+                g.exmin = std::min(g.exmin, ex); g.exmax = std::max(g.exmax, ex);
+            }
+            if (g.taps.empty()) continue;
+            gymin = std::min(gymin, g.eymin); gymax = std::max(gymax, g.eymax);
+            gxmin = std::min(gxmin, g.exmin); gxmax = std::max(gxmax, g.exmax);
+            groups.push_back(g);
+        }
+    }
+    int max_ext_y = 0, max_ext_x = 0;
+    for (auto& g : groups) {
+        max_ext_y = std::max(max_ext_y, g.eymax - g.eymin);
+        max_ext_x = std::max(max_ext_x, g.exmax - g.exmin);
+    }
+    // ---- tile shape -------------------------------------------------------------------------------
+    const int pw_align = env_int("FVC_TC_PW_ALIGN", 1);
+    const int smem_cap = 232448 - 2048;
+    int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y;
+    // S*N accumulator columns per partial buffer, CT/32 in {1,2,3,4,6,8} (template instantiations),
+    // CT <= 256 (two partial buffers in 512 TMEM columns, <= 128 running-sum registers per thread)
+    const int sx_max = std::min(env_int("FVC_TC_SX", 4), 256 / N);
+    for (int sx = std::max(1, sx_max); sx >= 1; --sx) {
+        const int ct32 = sx * N / 32;
+        if ((sx * N) % 32 != 0 || !(ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
+        int pw = 8 * sx + max_ext_x;
+        pw = cdiv(pw, pw_align) * pw_align;
+        size_t patch = (size_t)PH * pw * 128;
+        patch = (patch + 1023) & ~(size_t)1023;
+        for (int st = 6; st >= 2; --st) {
+            size_t need = 2 * patch + (size_t)st * N * 128 + 1024;
+            if ((int)need <= smem_cap) {
+                SX = sx; nst = st; PW = pw;
+                break;
+            }
+        }
+        if (SX) break;
+    }
+    if (!SX) {
+        set_error("tc_plan_create: no tile shape fits shared memory");
+        delete plan;
+        return FVC_ERR_STATE;
+    }
+    P.S = SX; P.SX = SX; P.PW = PW; P.PH = PH; P.nst = nst;
+    P.CT = SX * N;
+    P.patch_bytes = (uint32_t)((((size_t)PH * PW * 128) + 1023) & ~(size_t)1023);
+    P.patch_tx = (uint32_t)((size_t)PH * PW * 128);
+    P.btile_bytes = (uint32_t)N * 128u;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * P.CT)) cols <<= 1;
+    P.tmem_cols = cols;
+    P.tiles_x = cdiv(P.Wq, 8 * SX);
+    P.tiles_y = cdiv(P.Hq, 16);
+    // instruction descriptor: D=f32, A=B=f16 (0) or bf16 (1), K-major both, N, M=128
+    const uint32_t fmt = FVC_SPLIT_FP16 ? 0u : 1u;
+    P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+    for (auto& g : groups) {
+        g.tap_first = ntapent;
+        if (ntapent + (int)g.taps.size() > TC_MAX_TAPS) {
+            set_error("tap table overflow");
+            delete plan;
+            return FVC_ERR_STATE;
+        }
+        for (auto& tp : g.taps) P.tap_off[ntapent++] = ((tp.ey - g.eymin) * PW + (tp.ex - g.exmin)) * 128;
+    }
+    // ---- segment passes -----------------------------------------------------------------------------
+    struct SegPass { int seg, nbt, ks0, ks1, kind0, kind1, c0; };
+    std::vector<SegPass> segp;
+    if (Cp == 32) segp.push_back({0, 2, 4, 2, 2, 3, 0});
+    else if (Cp == 64) { segp.push_back({0, 2, 4, 4, 0, 1, 0}); segp.push_back({1, 1, 4, 0, 0, 0, 0}); }
+    else {
+        segp.push_back({0, 2, 4, 4, 0, 1, 0}); segp.push_back({1, 2, 4, 4, 0, 1, 64});
+        segp.push_back({2, 1, 4, 0, 0, 0, 0}); segp.push_back({3, 1, 4, 0, 0, 0, 64});
+    }
+    for (int si = 0; si < L.nsub; ++si) {
+        TcSub& sb = P.sub[si];
+        sb.pass_first = npass;
+        sb.py = L.sub[si].py; sb.px = L.sub[si].px;
+        sb.btile_first = (uint32_t)binfo.size();
+        // tap tables per group of this sub
+        for (auto& sp : segp) {
+            for (auto& g : groups) {
+                if (g.sub != si) continue;
+                if (npass >= TC_MAX_PASS) { set_error("too many passes"); delete plan; return FVC_ERR_STATE; }
+                TcPass& ps = P.pass[npass++];
+                ps.seg = (int8_t)sp.seg; ps.plane = (int8_t)g.plane;
+                ps.oy = (int8_t)g.eymin; ps.ox = (int8_t)g.exmin;
+                ps.ntaps = (int16_t)g.taps.size();
+                ps.nbt = (int8_t)sp.nbt; ps.ks0 = (int8_t)sp.ks0; ps.ks1 = (int8_t)sp.ks1;
+                {
+                    // taps per accumulation group: keep every TMEM chain <= chain_max MMAs
+                    const int per_tap = sp.ks0 + (sp.nbt == 2 ? sp.ks1 : 0);
+                    const int chain_max = env_int("FVC_TC_CHAIN", 24);
+                    ps.gtaps = (int8_t)std::max(1, std::min(127, chain_max / per_tap));
+                }
+                ps.tap_first = (int16_t)g.tap_first;
+                for (auto& tp : g.taps) {
+                    binfo.push_back({(int8_t)tp.r, (int8_t)tp.s, (uint8_t)sp.kind0, (uint8_t)sp.c0});
+                    if (sp.nbt == 2) binfo.push_back({(int8_t)tp.r, (int8_t)tp.s, (uint8_t)sp.kind1, (uint8_t)sp.c0});
+                }
+            }
+        }
+        sb.npass = npass - sb.pass_first;
+        sb.ngroups = 0;
+        for (int q = sb.pass_first; q < npass; ++q) sb.ngroups += cdiv(P.pass[q].ntaps, P.pass[q].gtaps);
+    }
+
+    // ---- weight stream -------------------------------------------------------------------------------
+    const int nbt_total = (int)binfo.size();
+    size_t wbytes = (size_t)nbt_total * N * 64 * sizeof(e16);
+    BTileInfo* dinfo = nullptr;
+    cudaError_t ce = cudaMalloc(&plan->wstream, wbytes);
+    if (ce == cudaSuccess) ce = cudaMalloc(&dinfo, binfo.size() * sizeof(BTileInfo));
+    if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(dinfo, binfo.data(), binfo.size() * sizeof(BTileInfo), cudaMemcpyHostToDevice, s);
+    if (ce != cudaSuccess) {
+        delete plan;
+        return cuda_fail(ce, "tc weight stream alloc", __FILE__, __LINE__);
+    }
+    {
+        // power-of-two weight scale: in half mode it lifts hi AND lo of the weights into the normal
+        // range (max |w| -> [2^11, 2^12)); the epilogue multiplies the accumulators by 1/scale.
+        float wscale = 1.f;
+#if FVC_SPLIT_FP16
+        float* dmax = nullptr;
+        float hmax = 0.f;
+        ce = cudaMalloc(&dmax, 4);
+        if (ce == cudaSuccess) {
+            k_absmax<<<1, 1024, 0, s>>>(w_ref, (size_t)L.Cin * L.Cout * L.k * L.k, dmax);
+            g_launch_count++;
+            ce = cudaMemcpyAsync(&hmax, dmax, 4, cudaMemcpyDeviceToHost, s);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+            cudaFree(dmax);
+        }
+        if (ce != cudaSuccess) {
+            cudaFree(dinfo);
+            cudaFree(plan->wstream);
+            delete plan;
+            return cuda_fail(ce, "k_absmax", __FILE__, __LINE__);
+        }
+        if (hmax > 0.f && std::isfinite(hmax)) {
+            int e = 0;
+            std::frexp(hmax, &e);              // hmax = m * 2^e, m in [0.5, 1)
+            wscale = std::ldexp(1.f, 12 - e);  // max |w| * scale in [2^11, 2^12)
+        }
+#endif
+        P.ep.acc_scale = ep.acc_scale / wscale;
+        size_t n = (size_t)nbt_total * N * 64;
+        k_tc_pack<<<(unsigned)cdiv64((int64_t)n, 256), 256, 0, s>>>(w_ref, plan->wstream, dinfo, nbt_total, N, L.Cin,
+                                                                    L.Cout, L.k, L.transposed, wscale);
+        g_launch_count++;
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);   // binfo (host vector) must outlive the copy
+        cudaFree(dinfo);
+        if (ce != cudaSuccess) {
+            cudaFree(plan->wstream);
+            delete plan;
+            return cuda_fail(ce, "k_tc_pack", __FILE__, __LINE__);
+        }
+    }
+
+    // ---- tensor maps -----------------------------------------------------------------------------------
+    {
+        const cuuint64_t rec = (cuuint64_t)Cp * 4;   // bytes per pixel record
+        const int nseg = Cp / 32;
+        const int Wd = in.parity ? in.W / 2 : in.W, Hd = in.parity ? in.H / 2 : in.H;
+        cuuint64_t dims[5] = {64, (cuuint64_t)nseg, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)(in.B * P.planes)};
+        cuuint64_t strides[4] = {128, rec, rec * Wd, rec * Wd * Hd};
+        cuuint32_t box[5] = {64, 1, (cuuint32_t)PW, (cuuint32_t)PH, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = encode(&P.mapA, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 5, (void*)in.p, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(A) failed: %d (Cp=%d W=%d H=%d PW=%d PH=%d)", (int)r, Cp, Wd, Hd, PW, PH);
+            cudaFree(plan->wstream);
+            delete plan;
+            return FVC_ERR_CUDA;
+        }
+        cuuint64_t bdims[2] = {64, (cuuint64_t)nbt_total * N};
+        cuuint64_t bstr[1] = {128};
+        cuuint32_t bbox[2] = {64, (cuuint32_t)N};
+        cuuint32_t bes[2] = {1, 1};
+        r = encode(&P.mapB, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, (void*)plan->wstream, bdims, bstr, bbox, bes,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+            cudaFree(plan->wstream);
+            delete plan;
+            return FVC_ERR_CUDA;
+        }
+    }
+    plan->smem = 1024 + 2 * (size_t)P.patch_bytes + (size_t)nst * P.btile_bytes + 512;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;
+    plan->grid = std::max(1, std::min(ntiles, sms));
+    *out = plan;
+    return 0;
+}
+
+template <int NCH>
+static int tc_launch_t(TcPlan* plan, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set = true;
+    }
+    k_conv_tc<NCH><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->P);
+    g_launch_count++;
+    FVC_CHECK_LAUNCH();
+    return 0;
+}
+
+int tc_plan_launch(TcPlan* plan, cudaStream_t s) {
+    FVC_ARG(plan != nullptr);
+    switch (plan->P.CT / 32) {
+        case 2: return tc_launch_t<2>(plan, s);
+        case 3: return tc_launch_t<3>(plan, s);
+        case 4: return tc_launch_t<4>(plan, s);
+        case 6: return tc_launch_t<6>(plan, s);
+        case 8: return tc_launch_t<8>(plan, s);
+    }
+    set_error("tc_plan_launch: unsupported accumulator width %d", plan->P.CT);
     return FVC_ERR_STATE;
 }
-int tc_plan_launch(TcPlan*, cudaStream_t) { return FVC_ERR_STATE; }
-void tc_plan_destroy(TcPlan* p) { delete p; }
+
+void tc_plan_destroy(TcPlan* plan) {
+    if (!plan) return;
+    if (plan->wstream) cudaFree(plan->wstream);
+    delete plan;
+}
+
 }  // namespace fvc

@@ -4,17 +4,20 @@
 
 namespace fvc {
 
-__device__ __forceinline__ void ep_load8(const __nv_bfloat16* rec, int Cp, int c0, float* v) {
+__device__ __forceinline__ void ep_load8(const e16* rec, int Cp, int c0, float* v) {
     uint4 h = *reinterpret_cast<const uint4*>(rec + c0);
     uint4 l = *reinterpret_cast<const uint4*>(rec + Cp + c0);
     const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        v[2 * j] = __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-        v[2 * j + 1] = __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+        float a, b, c, d;
+        e2f2(hh[j], a, b);
+        e2f2(ll[j], c, d);
+        v[2 * j] = a + c;
+        v[2 * j + 1] = b + d;
     }
 }
-__device__ __forceinline__ void ep_store8(__nv_bfloat16* rec, int Cp, int c0, const float* v, bool relu) {
+__device__ __forceinline__ void ep_store8(e16* rec, int Cp, int c0, const float* v, bool relu) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -23,11 +26,11 @@ __device__ __forceinline__ void ep_store8(__nv_bfloat16* rec, int Cp, int c0, co
             a = fmaxf(a, 0.f);
             b = fmaxf(b, 0.f);
         }
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(a, h0, l0);
-        split_bf16(b, h1, l1);
-        hi[j] = pack_bf16x2(h0, h1);
-        lo[j] = pack_bf16x2(l0, l1);
+        e16 h0, l0, h1, l1;
+        split16(a, h0, l0);
+        split16(b, h1, l1);
+        hi[j] = pack16x2(h0, h1);
+        lo[j] = pack16x2(l0, l1);
     }
     *reinterpret_cast<uint4*>(rec + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(rec + Cp + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -51,12 +54,12 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& ep, int Cout, int
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
             int c = co0 + j;
-            v[j] = (c < Cout) ? ep_act(v[j] + ep.bias[c], ep.act) : 0.f;
+            v[j] = (c < Cout) ? ep_act(v[j] * ep.acc_scale + ep.bias[c], ep.act) : 0.f;
         }
     }
     size_t pix = ((size_t)b * Hout + oy) * Wout + ox;
     if (ep.res_act.p) {
-        const __nv_bfloat16* rec = ep.res_act.p + act_pixel_offset(ep.res_act, b, oy, ox);
+        const e16* rec = ep.res_act.p + act_pixel_offset(ep.res_act, b, oy, ox);
 #pragma unroll
         for (int g = 0; g < NCH / 8; ++g) {
             if (co0 + g * 8 < ep.res_act.Cp) {
@@ -86,13 +89,13 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& ep, int Cout, int
         }
     }
     if (ep.out_act.p) {
-        __nv_bfloat16* rec = ep.out_act.p + act_pixel_offset(ep.out_act, b, oy, ox);
+        e16* rec = ep.out_act.p + act_pixel_offset(ep.out_act, b, oy, ox);
 #pragma unroll
         for (int g = 0; g < NCH / 8; ++g)
             if (co0 + g * 8 < ep.out_act.Cp) ep_store8(rec, ep.out_act.Cp, co0 + g * 8, v + g * 8, false);
     }
     if (ep.out_act_relu.p) {
-        __nv_bfloat16* rec = ep.out_act_relu.p + act_pixel_offset(ep.out_act_relu, b, oy, ox);
+        e16* rec = ep.out_act_relu.p + act_pixel_offset(ep.out_act_relu, b, oy, ox);
 #pragma unroll
         for (int g = 0; g < NCH / 8; ++g)
             if (co0 + g * 8 < ep.out_act_relu.Cp) ep_store8(rec, ep.out_act_relu.Cp, co0 + g * 8, v + g * 8, true);

@@ -156,16 +156,16 @@ int launch_flow_warp_nchw(const float* img, const float* flow, float* out, int B
 // ----------------------------------------------------------------------------------------------
 // record writers: one thread writes a whole Cp=32 record whose first `nv` channels are given
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_record32(__nv_bfloat16* rec, const float* v, int nv) {
-    // rec: 64 bf16 = 128 B: [hi 32][lo 32]
+__device__ __forceinline__ void store_record32(e16* rec, const float* v, int nv) {
+    // rec: 64 x 16 bit = 128 B: [hi 32][lo 32]
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        __nv_bfloat16 h0 = __float2bfloat16_rn(0.f), l0 = h0, h1 = h0, l1 = h0;
-        if (2 * j < nv) split_bf16(v[2 * j], h0, l0);
-        if (2 * j + 1 < nv) split_bf16(v[2 * j + 1], h1, l1);
-        hi[j] = pack_bf16x2(h0, h1);
-        lo[j] = pack_bf16x2(l0, l1);
+        e16 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+        if (2 * j < nv) split16(v[2 * j], h0, l0);
+        if (2 * j + 1 < nv) split16(v[2 * j + 1], h1, l1);
+        hi[j] = pack16x2(h0, h1);
+        lo[j] = pack16x2(l0, l1);
     }
     uint4* d = reinterpret_cast<uint4*>(rec);
 #pragma unroll
@@ -292,25 +292,28 @@ int launch_mc_finish(const float* res, const float* warpframe, const float* cur,
 // ----------------------------------------------------------------------------------------------
 // ACT helpers working on 8-channel groups (16-byte vectors of hi and of lo)
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load8(const __nv_bfloat16* rec, int Cp, int c8, float* v) {
+__device__ __forceinline__ void load8(const e16* rec, int Cp, int c8, float* v) {
     uint4 h = *reinterpret_cast<const uint4*>(rec + c8 * 8);
     uint4 l = *reinterpret_cast<const uint4*>(rec + Cp + c8 * 8);
     const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        v[2 * j] = __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-        v[2 * j + 1] = __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+        float a, b, c, d;
+        e2f2(hh[j], a, b);
+        e2f2(ll[j], c, d);
+        v[2 * j] = a + c;
+        v[2 * j + 1] = b + d;
     }
 }
-__device__ __forceinline__ void store8(__nv_bfloat16* rec, int Cp, int c8, const float* v) {
+__device__ __forceinline__ void store8(e16* rec, int Cp, int c8, const float* v) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * j], h0, l0);
-        split_bf16(v[2 * j + 1], h1, l1);
-        hi[j] = pack_bf16x2(h0, h1);
-        lo[j] = pack_bf16x2(l0, l1);
+        e16 h0, l0, h1, l1;
+        split16(v[2 * j], h0, l0);
+        split16(v[2 * j + 1], h1, l1);
+        hi[j] = pack16x2(h0, h1);
+        lo[j] = pack16x2(l0, l1);
     }
     *reinterpret_cast<uint4*>(rec + c8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(rec + Cp + c8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -430,8 +433,8 @@ __global__ void k_gdn_act(ActT in, int C, const float* __restrict__ beta, const 
     int x = (int)(i % in.W);
     int y = (int)((i / in.W) % in.H);
     int b = (int)(i / ((int64_t)in.W * in.H));
-    const __nv_bfloat16* rec = in.p + act_pixel_offset(in, b, y, x);
-    __nv_bfloat16* orec = out.p + act_pixel_offset(out, b, y, x);
+    const e16* rec = in.p + act_pixel_offset(in, b, y, x);
+    e16* orec = out.p + act_pixel_offset(out, b, y, x);
     float v[64], sq[64];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -453,7 +456,7 @@ __global__ void k_gdn_act(ActT in, int C, const float* __restrict__ beta, const 
                     if (c < C) acc = fmaf(gr[c], sq[c], acc);
                 float nrm = sqrtf(acc + sm[C * C + co]);
                 // v[co] with a runtime index would spill; recompute from the record instead
-                float xv = __bfloat162float(rec[co]) + __bfloat162float(rec[in.Cp + co]);
+                float xv = e2f(rec[co]) + e2f(rec[in.Cp + co]);
                 val = inverse ? xv * nrm : xv / nrm;
             }
             r[j] = val;
