@@ -45,6 +45,7 @@ _SIGNATURES = {
     "fvc_gop_forward_host": (_i, [C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, _s]),
     "fvc_ctx_launch_count": (_l, [C.c_void_p]),
     "fvc_ctx_last_conv_seconds": (C.c_double, [C.c_void_p]),
+    "fvc_ctx_profile_text": (C.c_char_p, [C.c_void_p]),
 }
 
 

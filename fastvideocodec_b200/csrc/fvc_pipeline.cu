@@ -71,7 +71,9 @@ struct fvc_ctx {
     bool profile = false;
     double last_conv_seconds = -1.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
+    std::vector<std::string> conv_event_names;
     size_t conv_event_used = 0;
+    std::string profile_text;
 
     // ---- buffers ---------------------------------------------------------------------------
     std::vector<float*> pyr1, pyr2;                 // planar pyramids, scale 1..levels-1 (scale 0 = user ptr)
@@ -337,6 +339,8 @@ static int run_conv(fvc_ctx* c, const std::string& name, ActT in, int Hout, int 
         }
         e0 = c->conv_events[c->conv_event_used].first;
         e1 = c->conv_events[c->conv_event_used].second;
+        if (c->conv_event_names.size() <= c->conv_event_used) c->conv_event_names.resize(c->conv_event_used + 1);
+        c->conv_event_names[c->conv_event_used] = name;
         c->conv_event_used++;
         FVC_CUDA(cudaEventRecord(e0, s));
     }
@@ -690,10 +694,14 @@ int fvc_pframe_forward(fvc_ctx* c, const float* cur, const float* ref, float* re
     if (rc == 0 && c->profile) {
         FVC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
         double tot = 0;
+        c->profile_text.clear();
+        char line[192];
         for (size_t i = 0; i < c->conv_event_used; ++i) {
             float ms = 0;
             cudaEventElapsedTime(&ms, c->conv_events[i].first, c->conv_events[i].second);
             tot += ms * 1e-3;
+            snprintf(line, sizeof(line), "%s %.4f\n", c->conv_event_names[i].c_str(), ms);
+            c->profile_text += line;
         }
         c->last_conv_seconds = tot;
     }
@@ -701,6 +709,7 @@ int fvc_pframe_forward(fvc_ctx* c, const float* cur, const float* ref, float* re
 }
 
 int64_t fvc_ctx_launch_count(fvc_ctx* c) { return c ? c->launches : -1; }
+const char* fvc_ctx_profile_text(fvc_ctx* c) { return c ? c->profile_text.c_str() : ""; }
 double fvc_ctx_last_conv_seconds(fvc_ctx* c) { return c ? c->last_conv_seconds : -1.0; }
 
 int64_t fvc_ctx_get_tensor(fvc_ctx* c, const char* name_c, float* out, int64_t capacity, void* stream) {

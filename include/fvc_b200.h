@@ -148,6 +148,8 @@ FVC_API int64_t fvc_ctx_launch_count(fvc_ctx* ctx);
 /* Dominant-kernel timing hook for bench.py: seconds spent in convolution kernels during the last
  * fvc_pframe_forward when FVC_PROFILE=1 was set at create time (uses CUDA events; else -1). */
 FVC_API double fvc_ctx_last_conv_seconds(fvc_ctx* ctx);
+/* Per-layer convolution times of the last profiled forward: lines "<layer> <ms>" (FVC_PROFILE=1). */
+FVC_API const char* fvc_ctx_profile_text(fvc_ctx* ctx);
 
 #ifdef __cplusplus
 }
