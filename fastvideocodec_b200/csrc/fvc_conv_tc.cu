@@ -20,7 +20,7 @@
 //     of taps): two partial-accumulator buffers ping-pong, and 16 accumulator warps drain each
 //     finished partial with tcgen05.ld and add it to a running sum in registers in fp32
 //     round-to-nearest, overlapped with the MMAs of the next group.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..19 =
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..17 =
 //     accumulator/epilogue warps (drain -> running sum -> bias/activation/residual -> hi/lo split
 //     -> global).  Persistent over tiles.
 #include <cuda.h>
@@ -38,7 +38,7 @@ namespace fvc {
 // ----------------------------------------------------------------------------------------------
 #define TC_MAX_PASS 16
 #define TC_MAX_TAPS 64
-#define TC_THREADS 640
+#define TC_THREADS 576   // 18 warps; 96 registers per thread (allocation granularity is 4 warps)
 
 struct TcPass {
     int8_t seg, plane;     // record segment (128 B unit) and parity plane (0 for stride-1 inputs)
@@ -46,6 +46,7 @@ struct TcPass {
     int16_t tap_first, ntaps;
     int8_t nbt, ks0, ks1;  // weight tiles per tap and their k-step counts (16 channels per k-step)
     int8_t gtaps;          // taps per accumulation group (one TMEM chain, drained to registers)
+    uint32_t btile_first;  // first weight tile of the pass in the stream
 };
 struct TcSub {
     int pass_first, npass, py, px;
@@ -60,9 +61,10 @@ struct alignas(64) TcParams {
     int32_t tap_off[TC_MAX_TAPS];  // byte offset of the tap's window inside the patch
     int nsub, S, SX, N, PW, PH, nst, CT;   // CT = S*N accumulator columns per partial buffer
     int Hq, Wq, tiles_x, tiles_y, B, os, Hout, Wout, Cout, nchunks;
-    uint32_t patch_bytes, patch_tx, btile_bytes, tmem_cols, idesc;
+    uint32_t patch_bytes, patch_tx, btile_bytes, stage_bytes, tmem_cols, idesc;
+    int npb, T;       // patch buffers (1 or 2), weight tiles per stage
+    uint32_t zero;    // always 0 (opaque to the compiler: used to build false dependencies)
     int planes;       // 1 or 4 (parity-planar input)
-    int bo_mode;      // 0: base_offset field = 0, 1: (addr >> 7) & 7
     Epilogue ep;
 };
 
@@ -91,15 +93,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug traps instead of hanging the GPU
+// bounded wait: a protocol bug traps instead of hanging the GPU.  (No printf here: a call in the slow
+// path makes the compiler spill every live accumulator around each wait.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
-            printf("fvc tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-                   bar, parity);
-            __trap();
-        }
+        if (++spins > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
@@ -155,18 +154,40 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+// one thread of a converged warp; the compiler then knows the branch is single-threaded and keeps
+// descriptors in uniform registers (no per-instruction waterfall as with `lane == 0`)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, int bo_mode) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);                 // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                                   // leading byte offset (ignored, K-major swizzled)
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;        // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                                   // descriptor version 1 (Blackwell)
-    if (bo_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;    // base offset, bits [49,52)
     d |= (uint64_t)2 << 61;                                   // SWIZZLE_128B
     return d;
+}
+
+// All MMAs of one weight stage: S sub-tiles x KS k-steps, straight-line (the issuing thread is the
+// bottleneck otherwise: ncu showed ~15 scalar instructions per MMA with runtime loops).
+template <int KS>
+__device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint64_t ad, uint64_t bd, uint32_t idesc,
+                                            uint32_t acc0, int S) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (s < S) {
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+                tc_mma(dcol + (uint32_t)s * N, ad + (uint64_t)(64 * s + 2 * k), bd + (uint64_t)(2 * k), idesc,
+                       k == 0 ? acc0 : 1u);
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -192,18 +213,138 @@ struct PassIter {
     }
 };
 
-template <int NCH>   // 8-column chunks of the running sum each accumulator thread owns (CT/4 = 8*NCH)
+// Tile epilogue of one accumulator thread: NCH chunks of 8 consecutive accumulator columns.  Global
+// loads (residual) of a batch of chunks are all issued before any of them is consumed and before the
+// batch's stores, so a thread pays one memory round trip per batch instead of one per chunk
+// (ncu: the per-chunk version was stall_long_sb-bound and starved the MMA pipe).
+template <int NCH, bool RES>
+__device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __restrict__ bias_s, const float* run,
+                                              int b, int sub, int ty, int tx, int th, int tw, uint32_t colbase) {
+    const Epilogue& ep = P.ep;
+    constexpr int HB = NCH > 4 ? 2 : NCH;   // chunks per batch (register budget: 96 regs at 576 threads)
+    const int N = P.N, Cout = P.Cout, act = ep.act;
+    const float acc_scale = ep.acc_scale;
+    const int qy = ty * 16 + th;
+    const int oy = qy * P.os + P.sub[sub].py;
+    const bool row_ok = qy < P.Hq;
+    int s0 = (int)colbase / N, c00 = (int)colbase - s0 * N;
+    // per-pixel state, recomputed only when the chunk sequence moves to the next sub-tile
+    int cur_s = -1;
+    bool ok = false;
+    e16 *rec_out = nullptr, *rec_relu = nullptr;
+    const e16* rec_res = nullptr;
+    size_t pixC = 0;   // pixel index * Cout (fp32 NHWC tensors)
+    auto enter_pixel = [&](int s) {
+        cur_s = s;
+        const int qx = (tx * P.SX + s) * 8 + tw;
+        const int ox = qx * P.os + P.sub[sub].px;
+        ok = row_ok && qx < P.Wq;
+        if (!ok) return;
+        if (ep.out_act.p) rec_out = ep.out_act.p + act_pixel_offset(ep.out_act, b, oy, ox);
+        if (ep.out_act_relu.p) rec_relu = ep.out_act_relu.p + act_pixel_offset(ep.out_act_relu, b, oy, ox);
+        if (RES) rec_res = ep.res_act.p + act_pixel_offset(ep.res_act, b, oy, ox);
+        pixC = (((size_t)b * P.Hout + oy) * P.Wout + ox) * (size_t)Cout;
+    };
+#pragma unroll
+    for (int h0 = 0; h0 < NCH; h0 += HB) {
+        uint4 rh[HB], rl[HB];
+        int cc[HB], ss[HB];
+        // ---- phase 1: residual loads of the whole batch (one memory round trip per batch) ------------
+#pragma unroll
+        for (int j = 0; j < HB; ++j) {
+            cc[j] = c00;
+            ss[j] = s0;
+            if (RES) {
+                if (s0 != cur_s) enter_pixel(s0);
+                rh[j] = make_uint4(0, 0, 0, 0);
+                rl[j] = make_uint4(0, 0, 0, 0);
+                if (ok && c00 < ep.res_act.Cp) {
+                    rh[j] = __ldg(reinterpret_cast<const uint4*>(rec_res + c00));
+                    rl[j] = __ldg(reinterpret_cast<const uint4*>(rec_res + ep.res_act.Cp + c00));
+                }
+            }
+            c00 += 8;
+            if (c00 >= N) { c00 -= N; ++s0; }
+        }
+        // ---- phase 2: bias, activation, residual, stores --------------------------------------------
+        // (bias_s is zero beyond Cout and those accumulators are exact zeros: no per-element channel
+        // masks; the activation is selected once per chunk, not per element)
+#pragma unroll
+        for (int j = 0; j < HB; ++j) {
+            if (ss[j] != cur_s) enter_pixel(ss[j]);
+            if (!ok) continue;
+            const int c0 = cc[j];
+            float v[8];
+            {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = fmaf(run[(h0 + j) * 8 + q], acc_scale, bb[q]);
+            }
+            if (act == FVC_ACT_RELU) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+            } else if (act == FVC_ACT_LRELU01) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * 0.1f;
+            } else if (act == FVC_ACT_EXP) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = expf(v[q]);
+            }
+            if (RES) {
+                const uint32_t hh[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w}, ll[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float a0, a1, b0, b1;
+                    e2f2(hh[q], a0, a1);
+                    e2f2(ll[q], b0, b1);
+                    v[2 * q] += a0 + b0;
+                    v[2 * q + 1] += a1 + b1;
+                }
+            }
+            if (ep.res_f32) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (c0 + q < Cout) v[q] += ep.res_f32[pixC + c0 + q];
+            }
+            if (ep.out_f32) {
+                if ((Cout & 3) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 8; q += 4)
+                        if (c0 + q < Cout)
+                            *reinterpret_cast<float4*>(ep.out_f32 + pixC + c0 + q) =
+                                make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (c0 + q < Cout) ep.out_f32[pixC + c0 + q] = v[q];
+                }
+            }
+            if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false);
+            if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp)
+                ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true);
+        }
+    }
+}
+
+// Warp roles: 0 = TMA producer (weight stream + patches), 1 = MMA issuer (+ TMEM alloc),
+// 2..17 = accumulator / epilogue warps (any 16 consecutive warps cover every TMEM lane quarter 4 times).
+// NCH: 8-column chunks of the running sum each accumulator thread owns (CT/4 = 8*NCH);
+// RES: the epilogue adds an ACT-format residual (ResBlock skip connection)
+template <int NCH, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: SWIZZLE_128B atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t patch0 = base;                                   // 2 patch sets
-    const uint32_t bst0 = base + 2 * P.patch_bytes;                 // nst weight stages
-    const uint32_t bars = bst0 + P.nst * P.btile_bytes;             // mbarriers (8 B each)
-    const uint32_t bar_pfull = bars, bar_pempty = bars + 16;        // [2] each
+    const uint32_t patch0 = base;                                   // npb patch buffers
+    const uint32_t bst0 = base + P.npb * P.patch_bytes;             // nst weight stages of T tiles
+    const uint32_t bars = bst0 + P.nst * P.stage_bytes;             // mbarriers (8 B each)
+    const uint32_t bar_pfull = bars, bar_pempty = bars + 16;        // [npb <= 2] each
     const uint32_t bar_bfull = bars + 32, bar_bempty = bars + 32 + 8 * 8;   // [nst <= 8] each
     const uint32_t bar_afull = bars + 32 + 16 * 8, bar_aempty = bar_afull + 16;  // partial buffers [2] each
     const uint32_t tmem_slot = bar_aempty + 16;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 256);   // [N <= 128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;
@@ -227,6 +368,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (threadIdx.x >= 64 && (int)threadIdx.x - 64 < P.N) {
+        const int c = (int)threadIdx.x - 64;
+        bias_s[c] = c < P.Cout ? P.ep.bias[c] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -234,113 +379,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        // ================================ TMA producer ==========================================
-        if (lane == 0) {
-            PassIter cur, nxt;
-            cur.tile = blockIdx.x; cur.pass = 0; cur.decode(P);
-            uint32_t gp = 0;       // global pass counter (patch ring position)
-            uint32_t gb = 0;       // global weight-stage counter
-            auto issue_patch = [&](const PassIter& it, uint32_t g) {
-                const TcPass& ps = P.pass[P.sub[it.sub].pass_first + it.pass];
-                const uint32_t set = g & 1u, ph = (g >> 1) & 1u;
-                mbar_wait(bar_pempty + 8 * set, ph ^ 1u);
-                mbar_expect_tx(bar_pfull + 8 * set, P.patch_tx);
-                int x0 = it.tx * 8 * P.SX + ps.ox, y0 = it.ty * 16 + ps.oy;
-                tma_load_5d(patch0 + set * P.patch_bytes, &P.mapA, bar_pfull + 8 * set, 0, ps.seg, x0, y0,
-                            it.b * P.planes + ps.plane);
-            };
-            if (cur.valid(ntiles)) issue_patch(cur, gp);
-            while (cur.valid(ntiles)) {
-                const TcSub& sb = P.sub[cur.sub];
-                const TcPass& ps = P.pass[sb.pass_first + cur.pass];
-                // weight tiles of this pass: contiguous in the stream
-                uint32_t bt = sb.btile_first;
-                for (int q = 0; q < cur.pass; ++q) {
-                    const TcPass& pq = P.pass[sb.pass_first + q];
-                    bt += (uint32_t)pq.ntaps * pq.nbt;
+        // ================= TMA producer: weight-stream ring + patch ring, polled by one thread ==========
+        // Two independent iterators; whichever ring has a free slot is served (a blocking wait on one
+        // ring would starve the other: the patch of the next pass frees only when the current pass ends).
+        if (elect_one()) {
+            PassIter wc, pc;
+            wc.tile = blockIdx.x; wc.pass = 0; wc.decode(P);
+            pc = wc;
+            uint32_t st = 0, stph = 0;   // weight-stage ring position and its phase bit
+            uint32_t set = 0, pph = 0;   // patch ring
+            const uint32_t nst = (uint32_t)P.nst, npb = (uint32_t)P.npb;
+            const int T = P.T;
+            int wi = 0;                  // next weight tile of wc's pass
+            uint32_t spins = 0;
+            while (wc.valid(ntiles) || pc.valid(ntiles)) {
+                bool progress = false;
+                if (pc.valid(ntiles) && mbar_try_wait(bar_pempty + 8 * set, pph ^ 1u)) {
+                    const TcPass& ps = P.pass[P.sub[pc.sub].pass_first + pc.pass];
+                    mbar_expect_tx(bar_pfull + 8 * set, P.patch_tx);
+                    const int x0 = pc.tx * 8 * P.SX + ps.ox, y0 = pc.ty * 16 + ps.oy;
+                    tma_load_5d(patch0 + set * P.patch_bytes, &P.mapA, bar_pfull + 8 * set, 0, ps.seg, x0, y0,
+                                pc.b * P.planes + ps.plane);
+                    if (++set == npb) { set = 0; pph ^= 1u; }
+                    pc.next(P, gridDim.x);
+                    progress = true;
                 }
-                const int nb = ps.ntaps * ps.nbt;
-                nxt = cur;
-                nxt.next(P, gridDim.x);
-                const int pref = min(P.nst - 1, nb - 1);
-                for (int i = 0; i < nb; ++i) {
-                    if (i == pref && nxt.valid(ntiles)) issue_patch(nxt, gp + 1);
-                    const uint32_t st = gb % P.nst, ph = (gb / P.nst) & 1u;
-                    mbar_wait(bar_bempty + 8 * st, ph ^ 1u);
-                    mbar_expect_tx(bar_bfull + 8 * st, P.btile_bytes);
-                    tma_load_2d(bst0 + st * P.btile_bytes, &P.mapB, bar_bfull + 8 * st, 0, (int)((bt + i) * P.N));
-                    ++gb;
+                if (wc.valid(ntiles) && mbar_try_wait(bar_bempty + 8 * st, stph ^ 1u)) {
+                    const TcPass& ps = P.pass[P.sub[wc.sub].pass_first + wc.pass];
+                    // T weight tiles per stage; the last stage of a pass over-reads (the stream is padded)
+                    mbar_expect_tx(bar_bfull + 8 * st, P.stage_bytes);
+                    tma_load_2d(bst0 + st * P.stage_bytes, &P.mapB, bar_bfull + 8 * st, 0,
+                                (int)((ps.btile_first + (uint32_t)wi) * (uint32_t)P.N));
+                    if (++st == nst) { st = 0; stph ^= 1u; }
+                    wi += T;
+                    if (wi >= ps.ntaps * ps.nbt) { wi = 0; wc.next(P, gridDim.x); }
+                    progress = true;
                 }
-                ++gp;
-                cur = nxt;
+                if (progress) spins = 0;
+                else if (++spins > (1u << 25)) __trap();
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer =============================================
-        if (lane == 0) {
+        if (elect_one()) {
             PassIter cur;
             cur.tile = blockIdx.x; cur.pass = 0; cur.decode(P);
-            uint32_t gp = 0, gb = 0, gg = 0;   // pass, weight-stage and accumulation-group counters
-            const uint32_t sbo = (uint32_t)P.PW * 128u;
+            uint32_t gg = 0;                    // accumulation-group counter
+            uint32_t set = 0, pph = 0;          // patch ring
+            uint32_t st = 0, stph = 0;          // weight-stage ring position and its phase bit
+            // descriptors: everything but the start address is fixed; per MMA only the low word moves
+            const uint64_t adesc0 = make_desc(0, (uint32_t)P.PW * 128u);
+            const uint64_t bdesc0 = make_desc(0, 1024u);
+            const int S = P.S, T = P.T;
+            const uint32_t N = (uint32_t)P.N, nst = (uint32_t)P.nst, CT = (uint32_t)P.CT, npb = (uint32_t)P.npb;
+            const uint32_t idesc = P.idesc, btile16 = P.btile_bytes >> 4;
             while (cur.valid(ntiles)) {
                 const TcSub& sb = P.sub[cur.sub];
                 const TcPass& ps = P.pass[sb.pass_first + cur.pass];
-                const uint32_t set = gp & 1u;
-                mbar_wait(bar_pfull + 8 * set, (gp >> 1) & 1u);
+                mbar_wait(bar_pfull + 8 * set, pph);
                 tc_fence_after();
                 const uint32_t pbase = patch0 + set * P.patch_bytes;
-                for (int t0 = 0; t0 < ps.ntaps; t0 += ps.gtaps) {
-                    const int t1 = min(t0 + (int)ps.gtaps, (int)ps.ntaps);
+                const int ntaps = ps.ntaps, gtaps = ps.gtaps, nbt = ps.nbt, ks1 = ps.ks1;
+                const int32_t* toffp = P.tap_off + ps.tap_first;
+                int slot = 0;                   // tile index inside the current weight stage
+                uint64_t bd = 0;
+                for (int t0 = 0; t0 < ntaps; t0 += gtaps) {
+                    const int t1 = min(t0 + gtaps, ntaps);
                     // partial buffer must have been drained by the accumulator warps
                     const uint32_t pb = gg & 1u;
                     mbar_wait(bar_aempty + 8 * pb, ((gg >> 1) & 1u) ^ 1u);
                     tc_fence_after();
+                    const uint32_t dcol = tmem_base + pb * CT;
                     for (int t = t0; t < t1; ++t) {
-                        const uint32_t toff = (uint32_t)P.tap_off[ps.tap_first + t];
-                        for (int j = 0; j < ps.nbt; ++j) {
-                            const uint32_t st = gb % P.nst;
-                            mbar_wait(bar_bfull + 8 * st, (gb / P.nst) & 1u);
-                            tc_fence_after();
-                            const uint32_t bbase = bst0 + st * P.btile_bytes;
-                            const int ks = j == 0 ? ps.ks0 : ps.ks1;
-                            const bool first = (t == t0 && j == 0);
-                            for (int s = 0; s < P.S; ++s) {
-                                const uint32_t abase = pbase + toff + (uint32_t)s * 8u * 128u;
-                                const uint32_t dcol = tmem_base + pb * P.CT + s * P.N;
-                                for (int k = 0; k < ks; ++k) {
-                                    uint64_t ad = make_desc(abase + k * 32u, sbo, P.bo_mode);
-                                    uint64_t bd = make_desc(bbase + k * 32u, 1024u, 0);
-                                    tc_mma(dcol, ad, bd, P.idesc, (first && k == 0) ? 0u : 1u);
-                                }
+                        const uint64_t ad = adesc0 + (uint64_t)((pbase + (uint32_t)toffp[t]) >> 4);
+                        for (int j = 0; j < nbt; ++j) {
+                            if (slot == 0) {
+                                mbar_wait(bar_bfull + 8 * st, stph);
+                                tc_fence_after();
+                                bd = bdesc0 + (uint64_t)((bst0 + st * P.stage_bytes) >> 4);
                             }
-                            tc_commit(bar_bempty + 8 * st);   // frees the weight stage when these MMAs retire
-                            ++gb;
+                            const uint32_t acc0 = (t == t0 && j == 0) ? 0u : 1u;
+                            // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
+                            if (j == 0 || ks1 == 4) issue_stage<4>(dcol, N, ad, bd, idesc, acc0, S);
+                            else issue_stage<2>(dcol, N, ad, bd, idesc, acc0, S);
+                            bd += btile16;
+                            if (++slot == T || (t == ntaps - 1 && j == nbt - 1)) {
+                                tc_commit(bar_bempty + 8 * st);   // frees the weight stage when these MMAs retire
+                                if (++st == nst) { st = 0; stph ^= 1u; }
+                                slot = 0;
+                            }
                         }
                     }
                     tc_commit(bar_afull + 8 * pb);            // short chain complete -> accumulator warps
                     ++gg;
                 }
-                tc_commit(bar_pempty + 8 * set);              // patch set reusable
-                ++gp;
+                tc_commit(bar_pempty + 8 * set);              // patch buffer reusable
+                if (++set == npb) { set = 0; pph ^= 1u; }
                 cur.next(P, gridDim.x);
             }
         }
-    } else if (warp >= 4) {
-        // ======================= accumulator / epilogue warps (16) =================================
+    } else if (warp >= 2) {
+        // ======================= accumulator / epilogue warps (16: warps 2..17) ====================
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
-        const int part = (warp - 4) >> 2;                 // which quarter of the CT columns
+        const int part = (warp - 2) >> 2;                 // which quarter of the CT columns
         const int row = quarter * 32 + lane;              // accumulator row = pixel inside the sub-tile
         const int th = row >> 3, tw = row & 7;
         const uint32_t colbase = (uint32_t)part * (uint32_t)(NCH * 8);
         uint32_t gg = 0;
         float run[NCH * 8];
+        const int tiles_xy = P.tiles_x * P.tiles_y;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            int t = tile;
-            const int tx = t % P.tiles_x; t /= P.tiles_x;
-            const int ty = t % P.tiles_y; t /= P.tiles_y;
-            const int sub = t % P.nsub;
-            const int b = t / P.nsub;
-            const int ng = P.sub[sub].ngroups;
+            const int ng = P.sub[(tile / tiles_xy) % P.nsub].ngroups;
             for (int g = 0; g < ng; ++g, ++gg) {
                 const uint32_t pb = gg & 1u;
                 mbar_wait(bar_afull + 8 * pb, (gg >> 1) & 1u);
@@ -349,7 +498,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     float v[8];
-                    tc_ld8(taddr + i * 8, reinterpret_cast<uint32_t*>(v));
+                    // At most two TMEM loads in flight: the address of load i carries a (zero) dependency on
+                    // the sums of chunk i-2.  Unconstrained, ptxas issues 4+ loads back to back and then
+                    // spills the 64 running sums around every group (seen in SASS).
+                    uint32_t dep = 0;
+                    if (NCH > 4 && i >= 2) dep = __float_as_uint(run[(i - 2) * 8]) & P.zero;
+                    tc_ld8(taddr + i * 8 + dep, reinterpret_cast<uint32_t*>(v));
                     tc_wait_ld();
                     if (g == 0) {
 #pragma unroll
@@ -363,17 +517,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
             }
-            // ---- epilogue from registers ----
-            const int qy = ty * 16 + th;
-#pragma unroll
-            for (int i = 0; i < NCH; ++i) {
-                const int col = (int)colbase + i * 8;
-                const int s = col / P.N, c0 = col - s * P.N;
-                const int qx = (tx * P.SX + s) * 8 + tw;
-                if (qy < P.Hq && qx < P.Wq)
-                    epilogue_apply<8>(P.ep, P.Cout, P.Hout, P.Wout, b, qy * P.os + P.sub[sub].py,
-                                      qx * P.os + P.sub[sub].px, c0, run + i * 8);
-            }
+            // tile coordinates are decoded only now (laundered through an empty asm) so that the epilogue's
+            // address arithmetic cannot be hoisted above the drain loop, where it would spill `run`
+            int t = tile;
+            asm volatile("" : "+r"(t));
+            const int tx = t % P.tiles_x; t /= P.tiles_x;
+            const int ty = t % P.tiles_y; t /= P.tiles_y;
+            const int sub = t % P.nsub;
+            const int b = t / P.nsub;
+            tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
         }
     }
     tc_fence_before();
@@ -507,7 +659,6 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     P.Hq = Hout / L.os; P.Wq = Wout / L.os;
     P.B = in.B;
     P.planes = (L.st == 2) ? 4 : 1;
-    P.bo_mode = env_int("FVC_TC_BO_MODE", 0);
     P.ep = ep;
 
     // ---- passes: (segment, plane) x taps ---------------------------------------------------------
@@ -548,37 +699,45 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     }
     // ---- tile shape -------------------------------------------------------------------------------
     const int pw_align = env_int("FVC_TC_PW_ALIGN", 1);
-    const int smem_cap = 232448 - 2048;
-    int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y;
+    const int smem_cap = 232448 - 1024 /*alignment*/ - 1024 /*barriers + bias*/;
+    const int tile_bytes = N * 128;
+    int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y, npb = 2, T = 1;
     // S*N accumulator columns per partial buffer, CT/32 in {1,2,3,4,6,8} (template instantiations),
-    // CT <= 256 (two partial buffers in 512 TMEM columns, <= 128 running-sum registers per thread)
-    const int sx_max = std::min(env_int("FVC_TC_SX", 4), 256 / N);
-    for (int sx = std::max(1, sx_max); sx >= 1; --sx) {
+    // CT <= 256 (two partial buffers in 512 TMEM columns, <= 64 running-sum registers per thread).
+    // Prefer the largest S (weights are re-read once per tile).  Two patch buffers when that still
+    // leaves room for a deep weight ring; otherwise one (big-halo 7x7 layers: the exposed patch load is
+    // a few % of a pass, a starved weight ring costs far more).
+    // (residual epilogues keep CT <= 192: 48 running sums leave registers for the prefetched skip data)
+    const int sx_max = std::min(env_int("FVC_TC_SX", 4), (ep.res_act.p ? 192 : 256) / N);
+    const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), 256 / N));
+    for (int sx = std::max(1, sx_max); sx >= 1 && !SX; --sx) {
         const int ct32 = sx * N / 32;
-        if ((sx * N) % 32 != 0 || !(ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
+        if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * 128;
         patch = (patch + 1023) & ~(size_t)1023;
-        for (int st = 6; st >= 2; --st) {
-            size_t need = 2 * patch + (size_t)st * N * 128 + 1024;
-            if ((int)need <= smem_cap) {
-                SX = sx; nst = st; PW = pw;
-                break;
-            }
+        for (int nb = 2; nb >= 1 && !SX; --nb) {
+            const long wroom = (long)smem_cap - (long)nb * (long)patch;
+            const long want = nb == 2 ? std::min<long>(48 * 1024, 6L * tile_bytes) : 2L * tile_bytes;
+            if (wroom < want) continue;
+            int t = (int)std::max<long>(1, std::min<long>(tmax, wroom / (4L * tile_bytes)));
+            int st = (int)std::min<long>(8, wroom / ((long)t * tile_bytes));
+            if (st < 2) continue;
+            SX = sx; nst = st; PW = pw; npb = nb; T = t;
         }
-        if (SX) break;
     }
     if (!SX) {
         set_error("tc_plan_create: no tile shape fits shared memory");
         delete plan;
         return FVC_ERR_STATE;
     }
-    P.S = SX; P.SX = SX; P.PW = PW; P.PH = PH; P.nst = nst;
+    P.S = SX; P.SX = SX; P.PW = PW; P.PH = PH; P.nst = nst; P.npb = npb; P.T = T;
     P.CT = SX * N;
     P.patch_bytes = (uint32_t)((((size_t)PH * PW * 128) + 1023) & ~(size_t)1023);
     P.patch_tx = (uint32_t)((size_t)PH * PW * 128);
     P.btile_bytes = (uint32_t)N * 128u;
+    P.stage_bytes = (uint32_t)T * P.btile_bytes;
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * P.CT)) cols <<= 1;
     P.tmem_cols = cols;
@@ -628,6 +787,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
                     ps.gtaps = (int8_t)std::max(1, std::min(127, chain_max / per_tap));
                 }
                 ps.tap_first = (int16_t)g.tap_first;
+                ps.btile_first = (uint32_t)binfo.size();
                 for (auto& tp : g.taps) {
                     binfo.push_back({(int8_t)tp.r, (int8_t)tp.s, (uint8_t)sp.kind0, (uint8_t)sp.c0});
                     if (sp.nbt == 2) binfo.push_back({(int8_t)tp.r, (int8_t)tp.s, (uint8_t)sp.kind1, (uint8_t)sp.c0});
@@ -641,9 +801,11 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
 
     // ---- weight stream -------------------------------------------------------------------------------
     const int nbt_total = (int)binfo.size();
-    size_t wbytes = (size_t)nbt_total * N * 64 * sizeof(e16);
+    // padded by T tiles: the last weight stage of a pass always loads a full T-tile box
+    size_t wbytes = (size_t)(nbt_total + T) * N * 64 * sizeof(e16);
     BTileInfo* dinfo = nullptr;
     cudaError_t ce = cudaMalloc(&plan->wstream, wbytes);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(plan->wstream, 0, wbytes, s);
     if (ce == cudaSuccess) ce = cudaMalloc(&dinfo, binfo.size() * sizeof(BTileInfo));
     if (ce == cudaSuccess)
         ce = cudaMemcpyAsync(dinfo, binfo.data(), binfo.size() * sizeof(BTileInfo), cudaMemcpyHostToDevice, s);
@@ -711,9 +873,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             delete plan;
             return FVC_ERR_CUDA;
         }
-        cuuint64_t bdims[2] = {64, (cuuint64_t)nbt_total * N};
+        cuuint64_t bdims[2] = {64, (cuuint64_t)(nbt_total + T) * N};
         cuuint64_t bstr[1] = {128};
-        cuuint32_t bbox[2] = {64, (cuuint32_t)N};
+        cuuint32_t bbox[2] = {64, (cuuint32_t)(T * N)};
         cuuint32_t bes[2] = {1, 1};
         r = encode(&P.mapB, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, (void*)plan->wstream, bdims, bstr, bbox, bes,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -725,7 +887,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             return FVC_ERR_CUDA;
         }
     }
-    plan->smem = 1024 + 2 * (size_t)P.patch_bytes + (size_t)nst * P.btile_bytes + 512;
+    plan->smem = 1024 + (size_t)npb * P.patch_bytes + (size_t)nst * P.stage_bytes + 1024;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -735,22 +897,28 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     return 0;
 }
 
-template <int NCH>
-static int tc_launch_t(TcPlan* plan, cudaStream_t s) {
+template <int NCH, bool RES>
+static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set = true;
     }
-    k_conv_tc<NCH><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->P);
+    k_conv_tc<NCH, RES><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->P);
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
 }
 
+template <int NCH>
+static int tc_launch_t(TcPlan* plan, cudaStream_t s) {
+    return plan->P.ep.res_act.p ? tc_launch_t2<NCH, true>(plan, s) : tc_launch_t2<NCH, false>(plan, s);
+}
+
 int tc_plan_launch(TcPlan* plan, cudaStream_t s) {
     FVC_ARG(plan != nullptr);
     switch (plan->P.CT / 32) {
+        case 1: return tc_launch_t<1>(plan, s);
         case 2: return tc_launch_t<2>(plan, s);
         case 3: return tc_launch_t<3>(plan, s);
         case 4: return tc_launch_t<4>(plan, s);

@@ -36,6 +36,36 @@ __device__ __forceinline__ void ep_store8(e16* rec, int Cp, int c0, const float*
     *reinterpret_cast<uint4*>(rec + Cp + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+
+// Packed split of 8 floats into hi/lo 16-bit pairs: one F2FP per two elements for hi, one for lo
+// (6 instructions per pair instead of ~14 for the scalar split16 path).
+__device__ __forceinline__ uint32_t ep_pack2(float a, float b) {
+    uint32_t r;
+#if FVC_SPLIT_FP16
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a
+#else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+#endif
+    return r;
+}
+__device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const float* v, bool relu) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = v[2 * j], b = v[2 * j + 1];
+        if (relu) {
+            a = fmaxf(a, 0.f);
+            b = fmaxf(b, 0.f);
+        }
+        hi[j] = ep_pack2(a, b);
+        float ha, hb;
+        e2f2(hi[j], ha, hb);
+        lo[j] = ep_pack2(a - ha, b - hb);
+    }
+    *reinterpret_cast<uint4*>(rec + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(rec + Cp + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 __device__ __forceinline__ float ep_act(float v, int act) {
     switch (act) {
         case FVC_ACT_RELU: return fmaxf(v, 0.f);
