@@ -38,7 +38,7 @@ namespace fvc {
 // ----------------------------------------------------------------------------------------------
 #define TC_MAX_PASS 16
 #define TC_MAX_TAPS 64
-#define TC_THREADS 576   // 18 warps; 96 registers per thread (allocation granularity is 4 warps)
+#define TC_THREADS 608   // 19 warps; 96 registers per thread (allocation granularity is 4 warps)
 
 struct TcPass {
     int8_t seg, plane;     // record segment (128 B unit) and parity plane (0 for stride-1 inputs)
@@ -64,6 +64,8 @@ struct alignas(64) TcParams {
     uint32_t patch_bytes, patch_tx, btile_bytes, stage_bytes, tmem_cols, idesc;
     int npb, T;       // patch buffers (1 or 2), weight tiles per stage
     uint32_t zero;    // always 0 (opaque to the compiler: used to build false dependencies)
+    uint32_t acc_sleep_ns;
+    unsigned long long* dbg;   // optional [8] cycle counters of block 0's MMA issuer (FVC_TC_DEBUG=1)
     int planes;       // 1 or 4 (parity-planar input)
     Epilogue ep;
 };
@@ -99,6 +101,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
+    }
+}
+// polite wait for warps that are off the critical path (16 accumulator warps polling at full speed
+// take issue slots from the MMA issuer warp that shares their scheduler)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (++spins > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
@@ -161,6 +172,12 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version 1)
@@ -174,18 +191,33 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
     return d;
 }
 
-// All MMAs of one weight stage: S sub-tiles x KS k-steps, straight-line (the issuing thread is the
-// bottleneck otherwise: ncu showed ~15 scalar instructions per MMA with runtime loops).
+// tcgen05.mma with the descriptors given as (low word, high word): the high words are loop constants
+// and the low words move by small immediates, so the issuing thread does 32-bit adds only.
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                        uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+// All MMAs of one weight tile: S sub-tiles x KS k-steps, straight-line (the issuing thread is the
+// bottleneck otherwise: the MMA queue is shallow, every scalar instruction between MMAs shows up as
+// tensor-pipe idle time).
 template <int KS>
-__device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint64_t ad, uint64_t bd, uint32_t idesc,
-                                            uint32_t acc0, int S) {
+__device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint32_t alo, uint32_t ahi, uint32_t blo,
+                                            uint32_t bhi, uint32_t idesc, uint32_t acc0, int S, int s_first) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        if (s < S) {
+        if (s < S && (s & 1) == s_first) {   // two issuer warps: even / odd sub-tiles
 #pragma unroll
             for (int k = 0; k < KS; ++k)
-                tc_mma(dcol + (uint32_t)s * N, ad + (uint64_t)(64 * s + 2 * k), bd + (uint64_t)(2 * k), idesc,
-                       k == 0 ? acc0 : 1u);
+                tc_mma2(dcol + (uint32_t)s * N, alo + (uint32_t)(64 * s + 2 * k), ahi, blo + (uint32_t)(2 * k), bhi,
+                        idesc, k == 0 ? acc0 : 1u);
         }
     }
 }
@@ -268,68 +300,83 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
         }
         // ---- phase 2: bias, activation, residual, stores --------------------------------------------
         // (bias_s is zero beyond Cout and those accumulators are exact zeros: no per-element channel
-        // masks; the activation is selected once per chunk, not per element)
+        // masks; the activation is selected once per chunk, not per element).  Chunks are finished in
+        // pairs so that ACT outputs go out as 32-byte (full-sector) stores.
+        // N % 16 == 0 and an even chunk count per thread make the first chunk of every pair start at a
+        // channel multiple of 16, so both chunks of a pair always lie in the same sub-tile / pixel.
+        constexpr int PAIR = (NCH % 2 == 0) ? 2 : 1;
 #pragma unroll
-        for (int j = 0; j < HB; ++j) {
-            if (ss[j] != cur_s) enter_pixel(ss[j]);
+        for (int j0 = 0; j0 < HB; j0 += PAIR) {
+            float v[PAIR * 8];
+            if (ss[j0] != cur_s) enter_pixel(ss[j0]);
             if (!ok) continue;
-            const int c0 = cc[j];
-            float v[8];
-            {
-                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0);
-                const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = fmaf(run[(h0 + j) * 8 + q], acc_scale, bb[q]);
-            }
-            if (act == FVC_ACT_RELU) {
+            for (int jj = 0; jj < PAIR; ++jj) {
+                const int j = j0 + jj;
+                const int c0 = cc[j];
+                float* w = v + jj * 8;
+                {
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
-            } else if (act == FVC_ACT_LRELU01) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * 0.1f;
-            } else if (act == FVC_ACT_EXP) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = expf(v[q]);
-            }
-            if (RES) {
-                const uint32_t hh[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w}, ll[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float a0, a1, b0, b1;
-                    e2f2(hh[q], a0, a1);
-                    e2f2(ll[q], b0, b1);
-                    v[2 * q] += a0 + b0;
-                    v[2 * q + 1] += a1 + b1;
+                    for (int q = 0; q < 8; ++q) w[q] = fmaf(run[(h0 + j) * 8 + q], acc_scale, bb[q]);
                 }
-            }
-            if (ep.res_f32) {
+                if (act == FVC_ACT_RELU) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (c0 + q < Cout) v[q] += ep.res_f32[pixC + c0 + q];
-            }
-            if (ep.out_f32) {
-                if ((Cout & 3) == 0) {
+                    for (int q = 0; q < 8; ++q) w[q] = fmaxf(w[q], 0.f);
+                } else if (act == FVC_ACT_LRELU01) {
 #pragma unroll
-                    for (int q = 0; q < 8; q += 4)
-                        if (c0 + q < Cout)
-                            *reinterpret_cast<float4*>(ep.out_f32 + pixC + c0 + q) =
-                                make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-                } else {
+                    for (int q = 0; q < 8; ++q) w[q] = w[q] > 0.f ? w[q] : w[q] * 0.1f;
+                } else if (act == FVC_ACT_EXP) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) w[q] = expf(w[q]);
+                }
+                if (RES) {
+                    const uint32_t hh[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w}, ll[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float a0, a1, b0, b1;
+                        e2f2(hh[q], a0, a1);
+                        e2f2(ll[q], b0, b1);
+                        w[2 * q] += a0 + b0;
+                        w[2 * q + 1] += a1 + b1;
+                    }
+                }
+                if (ep.res_f32) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        if (c0 + q < Cout) ep.out_f32[pixC + c0 + q] = v[q];
+                        if (c0 + q < Cout) w[q] += ep.res_f32[pixC + c0 + q];
+                }
+                if (ep.out_f32) {
+                    if ((Cout & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; q += 4)
+                            if (c0 + q < Cout)
+                                *reinterpret_cast<float4*>(ep.out_f32 + pixC + c0 + q) =
+                                    make_float4(w[q], w[q + 1], w[q + 2], w[q + 3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (c0 + q < Cout) ep.out_f32[pixC + c0 + q] = w[q];
+                    }
                 }
             }
-            if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false);
-            if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp)
-                ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true);
+            const int c0 = cc[j0];
+            if (PAIR == 2) {
+                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store16_packed(rec_out, ep.out_act.Cp, c0, v, false);
+                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store16_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true);
+            } else {
+                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false);
+                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true);
+            }
         }
     }
 }
 
-// Warp roles: 0 = TMA producer (weight stream + patches), 1 = MMA issuer (+ TMEM alloc),
-// 2..17 = accumulator / epilogue warps (any 16 consecutive warps cover every TMEM lane quarter 4 times).
+// Warp roles: 0 = TMA producer (weight stream + patches), 1, 2 = MMA issuers (warp 1 owns the TMEM
+// allocation), 3..18 = accumulator / epilogue warps (any 16 consecutive warps cover every TMEM lane
+// quarter 4 times).
 // NCH: 8-column chunks of the running sum each accumulator thread owns (CT/4 = 8*NCH);
 // RES: the epilogue adds an ACT-format residual (ResBlock skip connection)
 template <int NCH, bool RES>
@@ -352,13 +399,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_pfull + 8 * i, 1);
-            mbar_init(bar_pempty + 8 * i, 1);
-            mbar_init(bar_afull + 8 * i, 1);
+            mbar_init(bar_pempty + 8 * i, 2);   // one commit per MMA issuer warp
+            mbar_init(bar_afull + 8 * i, 2);
             mbar_init(bar_aempty + 8 * i, 16);  // one arrive per accumulator warp
         }
         for (int i = 0; i < P.nst; ++i) {
             mbar_init(bar_bfull + 8 * i, 1);
-            mbar_init(bar_bempty + 8 * i, 1);
+            mbar_init(bar_bempty + 8 * i, 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -368,8 +415,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x >= 64 && (int)threadIdx.x - 64 < P.N) {
-        const int c = (int)threadIdx.x - 64;
+    if (threadIdx.x >= 96 && (int)threadIdx.x - 96 < P.N) {
+        const int c = (int)threadIdx.x - 96;
         bias_s[c] = c < P.Cout ? P.ep.bias[c] : 0.f;
     }
     tc_fence_before();
@@ -419,9 +466,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 else if (++spins > (1u << 25)) __trap();
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer =============================================
-        if (elect_one()) {
+    } else if (warp == 1 || warp == 2) {
+        // ================================ MMA issuers ============================================
+        // Two warps run the same loop nest and issue the MMAs of the even / odd sub-tiles (disjoint
+        // accumulator columns, so no ordering hazard): the tensor-pipe queue is shallow and one warp's
+        // scalar work between MMA batches (descriptor arithmetic, barrier polls) is hidden by the other's
+        // MMAs.  Every "done" barrier counts one commit per issuer warp.
+        // The whole warp runs the loop nest (warp-uniform control flow and address arithmetic stay in
+        // uniform registers: 1-2 scalar instructions per MMA); only the elected lane issues tcgen05 ops.
+        {
+            const bool lead = elect_one();
+            const int s_first = warp - 1;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform copy
+            const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0 && warp == 1;
+            long long w_pfull = 0, w_aempty = 0, w_bfull = 0, w_issue = 0, n_issue = 0;
+            const long long t_begin = dbg_on ? clock64() : 0;
             PassIter cur;
             cur.tile = blockIdx.x; cur.pass = 0; cur.decode(P);
             uint32_t gg = 0;                    // accumulation-group counter
@@ -430,61 +489,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             // descriptors: everything but the start address is fixed; per MMA only the low word moves
             const uint64_t adesc0 = make_desc(0, (uint32_t)P.PW * 128u);
             const uint64_t bdesc0 = make_desc(0, 1024u);
+            const uint32_t ahi = (uint32_t)(adesc0 >> 32), bhi = (uint32_t)(bdesc0 >> 32);
+            const uint32_t lo0 = (uint32_t)adesc0;            // LBO field; the address bits are added below
             const int S = P.S, T = P.T;
             const uint32_t N = (uint32_t)P.N, nst = (uint32_t)P.nst, CT = (uint32_t)P.CT, npb = (uint32_t)P.npb;
-            const uint32_t idesc = P.idesc, btile16 = P.btile_bytes >> 4;
+            const uint32_t idesc = P.idesc, btile16 = P.btile_bytes >> 4, stage16 = P.stage_bytes >> 4;
+            const uint32_t bst16 = lo0 + (bst0 >> 4);
             while (cur.valid(ntiles)) {
                 const TcSub& sb = P.sub[cur.sub];
                 const TcPass& ps = P.pass[sb.pass_first + cur.pass];
-                mbar_wait(bar_pfull + 8 * set, pph);
-                tc_fence_after();
-                const uint32_t pbase = patch0 + set * P.patch_bytes;
-                const int ntaps = ps.ntaps, gtaps = ps.gtaps, nbt = ps.nbt, ks1 = ps.ks1;
+                { const long long c0 = dbg_on ? clock64() : 0;
+                  mbar_wait(bar_pfull + 8 * set, pph);
+                  if (dbg_on) w_pfull += clock64() - c0; }
+                const uint32_t pa16 = lo0 + ((patch0 + set * P.patch_bytes) >> 4);
+                const int ntaps = ps.ntaps, gtaps = ps.gtaps;
+                const bool two = ps.nbt == 2, short2 = ps.ks1 != 4;   // second tile per tap / with 2 k-steps
                 const int32_t* toffp = P.tap_off + ps.tap_first;
                 int slot = 0;                   // tile index inside the current weight stage
-                uint64_t bd = 0;
-                for (int t0 = 0; t0 < ntaps; t0 += gtaps) {
-                    const int t1 = min(t0 + gtaps, ntaps);
+                uint32_t blo = 0;
+                int t = 0;
+                uint32_t toff = (uint32_t)toffp[0] >> 4;
+                while (t < ntaps) {
+                    const int t1 = min(t + gtaps, ntaps);
                     // partial buffer must have been drained by the accumulator warps
                     const uint32_t pb = gg & 1u;
-                    mbar_wait(bar_aempty + 8 * pb, ((gg >> 1) & 1u) ^ 1u);
+                    { const long long c0 = dbg_on ? clock64() : 0;
+                      mbar_wait(bar_aempty + 8 * pb, ((gg >> 1) & 1u) ^ 1u);
+                      if (dbg_on) w_aempty += clock64() - c0; }
                     tc_fence_after();
-                    const uint32_t dcol = tmem_base + pb * CT;
-                    for (int t = t0; t < t1; ++t) {
-                        const uint64_t ad = adesc0 + (uint64_t)((pbase + (uint32_t)toffp[t]) >> 4);
-                        for (int j = 0; j < nbt; ++j) {
+                    const uint32_t dcol = tmem_u + pb * CT;
+                    uint32_t acc0 = 0u;
+                    for (; t < t1; ++t) {
+                        const uint32_t alo = pa16 + toff;
+                        toff = (uint32_t)toffp[min(t + 1, ntaps - 1)] >> 4;   // prefetched for the next tap
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (j == 1 && !two) break;
                             if (slot == 0) {
+                                const long long c0 = dbg_on ? clock64() : 0;
                                 mbar_wait(bar_bfull + 8 * st, stph);
-                                tc_fence_after();
-                                bd = bdesc0 + (uint64_t)((bst0 + st * P.stage_bytes) >> 4);
+                                if (dbg_on) w_bfull += clock64() - c0;
+                                blo = bst16 + st * stage16;
                             }
-                            const uint32_t acc0 = (t == t0 && j == 0) ? 0u : 1u;
-                            // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
-                            if (j == 0 || ks1 == 4) issue_stage<4>(dcol, N, ad, bd, idesc, acc0, S);
-                            else issue_stage<2>(dcol, N, ad, bd, idesc, acc0, S);
-                            bd += btile16;
-                            if (++slot == T || (t == ntaps - 1 && j == nbt - 1)) {
-                                tc_commit(bar_bempty + 8 * st);   // frees the weight stage when these MMAs retire
+                            const long long ci0 = dbg_on ? clock64() : 0;
+                            if (lead) {
+                                // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
+                                if (j == 1 && short2) issue_stage<2>(dcol, N, alo, ahi, blo, bhi, idesc, acc0, S, s_first);
+                                else issue_stage<4>(dcol, N, alo, ahi, blo, bhi, idesc, acc0, S, s_first);
+                            }
+                            if (dbg_on) { w_issue += clock64() - ci0; n_issue += 1; }
+                            acc0 = 1u;
+                            blo += btile16;
+                            if (++slot == T || (t == ntaps - 1 && (j == 1 || !two))) {
+                                if (lead) tc_commit(bar_bempty + 8 * st);   // frees the stage when these MMAs retire
                                 if (++st == nst) { st = 0; stph ^= 1u; }
                                 slot = 0;
                             }
                         }
                     }
-                    tc_commit(bar_afull + 8 * pb);            // short chain complete -> accumulator warps
+                    if (lead) tc_commit(bar_afull + 8 * pb);  // short chain complete -> accumulator warps
                     ++gg;
                 }
-                tc_commit(bar_pempty + 8 * set);              // patch buffer reusable
+                if (lead) tc_commit(bar_pempty + 8 * set);    // patch buffer reusable
+                __syncwarp();
                 if (++set == npb) { set = 0; pph ^= 1u; }
                 cur.next(P, gridDim.x);
             }
+            if (dbg_on && lead) {
+                P.dbg[0] = (unsigned long long)(clock64() - t_begin);
+                P.dbg[1] = (unsigned long long)w_pfull;
+                P.dbg[2] = (unsigned long long)w_aempty;
+                P.dbg[3] = (unsigned long long)w_bfull;
+                P.dbg[4] = (unsigned long long)w_issue;
+                P.dbg[5] = (unsigned long long)n_issue;
+            }
         }
-    } else if (warp >= 2) {
-        // ======================= accumulator / epilogue warps (16: warps 2..17) ====================
+    } else if (warp >= 3) {
+        // ======================= accumulator / epilogue warps (16: warps 3..18) ====================
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
-        const int part = (warp - 2) >> 2;                 // which quarter of the CT columns
+        const int part = (warp - 3) >> 2;                 // which quarter of the CT columns
         const int row = quarter * 32 + lane;              // accumulator row = pixel inside the sub-tile
         const int th = row >> 3, tw = row & 7;
         const uint32_t colbase = (uint32_t)part * (uint32_t)(NCH * 8);
+        constexpr bool PARK = NCH >= 6;
         uint32_t gg = 0;
         float run[NCH * 8];
         const int tiles_xy = P.tiles_x * P.tiles_y;
@@ -492,7 +579,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const int ng = P.sub[(tile / tiles_xy) % P.nsub].ngroups;
             for (int g = 0; g < ng; ++g, ++gg) {
                 const uint32_t pb = gg & 1u;
-                mbar_wait(bar_afull + 8 * pb, (gg >> 1) & 1u);
+                mbar_wait_sleep(bar_afull + 8 * pb, (gg >> 1) & 1u, P.acc_sleep_ns);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pb * P.CT + colbase;
 #pragma unroll
@@ -513,9 +600,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         for (int q = 0; q < 8; ++q) run[i * 8 + q] += v[q];   // fp32 round-to-nearest
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
+                if (!PARK || g + 1 < ng) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
+                }
             }
             // tile coordinates are decoded only now (laundered through an empty asm) so that the epilogue's
             // address arithmetic cannot be hoisted above the drain loop, where it would spill `run`
@@ -525,7 +614,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const int ty = t % P.tiles_y; t /= P.tiles_y;
             const int sub = t % P.nsub;
             const int b = t / P.nsub;
-            tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+            if constexpr (!PARK) {
+                tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+            } else {
+                // 48/64 running sums + the epilogue state do not fit 96 registers (ncu: spill reloads
+                // queued behind the epilogue's global stores were its main stall).  Park the upper half of
+                // the sums in the partial buffer that was just drained (it stays ours until we arrive on
+                // its "empty" barrier), finish the lower half from registers, then fetch the rest back.
+                constexpr int NH = NCH / 2;
+                const uint32_t pb = (gg - 1u) & 1u;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pb * P.CT + colbase;
+#pragma unroll
+                for (int i = NH; i < NCH; ++i) tc_st8(taddr + i * 8, reinterpret_cast<const uint32_t*>(run + i * 8));
+                tc_wait_st();
+                tile_epilogue<NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+#pragma unroll
+                for (int i = NH; i < NCH; ++i) {
+                    tc_ld8(taddr + i * 8, reinterpret_cast<uint32_t*>(run + (i - NH) * 8));
+                    tc_wait_ld();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
+                tile_epilogue<NCH - NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase + NH * 8);
+            }
         }
     }
     tc_fence_before();
@@ -599,6 +711,7 @@ __global__ void k_tc_pack(const float* __restrict__ w, e16* __restrict__ out, co
 // host: plan
 // ----------------------------------------------------------------------------------------------
 struct TcPlan {
+    unsigned long long* dbg = nullptr;
     TcParams P;
     e16* wstream = nullptr;
     size_t smem = 0;
@@ -887,6 +1000,11 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             return FVC_ERR_CUDA;
         }
     }
+    P.acc_sleep_ns = (uint32_t)env_int("FVC_TC_ACC_SLEEP", 100);
+    if (env_int("FVC_TC_DEBUG", 0)) {
+        if (cudaMalloc(&plan->dbg, 64) == cudaSuccess) cudaMemset(plan->dbg, 0, 64);
+        P.dbg = plan->dbg;
+    }
     plan->smem = 1024 + (size_t)npb * P.patch_bytes + (size_t)nst * P.stage_bytes + 1024;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -907,6 +1025,14 @@ static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
     k_conv_tc<NCH, RES><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->P);
     g_launch_count++;
     FVC_CHECK_LAUNCH();
+    if (plan->dbg) {   // debugging aid: where block 0's MMA issuer spent its cycles
+        unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+        FVC_CUDA(cudaStreamSynchronize(s));
+        FVC_CUDA(cudaMemcpy(h, plan->dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        const TcParams& Q = plan->P;
+        fprintf(stderr, "tcdbg N=%d S=%d T=%d nst=%d npb=%d PW=%d PH=%d Cout=%d Hout=%d total=%llu pfull=%llu aempty=%llu bfull=%llu issue=%llu nstage=%llu\n",
+                Q.N, Q.S, Q.T, Q.nst, Q.npb, Q.PW, Q.PH, Q.Cout, Q.Hout, h[0], h[1], h[2], h[3], h[4], h[5]);
+    }
     return 0;
 }
 
@@ -932,6 +1058,7 @@ int tc_plan_launch(TcPlan* plan, cudaStream_t s) {
 void tc_plan_destroy(TcPlan* plan) {
     if (!plan) return;
     if (plan->wstream) cudaFree(plan->wstream);
+    if (plan->dbg) cudaFree(plan->dbg);
     delete plan;
 }
 

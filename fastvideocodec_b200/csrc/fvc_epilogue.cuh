@@ -66,6 +66,41 @@ __device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const
     *reinterpret_cast<uint4*>(rec + Cp + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// 16 channels at once: one 32-byte (full L2 sector) store for the hi halves and one for the lo halves.
+// (16-byte stores write half sectors: ncu showed DRAM reads ~= output size, i.e. read-for-ownership
+// fills on every output sector.)  rec + c0 must be 32-byte aligned: c0 % 16 == 0.
+__device__ __forceinline__ void ep_pack8(const float* v, bool relu, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = v[2 * j], b = v[2 * j + 1];
+        if (relu) {
+            a = fmaxf(a, 0.f);
+            b = fmaxf(b, 0.f);
+        }
+        hi[j] = ep_pack2(a, b);
+        float ha, hb;
+        e2f2(hi[j], ha, hb);
+        lo[j] = ep_pack2(a - ha, b - hb);
+    }
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* r) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ep_store16_packed(e16* rec, int Cp, int c0, const float* v16, bool relu) {
+    uint32_t hi[8], lo[8];
+    ep_pack8(v16, relu, hi, lo);
+    ep_pack8(v16 + 8, relu, hi + 4, lo + 4);
+    st_global_v8(rec + c0, hi);
+    st_global_v8(rec + Cp + c0, lo);
+}
+
 __device__ __forceinline__ float ep_act(float v, int act) {
     switch (act) {
         case FVC_ACT_RELU: return fmaxf(v, 0.f);
