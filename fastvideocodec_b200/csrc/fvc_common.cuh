@@ -171,9 +171,13 @@ struct Epilogue {
     ActT out_act;             // optional ACT output (p == nullptr: none)
     ActT out_act_relu;        // optional second ACT output holding relu(y)
     float* out_f32;           // optional fp32 NHWC output [B,Hout,Wout,Cout]
-    const float* gdn_beta;    // fused (I)GDN: effective beta [C], gamma [C][C]; nullptr: none
+    const float* gdn_beta;    // (unused placeholder kept for the SIMT engine's argument check)
     const float* gdn_gamma;
     int gdn_inverse;
+    // tcgen05 engine only:
+    ActT out_act_sq;          // optional ACT output holding sq_scale * y^2 (input of the GDN 1x1 convolution)
+    float sq_scale;
+    int res_mode;             // how res_act enters: 0: y += r;  1: y = r / sqrt(y) (GDN);  2: y = r * sqrt(y) (IGDN)
 };
 
 }  // namespace fvc

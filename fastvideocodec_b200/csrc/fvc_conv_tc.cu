@@ -263,7 +263,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
     // per-pixel state, recomputed only when the chunk sequence moves to the next sub-tile
     int cur_s = -1;
     bool ok = false;
-    e16 *rec_out = nullptr, *rec_relu = nullptr;
+    e16 *rec_out = nullptr, *rec_relu = nullptr, *rec_sq = nullptr;
     const e16* rec_res = nullptr;
     size_t pixC = 0;   // pixel index * Cout (fp32 NHWC tensors)
     auto enter_pixel = [&](int s) {
@@ -274,6 +274,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
         if (!ok) return;
         if (ep.out_act.p) rec_out = ep.out_act.p + act_pixel_offset(ep.out_act, b, oy, ox);
         if (ep.out_act_relu.p) rec_relu = ep.out_act_relu.p + act_pixel_offset(ep.out_act_relu, b, oy, ox);
+        if (ep.out_act_sq.p) rec_sq = ep.out_act_sq.p + act_pixel_offset(ep.out_act_sq, b, oy, ox);
         if (RES) rec_res = ep.res_act.p + act_pixel_offset(ep.res_act, b, oy, ox);
         pixC = (((size_t)b * P.Hout + oy) * P.Wout + ox) * (size_t)Cout;
     };
@@ -334,13 +335,24 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
                 }
                 if (RES) {
                     const uint32_t hh[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w}, ll[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
+                    float r[8];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float a0, a1, b0, b1;
                         e2f2(hh[q], a0, a1);
                         e2f2(ll[q], b0, b1);
-                        w[2 * q] += a0 + b0;
-                        w[2 * q + 1] += a1 + b1;
+                        r[2 * q] = a0 + b0;
+                        r[2 * q + 1] = a1 + b1;
+                    }
+                    if (ep.res_mode == 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) w[q] += r[q];
+                    } else if (ep.res_mode == 1) {   // GDN.py:88-93: x / sqrt(beta + gamma . x^2)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) w[q] = r[q] / sqrtf(w[q]);
+                    } else {                         // IGDN: x * sqrt(.)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) w[q] = r[q] * sqrtf(w[q]);
                     }
                 }
                 if (ep.res_f32) {
@@ -369,6 +381,12 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
             } else {
                 if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false);
                 if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true);
+            }
+            if (ep.out_act_sq.p && c0 < ep.out_act_sq.Cp) {   // squares for the following (I)GDN
+#pragma unroll
+                for (int q = 0; q < PAIR * 8; ++q) v[q] = v[q] * v[q] * ep.sq_scale;
+                if (PAIR == 2) ep_store16_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false);
+                else ep_store8_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false);
             }
         }
     }
@@ -762,6 +780,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     int chans = L.Cout;
     if (ep.out_act.p) chans = std::max(chans, ep.out_act.Cp);
     if (ep.out_act_relu.p) chans = std::max(chans, ep.out_act_relu.Cp);
+    if (ep.out_act_sq.p) chans = std::max(chans, ep.out_act_sq.Cp);
     const int N = std::max(16, cdiv(chans, 16) * 16);   // MMA N: every channel of an output record is produced
     P.N = N;
     P.nchunks = 0;

@@ -92,7 +92,8 @@ struct fvc_ctx {
     float* wres = nullptr;                           // fp32 NHWC3
     float* prediction = nullptr;                     // planar
     ActT residual;                                   // parity
-    ActT r_raw[3], r[3];                             // resEncoder (raw only for the SIMT engine)
+    ActT r_raw[3], r[3];                             // resEncoder: conv output, GDN output
+    ActT r_sq[3], g_sq[3];                           // squares of the conv outputs (tcgen05 GDN path)
     float* feature = nullptr;                        // fp32 NHWC96
     ActT featabs;
     ActT p1, p2;
@@ -187,6 +188,11 @@ static int build_layers(fvc_ctx* c) {
         snprintf(buf, sizeof(buf), "resDecoder.igdn%d", i);
         g.name = buf; g.inverse = 1;
         c->gdn[buf] = g;
+        // tcgen05 engine: (I)GDN norm = 1x1 convolution of the squares with gamma_eff, bias beta_eff
+        snprintf(buf, sizeof(buf), "resEncoder.gdn%d#norm", i);
+        add_conv(c, buf, 64, 64, 1, 1, 0, FVC_ACT_NONE, 64);
+        snprintf(buf, sizeof(buf), "resDecoder.igdn%d#norm", i);
+        add_conv(c, buf, 64, 64, 1, 1, 0, FVC_ACT_NONE, 64);
     }
     c->be_z.name = "bitEstimator_z"; c->be_z.C = 64;
     c->be_mv.name = "bitEstimator_mv"; c->be_mv.C = 128;
@@ -273,6 +279,8 @@ static int build_buffers(fvc_ctx* c) {
     for (int i = 0; i < 3; ++i) {
         A(c->alloc_act(&c->r_raw[i], H >> (i + 1), W >> (i + 1), 64, 0));
         A(c->alloc_act(&c->r[i], H >> (i + 1), W >> (i + 1), 64, 1));
+        A(c->alloc_act(&c->r_sq[i], H >> (i + 1), W >> (i + 1), 64, 0));
+        A(c->alloc_act(&c->g_sq[i], H >> (3 - i), W >> (3 - i), 64, 0));
     }
     A(c->alloc(&c->feature, (size_t)B * (H / 16) * (W / 16) * 96 * 4));
     A(c->alloc_act(&c->featabs, H / 16, W / 16, 128, 0));
@@ -312,6 +320,9 @@ static Epilogue make_ep(const ConvRt& r) {
     ep.res_act = no_act();
     ep.out_act = no_act();
     ep.out_act_relu = no_act();
+    ep.out_act_sq = no_act();
+    ep.sq_scale = 1.f;
+    ep.res_mode = 0;
     return ep;
 }
 
@@ -365,8 +376,8 @@ static int run_conv(fvc_ctx* c, const std::string& name, ActT in, int Hout, int 
 
 // conv followed by (I)GDN: conv kernel writes the raw activations, a second kernel normalises
 // (fusing the 64x64 GDN matvec into the tcgen05 epilogue is future work; these layers are 3 % of the FLOPs)
-static int run_conv_gdn(fvc_ctx* c, const std::string& conv, const std::string& gdn, ActT in, ActT raw, ActT out,
-                        cudaStream_t s) {
+static int run_conv_gdn(fvc_ctx* c, const std::string& conv, const std::string& gdn, ActT in, ActT raw, ActT sq,
+                        ActT out, cudaStream_t s) {
     GdnRt& g = c->gdn[gdn];
     if (!g.have_b || !g.have_g) {
         set_error("parameters of %s not set", gdn.c_str());
@@ -375,9 +386,25 @@ static int run_conv_gdn(fvc_ctx* c, const std::string& conv, const std::string& 
     ConvRt& r = c->conv[conv];
     Epilogue ep = make_ep(r);
     ep.out_act = raw;
+    const bool tc = c->impl == FVC_IMPL_TC;
+    // squares are stored scaled by 2^-6 so that |x| up to ~2000 stays inside the fp16 range of the hi half
+    const float sq_scale = 1.f / 64.f;
+    if (tc) {
+        ep.out_act_sq = sq;
+        ep.sq_scale = sq_scale;
+    }
     int rc = run_conv(c, conv, in, out.H, out.W, ep, s);
     if (rc) return rc;
-    return launch_gdn_act(raw, g.C, g.beta_eff, g.gamma_eff, g.inverse, out, s);
+    if (!tc) return launch_gdn_act(raw, g.C, g.beta_eff, g.gamma_eff, g.inverse, out, s);
+    // norm_i = beta_i + sum_j gamma_ij x_j^2 as a 1x1 tcgen05 convolution; y = x / sqrt(norm) or x * sqrt(norm)
+    const std::string nname = gdn + "#norm";
+    ConvRt& n = c->conv[nname];
+    Epilogue en = make_ep(n);
+    en.acc_scale = 1.f / sq_scale;
+    en.res_act = raw;
+    en.res_mode = g.inverse ? 2 : 1;
+    en.out_act = out;
+    return run_conv(c, nname, sq, out.H, out.W, en, s);
 }
 
 static int res_block(fvc_ctx* c, int idx, ActT x_relu, ActT x_skip, ActT tmp, ActT out, ActT out_relu,
@@ -491,9 +518,9 @@ static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_
     }
     R(launch_mc_finish(c->wres, c->warpframe, cur, c->prediction, c->residual, s));
     // ---- residual encoder (analysis.py:44-48) ---------------------------------------------------
-    R(run_conv_gdn(c, "resEncoder.conv1", "resEncoder.gdn1", c->residual, c->r_raw[0], c->r[0], s));
-    R(run_conv_gdn(c, "resEncoder.conv2", "resEncoder.gdn2", c->r[0], c->r_raw[1], c->r[1], s));
-    R(run_conv_gdn(c, "resEncoder.conv3", "resEncoder.gdn3", c->r[1], c->r_raw[2], c->r[2], s));
+    R(run_conv_gdn(c, "resEncoder.conv1", "resEncoder.gdn1", c->residual, c->r_raw[0], c->r_sq[0], c->r[0], s));
+    R(run_conv_gdn(c, "resEncoder.conv2", "resEncoder.gdn2", c->r[0], c->r_raw[1], c->r_sq[1], c->r[1], s));
+    R(run_conv_gdn(c, "resEncoder.conv3", "resEncoder.gdn3", c->r[1], c->r_raw[2], c->r_sq[2], c->r[2], s));
     {
         Epilogue ep = make_ep(c->conv["resEncoder.conv4"]);
         ep.out_f32 = c->feature;
@@ -532,9 +559,9 @@ static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_
     R(launch_quant_bits_laplace(c->feature, c->sigma, (int64_t)B * (H / 16) * (W / 16) * 96, 96, nullptr,
                                 c->feat_hat, c->bits_partials + 0 * maxb, &nb_f, s));
     // ---- residual decoder (synthesis.py:54-58) --------------------------------------------------
-    R(run_conv_gdn(c, "resDecoder.deconv1", "resDecoder.igdn1", c->feat_hat, c->g_raw[0], c->g[0], s));
-    R(run_conv_gdn(c, "resDecoder.deconv2", "resDecoder.igdn2", c->g[0], c->g_raw[1], c->g[1], s));
-    R(run_conv_gdn(c, "resDecoder.deconv3", "resDecoder.igdn3", c->g[1], c->g_raw[2], c->g[2], s));
+    R(run_conv_gdn(c, "resDecoder.deconv1", "resDecoder.igdn1", c->feat_hat, c->g_raw[0], c->g_sq[0], c->g[0], s));
+    R(run_conv_gdn(c, "resDecoder.deconv2", "resDecoder.igdn2", c->g[0], c->g_raw[1], c->g_sq[1], c->g[1], s));
+    R(run_conv_gdn(c, "resDecoder.deconv3", "resDecoder.igdn3", c->g[1], c->g_raw[2], c->g_sq[2], c->g[2], s));
     {
         Epilogue ep = make_ep(c->conv["resDecoder.deconv4"]);
         ep.out_f32 = c->recon_res;
@@ -647,7 +674,17 @@ int fvc_ctx_set_param(fvc_ctx* c, const char* key_c, const float* data, int64_t 
             set_error("unknown parameter %s", key_c);
             return FVC_ERR_ARG;
         }
-        if (g.have_b && g.have_g) return launch_gdn_reparam(g.beta_raw, g.gamma_raw, g.beta_eff, g.gamma_eff, g.C, s);
+        if (g.have_b && g.have_g) {
+            int rc = launch_gdn_reparam(g.beta_raw, g.gamma_raw, g.beta_eff, g.gamma_eff, g.C, s);
+            if (rc) return rc;
+            ConvRt& n = c->conv[mod + "#norm"];   // gamma_eff is [out][in] = a 1x1 OIHW kernel
+            FVC_CUDA(cudaMemcpyAsync(n.w_raw, g.gamma_eff, (size_t)g.C * g.C * 4, cudaMemcpyDeviceToDevice, s));
+            FVC_CUDA(cudaMemcpyAsync(n.bias, g.beta_eff, (size_t)g.C * 4, cudaMemcpyDeviceToDevice, s));
+            rc = simt_pack_weights(n.L, n.w_raw, n.CinP, n.CoutS, &n.simt, s);
+            if (rc) return rc;
+            if (n.tc) { tc_plan_destroy(n.tc); n.tc = nullptr; }
+            n.have_w = n.have_b = true;
+        }
         return 0;
     }
     // bitEstimator_{z,mv}.f{1..4}.{h,b,a}
