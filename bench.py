@@ -228,8 +228,13 @@ def run_ours(args, rank, world, local_rank):
         conv_t = sorted(conv_s[1:])[len(conv_s[1:]) // 2]
         flops = FLOP_PER_PX * H * W
         ach = flops / conv_t / 1e12
+        traffic = None   # DRAM bytes of the convolution launches of one frame, from the committed ncu pass
+        tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_frame")
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": None, "kernel": "convolution engine (%s), all conv launches of one P-frame" % impl_name,
+                "traffic": traffic, "kernel": "convolution engine (%s), all conv launches of one P-frame" % impl_name,
                 "algorithmic_flop_per_frame": flops, "conv_seconds_per_frame": conv_t,
                 "conv_share_of_frame": conv_t / (ms_max * 1e-3 / (args.steps * (GOP - 1))), "peak_source": how}
         pm.release()
@@ -239,7 +244,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "P-frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2-split (fp32 accumulate)" if impl_name == "tc" else "f32",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16 hi/lo pairs x3 MMAs (fp32 accumulate)" if impl_name == "tc" else "f32",
                 "data": "synthetic",
                 "config": {"workload": "DVC P-frame forward %dx%d, GOP=%d (9 P-frames/step/rank), B=1, configs[1]; "
                                        "GOPs sharded by rank (configs[2])" % (H, W, GOP),
