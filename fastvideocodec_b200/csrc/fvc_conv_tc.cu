@@ -584,86 +584,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         }
     } else if (warp >= 3) {
         // ======================= accumulator / epilogue warps (16: warps 3..18) ====================
-        // Per group: drain the finished partial accumulator into the running sums (registers).  At the end
-        // of a tile the sums are parked in a third TMEM buffer ("final") and the next tile's drains start
-        // at once; the previous tile's epilogue (bias, activation, split, global stores) is then worked off
-        // one unit after each drain, so the MMA pipe never waits for an epilogue (measured before: the
-        // issuer spent 25-65 % of its time waiting for accumulator buffers on large-output layers).
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
         const int part = (warp - 3) >> 2;                 // which quarter of the CT columns
         const int row = quarter * 32 + lane;              // accumulator row = pixel inside the sub-tile
         const int th = row >> 3, tw = row & 7;
         const uint32_t colbase = (uint32_t)part * (uint32_t)(NCH * 8);
-        constexpr int UW = (NCH % 2 == 0) ? 2 : 1;        // chunks per epilogue unit (pairs -> 32-byte stores)
-        constexpr int NUNITS = NCH / UW;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + colbase;
-        const uint32_t final_addr = lane_base + 2u * (uint32_t)P.CT;
-        const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == 3 && lane == 0;
-        long long a_wait = 0, a_drain = 0, a_epi = 0;
+        constexpr bool PARK = NCH >= 6;
         uint32_t gg = 0;
         float run[NCH * 8];
         const int tiles_xy = P.tiles_x * P.tiles_y;
-        int pend_tile = -1, pend_unit = 0;                // epilogue of pend_tile: units [pend_unit, NUNITS) left
-        auto epilogue_unit = [&]() {
-            const long long ce0 = P.dbg ? clock64() : 0;
-            int t = pend_tile;
-            const int tx = t % P.tiles_x; t /= P.tiles_x;
-            const int ty = t % P.tiles_y; t /= P.tiles_y;
-            const int sub = t % P.nsub;
-            const int b = t / P.nsub;
-            float v[UW * 8];
-            if (UW == 2) tc_ld16(final_addr + pend_unit * 16, reinterpret_cast<uint32_t*>(v));
-            else tc_ld8(final_addr + pend_unit * 8, reinterpret_cast<uint32_t*>(v));
-            tc_wait_ld();
-            tile_epilogue<UW, RES>(P, bias_s, v, b, sub, ty, tx, th, tw, colbase + (uint32_t)(pend_unit * UW * 8));
-            if (++pend_unit == NUNITS) pend_tile = -1;
-            if (P.dbg) a_epi += clock64() - ce0;
-        };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int ng = P.sub[(tile / tiles_xy) % P.nsub].ngroups;
             for (int g = 0; g < ng; ++g, ++gg) {
                 const uint32_t pb = gg & 1u;
-                const long long ca0 = P.dbg ? clock64() : 0;
                 mbar_wait_sleep(bar_afull + 8 * pb, (gg >> 1) & 1u, P.acc_sleep_ns);
                 tc_fence_after();
-                const long long ca1 = P.dbg ? clock64() : 0;
-                const uint32_t taddr = lane_base + pb * P.CT;
-                // Wide TMEM loads: one round trip per W chunks instead of one per chunk
-                constexpr int W = (NCH % 4 == 0) ? 4 : ((NCH % 2 == 0) ? 2 : 1);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pb * P.CT + colbase;
 #pragma unroll
-                for (int i = 0; i < NCH; i += W) {
-                    float v[W * 8];
-                    if (W == 4) tc_ld32(taddr + i * 8, reinterpret_cast<uint32_t*>(v));
-                    else if (W == 2) tc_ld16(taddr + i * 8, reinterpret_cast<uint32_t*>(v));
-                    else tc_ld8(taddr + i * 8, reinterpret_cast<uint32_t*>(v));
+                for (int i = 0; i < NCH; ++i) {
+                    float v[8];
+                    // At most two TMEM loads in flight: the address of load i carries a (zero) dependency on
+                    // the sums of chunk i-2.  Unconstrained, ptxas issues 4+ loads back to back and then
+                    // spills the 64 running sums around every group (seen in SASS).
+                    uint32_t dep = 0;
+                    if (NCH > 4 && i >= 2) dep = __float_as_uint(run[(i - 2) * 8]) & P.zero;
+                    tc_ld8(taddr + i * 8 + dep, reinterpret_cast<uint32_t*>(v));
                     tc_wait_ld();
                     if (g == 0) {
 #pragma unroll
-                        for (int q = 0; q < W * 8; ++q) run[i * 8 + q] = v[q];
+                        for (int q = 0; q < 8; ++q) run[i * 8 + q] = v[q];
                     } else {
 #pragma unroll
-                        for (int q = 0; q < W * 8; ++q) run[i * 8 + q] += v[q];   // fp32 round-to-nearest
+                        for (int q = 0; q < 8; ++q) run[i * 8 + q] += v[q];   // fp32 round-to-nearest
                     }
+                }
+                if (!PARK || g + 1 < ng) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
+                }
+            }
+            // tile coordinates are decoded only now (laundered through an empty asm) so that the epilogue's
+            // address arithmetic cannot be hoisted above the drain loop, where it would spill `run`
+            int t = tile;
+            asm volatile("" : "+r"(t));
+            const int tx = t % P.tiles_x; t /= P.tiles_x;
+            const int ty = t % P.tiles_y; t /= P.tiles_y;
+            const int sub = t % P.nsub;
+            const int b = t / P.nsub;
+            if constexpr (!PARK) {
+                tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+            } else {
+                // 48/64 running sums + the epilogue state do not fit 96 registers (ncu: spill reloads
+                // queued behind the epilogue's global stores were its main stall).  Park the upper half of
+                // the sums in the partial buffer that was just drained (it stays ours until we arrive on
+                // its "empty" barrier), finish the lower half from registers, then fetch the rest back.
+                constexpr int NH = ((NCH / 2) + 1) & ~1;
+                const uint32_t pb = (gg - 1u) & 1u;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pb * P.CT + colbase;
+#pragma unroll
+                for (int i = NH; i < NCH; ++i) tc_st8(taddr + i * 8, reinterpret_cast<const uint32_t*>(run + i * 8));
+                tc_wait_st();
+                tile_epilogue<NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+#pragma unroll
+                for (int i = NH; i < NCH; ++i) {
+                    tc_ld8(taddr + i * 8, reinterpret_cast<uint32_t*>(run + (i - NH) * 8));
+                    tc_wait_ld();
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
-                if (P.dbg) { const long long ca2 = clock64(); a_wait += ca1 - ca0; a_drain += ca2 - ca1; }
-                if (pend_tile >= 0) epilogue_unit();      // previous tile's epilogue, one unit per drain
+                tile_epilogue<NCH - NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase + NH * 8);
             }
-            while (pend_tile >= 0) epilogue_unit();       // the final buffer must be free before it is reused
-            // park this tile's sums (same thread reads them back: no cross-thread ordering needed)
-#pragma unroll
-            for (int i = 0; i < NCH; ++i) tc_st8(final_addr + i * 8, reinterpret_cast<const uint32_t*>(run + i * 8));
-            tc_wait_st();
-            pend_tile = tile;
-            pend_unit = 0;
-        }
-        while (pend_tile >= 0) epilogue_unit();
-        if (adbg) {
-            P.dbg[6] = (unsigned long long)a_wait;
-            P.dbg[7] = (unsigned long long)a_drain;
-            P.dbg[8] = (unsigned long long)a_epi;
         }
     }
     tc_fence_before();
@@ -848,13 +840,11 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // leaves room for a deep weight ring; otherwise one (big-halo 7x7 layers: the exposed patch load is
     // a few % of a pass, a starved weight ring costs far more).
     // (residual epilogues keep CT <= 192: 48 running sums leave registers for the prefetched skip data)
-    // CT = S*N <= 128: two partial buffers + one "final" buffer (parked sums of the previous tile) in 512
-    // TMEM columns, 32 running sums per accumulator thread.
-    const int sx_max = std::min(env_int("FVC_TC_SX", 4), std::max(1, env_int("FVC_TC_CTMAX", 128) / N));
+    const int sx_max = std::min(env_int("FVC_TC_SX", 4), (ep.res_act.p ? 192 : 256) / N);
     const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), 256 / N));
     for (int sx = std::max(1, sx_max); sx >= 1 && !SX; --sx) {
         const int ct32 = sx * N / 32;
-        if ((sx * N) % 32 != 0 || !(ct32 >= 1 && ct32 <= 4)) continue;
+        if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * 128;
@@ -881,7 +871,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     P.btile_bytes = (uint32_t)N * 128u;
     P.stage_bytes = (uint32_t)T * P.btile_bytes;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(3 * P.CT)) cols <<= 1;
+    while (cols < (uint32_t)(2 * P.CT)) cols <<= 1;
     P.tmem_cols = cols;
     P.tiles_x = cdiv(P.Wq, 8 * SX);
     P.tiles_y = cdiv(P.Hq, 16);
@@ -1031,7 +1021,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     }
     P.acc_sleep_ns = (uint32_t)env_int("FVC_TC_ACC_SLEEP", 100);
     if (env_int("FVC_TC_DEBUG", 0)) {
-        if (cudaMalloc(&plan->dbg, 128) == cudaSuccess) cudaMemset(plan->dbg, 0, 128);
+        if (cudaMalloc(&plan->dbg, 64) == cudaSuccess) cudaMemset(plan->dbg, 0, 64);
         P.dbg = plan->dbg;
     }
     plan->smem = 1024 + (size_t)npb * P.patch_bytes + (size_t)nst * P.stage_bytes + 1024;
@@ -1055,12 +1045,12 @@ static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     if (plan->dbg) {   // debugging aid: where block 0's MMA issuer spent its cycles
-        unsigned long long h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
         FVC_CUDA(cudaStreamSynchronize(s));
         FVC_CUDA(cudaMemcpy(h, plan->dbg, sizeof(h), cudaMemcpyDeviceToHost));
         const TcParams& Q = plan->P;
-        fprintf(stderr, "tcdbg N=%d S=%d T=%d nst=%d npb=%d PW=%d PH=%d Cout=%d Hout=%d total=%llu pfull=%llu aempty=%llu bfull=%llu issue=%llu nstage=%llu | acc: wait=%llu drain=%llu epi=%llu\n",
-                Q.N, Q.S, Q.T, Q.nst, Q.npb, Q.PW, Q.PH, Q.Cout, Q.Hout, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+        fprintf(stderr, "tcdbg N=%d S=%d T=%d nst=%d npb=%d PW=%d PH=%d Cout=%d Hout=%d total=%llu pfull=%llu aempty=%llu bfull=%llu issue=%llu nstage=%llu\n",
+                Q.N, Q.S, Q.T, Q.nst, Q.npb, Q.PW, Q.PH, Q.Cout, Q.Hout, h[0], h[1], h[2], h[3], h[4], h[5]);
     }
     return 0;
 }
@@ -1077,6 +1067,8 @@ int tc_plan_launch(TcPlan* plan, cudaStream_t s) {
         case 2: return tc_launch_t<2>(plan, s);
         case 3: return tc_launch_t<3>(plan, s);
         case 4: return tc_launch_t<4>(plan, s);
+        case 6: return tc_launch_t<6>(plan, s);
+        case 8: return tc_launch_t<8>(plan, s);
     }
     set_error("tc_plan_launch: unsupported accumulator width %d", plan->P.CT);
     return FVC_ERR_STATE;
