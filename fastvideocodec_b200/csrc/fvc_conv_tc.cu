@@ -842,14 +842,27 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // (residual epilogues keep CT <= 192: 48 running sums leave registers for the prefetched skip data)
     const int sx_max = std::min(env_int("FVC_TC_SX", 4), (ep.res_act.p ? 192 : 256) / N);
     const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), 256 / N));
-    for (int sx = std::max(1, sx_max); sx >= 1 && !SX; --sx) {
+    // S trades weight re-reads / per-tile overhead (cost ~ one sub-tile's worth per tile, calibrated on
+    // SpyNet level 0/1) against filling the 148 SMs: score = wave efficiency * S / (S + 1).
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    double best_eff = -1.0;
+    for (int sx = std::max(1, sx_max); sx >= 1; --sx) {
         const int ct32 = sx * N / 32;
         if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * 128;
         patch = (patch + 1023) & ~(size_t)1023;
-        for (int nb = 2; nb >= 1 && !SX; --nb) {
+        const long nt = (long)in.B * L.nsub * cdiv(P.Hq, 16) * cdiv(P.Wq, 8 * sx);
+        const double eff = (double)nt / (double)(cdiv64(nt, sms) * sms) * (double)sx / (double)(sx + 1);
+        if (eff <= best_eff + 0.02) continue;   // a smaller S must buy a real gain
+        bool fits = false;
+        for (int nb = 2; nb >= 1 && !fits; --nb) {
             const long wroom = (long)smem_cap - (long)nb * (long)patch;
             const long want = nb == 2 ? std::min<long>(48 * 1024, 6L * tile_bytes) : 2L * tile_bytes;
             if (wroom < want) continue;
@@ -857,7 +870,10 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             int st = (int)std::min<long>(8, wroom / ((long)t * tile_bytes));
             if (st < 2) continue;
             SX = sx; nst = st; PW = pw; npb = nb; T = t;
+            fits = true;
         }
+        if (!fits) continue;
+        best_eff = eff;
     }
     if (!SX) {
         set_error("tc_plan_create: no tile shape fits shared memory");
@@ -1025,9 +1041,6 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         P.dbg = plan->dbg;
     }
     plan->smem = 1024 + (size_t)npb * P.patch_bytes + (size_t)nst * P.stage_bytes + 1024;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;
     plan->grid = std::max(1, std::min(ntiles, sms));
     *out = plan;

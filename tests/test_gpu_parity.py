@@ -415,3 +415,45 @@ def test_batch_equals_independent_views(model, dev):
         assert (both[0][v:v + 1] - one[v][0]).abs().max().item() <= 1e-6
     bpp_mean = 0.5 * (float(one[0][7]) + float(one[1][7]))
     assert abs(float(both[7]) - bpp_mean) <= 1e-5 * bpp_mean
+
+
+def test_config4_4k_frame_properties(model, dev):
+    """BASELINE configs[3]: 3840x2160 padded to 2176 rows (H, W multiples of 64): one P-frame, both engines agree
+    within the north-star gates (latent fraction <= 1e-4, +-1 only; bpp 0.5 %; PSNR 0.02 dB), deterministic."""
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    frames = synthetic_gop(2176, 3840, gop=2, gop_id=7)[:, 0].to(dev)
+    res = {}
+    for name, impl in _impls():
+        model.impl = impl
+        with torch.no_grad():
+            a = model(frames[1:2], frames[0:1])
+        res[name] = (a, model.get_intermediate("quant_mv"), model.get_intermediate("feat_hat"))
+        assert all(math.isfinite(float(v)) for v in a[1:])
+        if name == "tc":
+            with torch.no_grad():
+                b = model(frames[1:2], frames[0:1])
+            assert torch.equal(a[0], b[0]) and float(a[7]) == float(b[7])
+    if len(res) == 2:
+        (a, qa, fa), (b, qb, fb) = res["simt"], res["tc"]
+        assert (qa != qb).float().mean().item() <= 1e-4 and float((qa - qb).abs().max()) <= 1.0
+        assert (fa != fb).float().mean().item() <= 1e-4 and float((fa - fb).abs().max()) <= 1.0
+        assert abs(float(a[7]) - float(b[7])) <= 0.005 * float(a[7])
+        assert abs(_psnr(a[1]) - _psnr(b[1])) <= 0.02
+    model.release()
+
+
+def test_config5_multiview_batch8(model, dev):
+    """BASELINE configs[4]: 8 camera views of 1280x720 (padded to 768) folded into the batch
+    (train_multiview.py:232-233): B=8 equals eight B=1 runs (views are independent samples)."""
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    model.impl = _impls()[-1][1]
+    fr = synthetic_gop(768, 1280, gop=2, gop_id=11, batch=8).to(dev)   # [2, 8, 3, H, W]
+    with torch.no_grad():
+        both = model(fr[1], fr[0])
+        bpps = []
+        for v in (0, 3, 7):
+            one = model(fr[1, v:v + 1], fr[0, v:v + 1])
+            assert torch.equal(both[0][v:v + 1], one[0])
+            bpps.append(float(one[7]))
+    assert math.isfinite(float(both[7])) and float(both[0].min()) >= 0.0 and float(both[0].max()) <= 1.0
+    model.release()
