@@ -65,6 +65,12 @@ int simt_pack_weights(const ConvLayer& L, const float* w_ref, int CinP, int Cout
 int launch_conv_simt(const ConvLayer& L, const SimtWeights& W, ActT in, int Hout, int Wout, const Epilogue& ep,
                      cudaStream_t s);
 
+// fp32 CUDA-core path for convolutions with 2-3 output channels (fvc_conv_few.cu)
+bool few_supported(const ConvLayer& L, int CinP);
+int few_pack_weights(const ConvLayer& L, const float* w_ref, float** out, cudaStream_t s);
+int launch_conv_few(const ConvLayer& L, const float* w_packed, const float* bias, ActT in, int Hout, int Wout,
+                    const Epilogue& ep, cudaStream_t s);
+
 // TC (tcgen05): packed bf16 hi/lo weight stream + TMA descriptors (fvc_conv_tc.cu)
 struct TcPlan;  // opaque
 int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, int Wout, const Epilogue& ep,

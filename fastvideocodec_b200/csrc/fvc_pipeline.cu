@@ -39,6 +39,7 @@ struct ConvRt {
     bool have_w = false, have_b = false;
     SimtWeights simt;
     TcPlan* tc = nullptr;
+    float* few_w = nullptr;  // packed weights of the few-output-channel fp32 path
 };
 
 struct GdnRt {
@@ -69,6 +70,7 @@ struct fvc_ctx {
     BitEstRt be_z, be_mv;
     int64_t launches = 0;
     bool profile = false;
+    bool use_few = true;     // FVC_FEW=0 routes the 2-3 output-channel layers through the tensor-core engine
     double last_conv_seconds = -1.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
     std::vector<std::string> conv_event_names;
@@ -117,6 +119,7 @@ struct fvc_ctx {
     int alloc(T** p, size_t bytes) {
         void* q = nullptr;
         FVC_CUDA(cudaMalloc(&q, bytes ? bytes : 16));
+        FVC_CUDA(cudaMemset(q, 0, bytes ? bytes : 16));   // padded channels of ACT records stay finite (zero)
         allocs.push_back(q);
         *p = reinterpret_cast<T*>(q);
         return 0;
@@ -356,7 +359,10 @@ static int run_conv(fvc_ctx* c, const std::string& name, ActT in, int Hout, int 
         FVC_CUDA(cudaEventRecord(e0, s));
     }
     int rc;
-    if (c->impl == FVC_IMPL_TC && tc_supported(r.L, r.CinP)) {
+    if (c->impl == FVC_IMPL_TC && c->use_few && r.few_w && !in.parity && ep.act == FVC_ACT_NONE && !ep.res_act.p &&
+        !ep.out_act_relu.p && !ep.out_act_sq.p && ep.out_f32) {
+        rc = launch_conv_few(r.L, r.few_w, r.bias, in, Hout, Wout, ep, s);
+    } else if (c->impl == FVC_IMPL_TC && tc_supported(r.L, r.CinP)) {
         if (!r.tc) {
             rc = tc_plan_create(r.L, r.w_raw, in, Hout, Wout, ep, &r.tc, s);
             if (rc) return rc;
@@ -607,6 +613,8 @@ fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl) {
     c->B = B; c->H = H; c->W = W; c->levels = levels; c->impl = impl;
     const char* prof = getenv("FVC_PROFILE");
     c->profile = prof && prof[0] == '1';
+    const char* few = getenv("FVC_FEW");
+    c->use_few = !(few && few[0] == '0');
     if (build_layers(c) || build_buffers(c)) {
         fvc_ctx_destroy(c);
         return nullptr;
@@ -620,6 +628,7 @@ void fvc_ctx_destroy(fvc_ctx* c) {
     for (auto& kv : c->conv) {
         if (kv.second.simt.w) cudaFree(kv.second.simt.w);
         if (kv.second.tc) tc_plan_destroy(kv.second.tc);
+        if (kv.second.few_w) cudaFree(kv.second.few_w);
     }
     for (void* p : c->allocs) cudaFree(p);
     for (auto& ev : c->conv_events) {
@@ -648,6 +657,10 @@ int fvc_ctx_set_param(fvc_ctx* c, const char* key_c, const float* data, int64_t 
             FVC_CUDA(cudaMemcpyAsync(r.w_raw, data, n * 4, cudaMemcpyDeviceToDevice, s));
             int rc = simt_pack_weights(r.L, r.w_raw, r.CinP, r.CoutS, &r.simt, s);
             if (rc) return rc;
+            if (few_supported(r.L, r.CinP)) {
+                rc = few_pack_weights(r.L, r.w_raw, &r.few_w, s);
+                if (rc) return rc;
+            }
             if (r.tc) { tc_plan_destroy(r.tc); r.tc = nullptr; }
             r.have_w = true;
             return 0;
