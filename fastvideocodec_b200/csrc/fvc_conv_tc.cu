@@ -840,7 +840,12 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // leaves room for a deep weight ring; otherwise one (big-halo 7x7 layers: the exposed patch load is
     // a few % of a pass, a starved weight ring costs far more).
     // (residual epilogues keep CT <= 192: 48 running sums leave registers for the prefetched skip data)
-    const int sx_max = std::min(env_int("FVC_TC_SX", 4), (ep.res_act.p ? 192 : 256) / N);
+    // measured per layer class at 1080p (chain 48): N = 128 runs best with S = 1 (32 running sums, no spills:
+    // the 64-sum variant stalls on spill reloads queued behind its own global stores), N = 64 3x3/5x5 layers
+    // with S = 3, the 7x7 N = 64 layer (SpyNet conv2) with S = 4
+    const int ct_cap = N > 96 ? env_int("FVC_TC_CTMAX128", 128)
+                              : env_int("FVC_TC_CTMAX", (N > 32 && L.k < 7) ? 192 : 256);
+    const int sx_max = std::min(env_int("FVC_TC_SX", 4), std::max(1, std::min(ct_cap, ep.res_act.p ? 192 : 256) / N));
     const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), 256 / N));
     // S trades weight re-reads / per-tile overhead (cost ~ one sub-tile's worth per tile, calibrated on
     // SpyNet level 0/1) against filling the 148 SMs: score = wave efficiency * S / (S + 1).
