@@ -75,7 +75,8 @@ int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int 
     int Ho = transposed ? H * stride : H / stride, Wo = transposed ? W * stride : W / stride;
     TmpPool tmp(s);
     ActT in;
-    in.B = B; in.H = H; in.W = W; in.Cp = pad_c(Cin); in.parity = (!transposed && stride == 2) ? 1 : 0;
+    in.B = B; in.H = H; in.W = W; in.Cp = (impl == FVC_IMPL_TC && Cin <= 8) ? 8 : pad_c(Cin);   // narrow records for the input layers
+    in.parity = (!transposed && stride == 2) ? 1 : 0;
     if (tmp.get(&in.p, act_bytes(B, H, W, in.Cp))) return FVC_ERR_CUDA;
     int rc = launch_nchw_to_act(x, in, Cin, 0, s);
     if (rc) return rc;

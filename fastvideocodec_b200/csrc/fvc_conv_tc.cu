@@ -63,6 +63,8 @@ struct alignas(64) TcParams {
     int Hq, Wq, tiles_x, tiles_y, B, os, Hout, Wout, Cout, nchunks;
     uint32_t patch_bytes, patch_tx, btile_bytes, stage_bytes, tmem_cols, idesc;
     int npb, T;       // patch buffers (1 or 2), weight tiles per stage
+    int pitch;        // bytes per pixel of a record segment in shared memory: 128 (SWIZZLE_128B), or 32 for the
+                      // 8-channel records [hi 8 | lo 8] of the network's input layers (SWIZZLE_32B)
     uint32_t zero;    // always 0 (opaque to the compiler: used to build false dependencies)
     uint32_t acc_sleep_ns;
     unsigned long long* dbg;   // optional [8] cycle counters of block 0's MMA issuer (FVC_TC_DEBUG=1)
@@ -181,13 +183,13 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout = 2u) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);                 // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                                   // leading byte offset (ignored, K-major swizzled)
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;        // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                                   // descriptor version 1 (Blackwell)
-    d |= (uint64_t)2 << 61;                                   // SWIZZLE_128B
+    d |= (uint64_t)layout << 61;                              // 2: SWIZZLE_128B, 6: SWIZZLE_32B
     return d;
 }
 
@@ -210,13 +212,14 @@ __device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t alo, uint32_t 
 // tensor-pipe idle time).
 template <int KS>
 __device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint32_t alo, uint32_t ahi, uint32_t blo,
-                                            uint32_t bhi, uint32_t idesc, uint32_t acc0, int S, int s_first) {
+                                            uint32_t bhi, uint32_t idesc, uint32_t acc0, int S, int s_first,
+                                            uint32_t sstep) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         if (s < S && (s & 1) == s_first) {   // two issuer warps: even / odd sub-tiles
 #pragma unroll
             for (int k = 0; k < KS; ++k)
-                tc_mma2(dcol + (uint32_t)s * N, alo + (uint32_t)(64 * s + 2 * k), ahi, blo + (uint32_t)(2 * k), bhi,
+                tc_mma2(dcol + (uint32_t)s * N, alo + (uint32_t)s * sstep + (uint32_t)(2 * k), ahi, blo + (uint32_t)(2 * k), bhi,
                         idesc, k == 0 ? acc0 : 1u);
         }
     }
@@ -505,8 +508,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             uint32_t set = 0, pph = 0;          // patch ring
             uint32_t st = 0, stph = 0;          // weight-stage ring position and its phase bit
             // descriptors: everything but the start address is fixed; per MMA only the low word moves
-            const uint64_t adesc0 = make_desc(0, (uint32_t)P.PW * 128u);
-            const uint64_t bdesc0 = make_desc(0, 1024u);
+            const uint32_t layout = P.pitch == 32 ? 6u : 2u;
+            const uint64_t adesc0 = make_desc(0, (uint32_t)(P.PW * P.pitch), layout);
+            const uint64_t bdesc0 = make_desc(0, (uint32_t)(8 * P.pitch), layout);
+            const uint32_t sstep = (uint32_t)(8 * P.pitch) >> 4;   // next sub-tile: 8 pixels further
             const uint32_t ahi = (uint32_t)(adesc0 >> 32), bhi = (uint32_t)(bdesc0 >> 32);
             const uint32_t lo0 = (uint32_t)adesc0;            // LBO field; the address bits are added below
             const int S = P.S, T = P.T;
@@ -522,10 +527,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 const uint32_t pa16 = lo0 + ((patch0 + set * P.patch_bytes) >> 4);
                 const int ntaps = ps.ntaps, gtaps = ps.gtaps;
                 const bool two = ps.nbt == 2, short2 = ps.ks1 != 4;   // second tile per tap / with 2 k-steps
+                const bool narrow = ps.ks0 == 1;                      // 8-channel records: one k-step per tile
                 const int32_t* toffp = P.tap_off + ps.tap_first;
                 int slot = 0;                   // tile index inside the current weight stage
                 uint32_t blo = 0;
                 int t = 0;
+                if (narrow) {
+                    // 8-channel records: a tile is a single k-step, so whole weight stages (T/2 taps x 2 tiles x S
+                    // sub-tiles) are issued per loop iteration; per-tile loop control would dominate otherwise
+                    while (t < ntaps) {
+                        const int t0 = t, t1 = min(t + gtaps, ntaps);
+                        const uint32_t pb = gg & 1u;
+                        { const long long c0 = dbg_on ? clock64() : 0;
+                          mbar_wait(bar_aempty + 8 * pb, ((gg >> 1) & 1u) ^ 1u);
+                          if (dbg_on) w_aempty += clock64() - c0; }
+                        tc_fence_after();
+                        const uint32_t dcol = tmem_u + pb * CT;
+                        while (t < t1) {
+                            if (slot == 0) {
+                                const long long c0 = dbg_on ? clock64() : 0;
+                                mbar_wait(bar_bfull + 8 * st, stph);
+                                if (dbg_on) w_bfull += clock64() - c0;
+                                blo = bst16 + st * stage16;
+                            }
+                            const int nt = min((T - slot) >> 1, t1 - t);
+                            if (lead) {
+                                uint32_t toff = (uint32_t)toffp[t] >> 4;
+                                for (int u = 0; u < nt; ++u) {
+                                    const uint32_t alo = pa16 + toff;
+                                    toff = (uint32_t)toffp[min(t + u + 1, ntaps - 1)] >> 4;
+                                    const uint32_t b0 = blo + (uint32_t)(2 * u) * btile16;
+                                    issue_stage<1>(dcol, N, alo, ahi, b0, bhi, idesc, (t + u == t0) ? 0u : 1u, S, s_first, sstep);
+                                    issue_stage<1>(dcol, N, alo, ahi, b0 + btile16, bhi, idesc, 1u, S, s_first, sstep);
+                                }
+                            }
+                            t += nt;
+                            slot += 2 * nt;
+                            blo += (uint32_t)(2 * nt) * btile16;
+                            if (slot >= T || t == ntaps) {
+                                if (lead) tc_commit(bar_bempty + 8 * st);
+                                if (++st == nst) { st = 0; stph ^= 1u; }
+                                slot = 0;
+                            }
+                        }
+                        if (lead) tc_commit(bar_afull + 8 * pb);
+                        ++gg;
+                    }
+                }
                 uint32_t toff = (uint32_t)toffp[0] >> 4;
                 while (t < ntaps) {
                     const int t1 = min(t + gtaps, ntaps);
@@ -552,8 +600,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                             const long long ci0 = dbg_on ? clock64() : 0;
                             if (lead) {
                                 // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
-                                if (j == 1 && short2) issue_stage<2>(dcol, N, alo, ahi, blo, bhi, idesc, acc0, S, s_first);
-                                else issue_stage<4>(dcol, N, alo, ahi, blo, bhi, idesc, acc0, S, s_first);
+                                if (j == 1 && short2) issue_stage<2>(dcol, N, alo, ahi, blo, bhi, idesc, acc0, S, s_first, sstep);
+                                else issue_stage<4>(dcol, N, alo, ahi, blo, bhi, idesc, acc0, S, s_first, sstep);
                             }
                             if (dbg_on) { w_issue += clock64() - ci0; n_issue += 1; }
                             acc0 = 1u;
@@ -674,6 +722,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 struct BTileInfo {
     int8_t r, s;       // kernel tap
     uint8_t kind;      // 0: hi(c0..c0+63)  1: lo(c0..c0+63)  2: [hi(0..31) | hi(0..31)]  3: [lo(0..31) | 0]
+                       // 4: [hi(0..7) | hi(0..7)]  5: [lo(0..7) | 0]   (16-element rows)
     uint8_t c0;
 };
 __global__ void k_absmax(const float* __restrict__ w, size_t n, float* __restrict__ out) {
@@ -693,13 +742,14 @@ __global__ void k_absmax(const float* __restrict__ w, size_t n, float* __restric
 }
 
 __global__ void k_tc_pack(const float* __restrict__ w, e16* __restrict__ out, const BTileInfo* __restrict__ info,
-                          int ntiles, int N, int Cin, int Cout, int k, int transposed, float wscale) {
-    size_t n = (size_t)ntiles * N * 64;
+                          int ntiles, int N, int Cin, int Cout, int k, int transposed, float wscale, int rowlen) {
+    // rowlen: 16-bit elements per weight-tile row (64 = 128-byte rows; 16 = 32-byte rows of the 8-channel records)
+    size_t n = (size_t)ntiles * N * rowlen;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int col = (int)(i & 63);
-    int row = (int)((i >> 6) % N);
-    int tile = (int)(i / ((size_t)N * 64));
+    int col = (int)(i % rowlen);
+    int row = (int)((i / rowlen) % N);
+    int tile = (int)(i / ((size_t)N * rowlen));
     BTileInfo bi = info[tile];
     int ci;
     bool lo;
@@ -710,10 +760,17 @@ __global__ void k_tc_pack(const float* __restrict__ w, e16* __restrict__ out, co
     } else if (bi.kind == 2) {
         ci = col & 31;
         lo = false;
-    } else {
+    } else if (bi.kind == 3) {
         ci = col & 31;
         lo = true;
         zero = col >= 32;
+    } else if (bi.kind == 4) {   // [hi(0..7) | hi(0..7)] against [a_hi | a_lo]
+        ci = col & 7;
+        lo = false;
+    } else {                     // 5: [lo(0..7) | 0]
+        ci = col & 7;
+        lo = true;
+        zero = col >= 8;
     }
     float v = 0.f;
     if (!zero && ci < Cin && row < Cout) {
@@ -752,7 +809,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 bool tc_supported(const ConvLayer& L, int CinP) {
-    if (!(CinP == 32 || CinP == 64 || CinP == 128)) return false;
+    if (!(CinP == 8 || CinP == 32 || CinP == 64 || CinP == 128)) return false;
     if (L.k > 7 || L.Cout > 128) return false;
     return true;
 }
@@ -832,7 +889,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // ---- tile shape -------------------------------------------------------------------------------
     const int pw_align = env_int("FVC_TC_PW_ALIGN", 1);
     const int smem_cap = 232448 - 1024 /*alignment*/ - 1024 /*barriers + bias*/;
-    const int tile_bytes = N * 128;
+    const int pitch = Cp == 8 ? 32 : 128;
+    P.pitch = pitch;
+    const int tile_bytes = N * pitch;
     int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y, npb = 2, T = 1;
     // S*N accumulator columns per partial buffer, CT/32 in {1,2,3,4,6,8} (template instantiations),
     // CT <= 256 (two partial buffers in 512 TMEM columns, <= 64 running-sum registers per thread).
@@ -861,7 +920,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
-        size_t patch = (size_t)PH * pw * 128;
+        size_t patch = (size_t)PH * pw * pitch;
         patch = (patch + 1023) & ~(size_t)1023;
         const long nt = (long)in.B * L.nsub * cdiv(P.Hq, 16) * cdiv(P.Wq, 8 * sx);
         const double eff = (double)nt / (double)(cdiv64(nt, sms) * sms) * (double)sx / (double)(sx + 1);
@@ -872,6 +931,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             const long want = nb == 2 ? std::min<long>(48 * 1024, 6L * tile_bytes) : 2L * tile_bytes;
             if (wroom < want) continue;
             int t = (int)std::max<long>(1, std::min<long>(tmax, wroom / (4L * tile_bytes)));
+            if (pitch == 32) t = std::max(2, t & ~1);   // narrow records: stages hold whole taps (2 tiles each)
             int st = (int)std::min<long>(8, wroom / ((long)t * tile_bytes));
             if (st < 2) continue;
             SX = sx; nst = st; PW = pw; npb = nb; T = t;
@@ -887,9 +947,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     }
     P.S = SX; P.SX = SX; P.PW = PW; P.PH = PH; P.nst = nst; P.npb = npb; P.T = T;
     P.CT = SX * N;
-    P.patch_bytes = (uint32_t)((((size_t)PH * PW * 128) + 1023) & ~(size_t)1023);
-    P.patch_tx = (uint32_t)((size_t)PH * PW * 128);
-    P.btile_bytes = (uint32_t)N * 128u;
+    P.patch_bytes = (uint32_t)((((size_t)PH * PW * pitch) + 1023) & ~(size_t)1023);
+    P.patch_tx = (uint32_t)((size_t)PH * PW * pitch);
+    P.btile_bytes = (uint32_t)(N * pitch);
     P.stage_bytes = (uint32_t)T * P.btile_bytes;
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * P.CT)) cols <<= 1;
@@ -907,12 +967,13 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             delete plan;
             return FVC_ERR_STATE;
         }
-        for (auto& tp : g.taps) P.tap_off[ntapent++] = ((tp.ey - g.eymin) * PW + (tp.ex - g.exmin)) * 128;
+        for (auto& tp : g.taps) P.tap_off[ntapent++] = ((tp.ey - g.eymin) * PW + (tp.ex - g.exmin)) * pitch;
     }
     // ---- segment passes -----------------------------------------------------------------------------
     struct SegPass { int seg, nbt, ks0, ks1, kind0, kind1, c0; };
     std::vector<SegPass> segp;
-    if (Cp == 32) segp.push_back({0, 2, 4, 2, 2, 3, 0});
+    if (Cp == 8) segp.push_back({0, 2, 1, 1, 4, 5, 0});
+    else if (Cp == 32) segp.push_back({0, 2, 4, 2, 2, 3, 0});
     else if (Cp == 64) { segp.push_back({0, 2, 4, 4, 0, 1, 0}); segp.push_back({1, 1, 4, 0, 0, 0, 0}); }
     else {
         segp.push_back({0, 2, 4, 4, 0, 1, 0}); segp.push_back({1, 2, 4, 4, 0, 1, 64});
@@ -955,7 +1016,8 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // ---- weight stream -------------------------------------------------------------------------------
     const int nbt_total = (int)binfo.size();
     // padded by T tiles: the last weight stage of a pass always loads a full T-tile box
-    size_t wbytes = (size_t)(nbt_total + T) * N * 64 * sizeof(e16);
+    const int rowlen = pitch / 2;
+    size_t wbytes = (size_t)(nbt_total + T) * N * rowlen * sizeof(e16);
     BTileInfo* dinfo = nullptr;
     cudaError_t ce = cudaMalloc(&plan->wstream, wbytes);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(plan->wstream, 0, wbytes, s);
@@ -994,9 +1056,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         }
 #endif
         P.ep.acc_scale = ep.acc_scale / wscale;
-        size_t n = (size_t)nbt_total * N * 64;
+        size_t n = (size_t)nbt_total * N * rowlen;
         k_tc_pack<<<(unsigned)cdiv64((int64_t)n, 256), 256, 0, s>>>(w_ref, plan->wstream, dinfo, nbt_total, N, L.Cin,
-                                                                    L.Cout, L.k, L.transposed, wscale);
+                                                                    L.Cout, L.k, L.transposed, wscale, rowlen);
         g_launch_count++;
         ce = cudaGetLastError();
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);   // binfo (host vector) must outlive the copy
@@ -1011,14 +1073,16 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // ---- tensor maps -----------------------------------------------------------------------------------
     {
         const cuuint64_t rec = (cuuint64_t)Cp * 4;   // bytes per pixel record
-        const int nseg = Cp / 32;
+        const int nseg = std::max(1, Cp / 32);
         const int Wd = in.parity ? in.W / 2 : in.W, Hd = in.parity ? in.H / 2 : in.H;
-        cuuint64_t dims[5] = {64, (cuuint64_t)nseg, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)(in.B * P.planes)};
-        cuuint64_t strides[4] = {128, rec, rec * Wd, rec * Wd * Hd};
-        cuuint32_t box[5] = {64, 1, (cuuint32_t)PW, (cuuint32_t)PH, 1};
+        const CUtensorMapSwizzle swz = pitch == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+        cuuint64_t dims[5] = {(cuuint64_t)rowlen, (cuuint64_t)nseg, (cuuint64_t)Wd, (cuuint64_t)Hd,
+                              (cuuint64_t)(in.B * P.planes)};
+        cuuint64_t strides[4] = {(cuuint64_t)pitch, rec, rec * Wd, rec * Wd * Hd};
+        cuuint32_t box[5] = {(cuuint32_t)rowlen, 1, (cuuint32_t)PW, (cuuint32_t)PH, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = encode(&P.mapA, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 5, (void*)in.p, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled(A) failed: %d (Cp=%d W=%d H=%d PW=%d PH=%d)", (int)r, Cp, Wd, Hd, PW, PH);
@@ -1026,12 +1090,12 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             delete plan;
             return FVC_ERR_CUDA;
         }
-        cuuint64_t bdims[2] = {64, (cuuint64_t)(nbt_total + T) * N};
-        cuuint64_t bstr[1] = {128};
-        cuuint32_t bbox[2] = {64, (cuuint32_t)(T * N)};
+        cuuint64_t bdims[2] = {(cuuint64_t)rowlen, (cuuint64_t)(nbt_total + T) * N};
+        cuuint64_t bstr[1] = {(cuuint64_t)pitch};
+        cuuint32_t bbox[2] = {(cuuint32_t)rowlen, (cuuint32_t)(T * N)};
         cuuint32_t bes[2] = {1, 1};
         r = encode(&P.mapB, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, (void*)plan->wstream, bdims, bstr, bbox, bes,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r);

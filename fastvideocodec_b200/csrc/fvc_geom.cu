@@ -174,6 +174,26 @@ __device__ __forceinline__ void store_record32(e16* rec, const float* v, int nv)
     for (int j = 0; j < 4; ++j) d[4 + j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
 }
 
+// narrow record (Cp = 8): [hi 8][lo 8] = 32 B
+__device__ __forceinline__ void store_record8(e16* rec, const float* v, int nv) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        e16 h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+        if (2 * j < nv) split16(v[2 * j], h0, l0);
+        if (2 * j + 1 < nv) split16(v[2 * j + 1], h1, l1);
+        hi[j] = pack16x2(h0, h1);
+        lo[j] = pack16x2(l0, l1);
+    }
+    uint4* d = reinterpret_cast<uint4*>(rec);
+    d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    d[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void store_record(const ActT& t, e16* rec, const float* v, int nv) {
+    if (t.Cp == 8) store_record8(rec, v, nv);
+    else store_record32(rec, v, nv);
+}
+
 // ----------------------------------------------------------------------------------------------
 // SpyNet level preparation (endecoder.py:352-354): up = 2*up2(flow_prev); X = [im1, warp(im2,up), up]
 // ----------------------------------------------------------------------------------------------
@@ -209,12 +229,12 @@ __global__ void k_spynet_prep(const float* __restrict__ im1, const float* __rest
     }
     v[6] = ux;
     v[7] = uy;
-    store_record32(X.p + act_pixel_offset(X, b, y, x), v, 8);
+    store_record(X, X.p + act_pixel_offset(X, b, y, x), v, 8);
     reinterpret_cast<float2*>(flow_up)[i] = make_float2(ux, uy);
 }
 int launch_spynet_prep(const float* im1, const float* im2, const float* flow_prev, ActT X, float* flow_up,
                        cudaStream_t s) {
-    FVC_ARG(X.Cp == 32);
+    FVC_ARG(X.Cp == 32 || X.Cp == 8);
     int64_t n = (int64_t)X.B * X.H * X.W;
     k_spynet_prep<<<LAUNCH_1D(n, 128), 0, s>>>(im1, im2, flow_prev, X, flow_up);
     g_launch_count++;
@@ -246,10 +266,10 @@ __global__ void k_mc_prep(const float* __restrict__ ref, const float* __restrict
         v[3 + c] = pl[po];
         warpframe[((size_t)b * 3 + c) * hw + po] = v[c];
     }
-    store_record32(X.p + act_pixel_offset(X, b, y, x), v, 6);
+    store_record(X, X.p + act_pixel_offset(X, b, y, x), v, 6);
 }
 int launch_mc_prep(const float* ref, const float* mv, float* warpframe, ActT X, cudaStream_t s) {
-    FVC_ARG(X.Cp == 32);
+    FVC_ARG(X.Cp == 32 || X.Cp == 8);
     int64_t n = (int64_t)X.B * X.H * X.W;
     k_mc_prep<<<LAUNCH_1D(n, 128), 0, s>>>(ref, mv, warpframe, X);
     g_launch_count++;
@@ -277,11 +297,11 @@ __global__ void k_mc_finish(const float* __restrict__ res, const float* __restri
         pred[o] = p;
         v[c] = cur[o] - p;
     }
-    store_record32(R.p + act_pixel_offset(R, b, y, x), v, 3);
+    store_record(R, R.p + act_pixel_offset(R, b, y, x), v, 3);
 }
 int launch_mc_finish(const float* res, const float* warpframe, const float* cur, float* pred, ActT R,
                      cudaStream_t s) {
-    FVC_ARG(R.Cp == 32);
+    FVC_ARG(R.Cp == 32 || R.Cp == 8);
     int64_t n = (int64_t)R.B * R.H * R.W;
     k_mc_finish<<<LAUNCH_1D(n, 128), 0, s>>>(res, warpframe, cur, pred, R);
     g_launch_count++;

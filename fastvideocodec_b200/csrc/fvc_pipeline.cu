@@ -64,6 +64,7 @@ using namespace fvc;
 
 struct fvc_ctx {
     int B, H, W, levels, impl;
+    int cp_narrow = 32;
     std::vector<void*> allocs;
     std::map<std::string, ConvRt> conv;
     std::map<std::string, GdnRt> gdn;
@@ -145,23 +146,28 @@ static void add_conv(fvc_ctx* c, const std::string& name, int Cin, int Cout, int
 
 static int build_layers(fvc_ctx* c) {
     char buf[128];
+    // records of the network's input layers (<= 8 real channels): narrow [hi 8 | lo 8] records on the
+    // tensor-core engine (one 16-element k-step per tap and product pair instead of a 32-channel padded one)
+    const int cin_narrow = c->impl == FVC_IMPL_TC ? 8 : 32;
+    c->cp_narrow = cin_narrow;
     const int sp[5][2] = {{8, 32}, {32, 64}, {64, 32}, {32, 16}, {16, 2}};
     for (int l = 0; l < c->levels; ++l)
         for (int i = 0; i < 5; ++i) {
             snprintf(buf, sizeof(buf), "opticFlow.moduleBasic.%d.conv%d", l, i + 1);
-            add_conv(c, buf, sp[i][0], sp[i][1], 7, 1, 0, i < 4 ? FVC_ACT_RELU : FVC_ACT_NONE, pad_c(sp[i][0]));
+            add_conv(c, buf, sp[i][0], sp[i][1], 7, 1, 0, i < 4 ? FVC_ACT_RELU : FVC_ACT_NONE,
+                     i == 0 ? cin_narrow : pad_c(sp[i][0]));
         }
     for (int i = 1; i <= 8; ++i) {
         snprintf(buf, sizeof(buf), "mvEncoder.conv%d", i);
         add_conv(c, buf, i == 1 ? 2 : 128, 128, 3, (i & 1) ? 2 : 1, 0, i < 8 ? FVC_ACT_LRELU01 : FVC_ACT_NONE,
-                 i == 1 ? 32 : 128);
+                 i == 1 ? cin_narrow : 128);
     }
     for (int i = 1; i <= 8; ++i) {
         snprintf(buf, sizeof(buf), "mvDecoder.deconv%d", i);
         if (i & 1) add_conv(c, buf, 128, 128, 3, 2, 1, FVC_ACT_LRELU01, 128);
         else add_conv(c, buf, 128, i == 8 ? 2 : 128, 3, 1, 0, i < 8 ? FVC_ACT_LRELU01 : FVC_ACT_NONE, 128);
     }
-    add_conv(c, "warpnet.feature_ext", 6, 64, 3, 1, 0, FVC_ACT_RELU, 32);
+    add_conv(c, "warpnet.feature_ext", 6, 64, 3, 1, 0, FVC_ACT_RELU, cin_narrow);
     for (int i = 0; i < 6; ++i) {
         snprintf(buf, sizeof(buf), "warpnet.conv%d.conv1", i);
         add_conv(c, buf, 64, 64, 3, 1, 0, FVC_ACT_RELU, 64);  // relu2 fused into conv1's epilogue
@@ -169,7 +175,7 @@ static int build_layers(fvc_ctx* c) {
         add_conv(c, buf, 64, 64, 3, 1, 0, FVC_ACT_NONE, 64);
     }
     add_conv(c, "warpnet.conv6", 64, 3, 3, 1, 0, FVC_ACT_NONE, 64);
-    add_conv(c, "resEncoder.conv1", 3, 64, 5, 2, 0, FVC_ACT_NONE, 32);
+    add_conv(c, "resEncoder.conv1", 3, 64, 5, 2, 0, FVC_ACT_NONE, cin_narrow);
     add_conv(c, "resEncoder.conv2", 64, 64, 5, 2, 0, FVC_ACT_NONE, 64);
     add_conv(c, "resEncoder.conv3", 64, 64, 5, 2, 0, FVC_ACT_NONE, 64);
     add_conv(c, "resEncoder.conv4", 64, 96, 5, 2, 0, FVC_ACT_NONE, 64);
@@ -231,7 +237,7 @@ static int build_buffers(fvc_ctx* c) {
     c->sflow_up.assign(L, nullptr); c->sflow.assign(L, nullptr);
     for (int i = 0; i < L; ++i) {
         int h = H >> (L - 1 - i), w = W >> (L - 1 - i);
-        A(c->alloc_act(&c->sx[i], h, w, 32, 0));
+        A(c->alloc_act(&c->sx[i], h, w, c->cp_narrow, 0));
         A(c->alloc_act(&c->sa1[i], h, w, 32, 0));
         A(c->alloc_act(&c->sa2[i], h, w, 64, 0));
         A(c->alloc_act(&c->sa3[i], h, w, 32, 0));
@@ -239,7 +245,7 @@ static int build_buffers(fvc_ctx* c) {
         A(c->alloc(&c->sflow_up[i], (size_t)B * h * w * 2 * 4));
         A(c->alloc(&c->sflow[i], (size_t)B * h * w * 2 * 4));
     }
-    A(c->alloc_act(&c->estmv_act, H, W, 32, 1));
+    A(c->alloc_act(&c->estmv_act, H, W, c->cp_narrow, 1));
     // mvEncoder: conv i output at H >> ceil(i/2); parity layout when the consumer is a stride-2 conv
     for (int i = 1; i <= 7; ++i) {
         int sh = (i + 1) / 2;
@@ -253,7 +259,7 @@ static int build_buffers(fvc_ctx* c) {
     }
     A(c->alloc(&c->mv_hat, (size_t)B * H * W * 2 * 4));
     A(c->alloc(&c->warpframe, (size_t)B * 3 * H * W * 4));
-    A(c->alloc_act(&c->xmc, H, W, 32, 0));
+    A(c->alloc_act(&c->xmc, H, W, c->cp_narrow, 0));
     A(c->alloc_act(&c->wf, H, W, 64, 0));
     A(c->alloc_act(&c->wt0, H, W, 64, 0));
     A(c->alloc_act(&c->wc0, H, W, 64, 0));
@@ -278,7 +284,7 @@ static int build_buffers(fvc_ctx* c) {
     A(c->alloc_act(&c->wc5, H, W, 64, 0));
     A(c->alloc(&c->wres, (size_t)B * H * W * 3 * 4));
     A(c->alloc(&c->prediction, (size_t)B * 3 * H * W * 4));
-    A(c->alloc_act(&c->residual, H, W, 32, 1));
+    A(c->alloc_act(&c->residual, H, W, c->cp_narrow, 1));
     for (int i = 0; i < 3; ++i) {
         A(c->alloc_act(&c->r_raw[i], H >> (i + 1), W >> (i + 1), 64, 0));
         A(c->alloc_act(&c->r[i], H >> (i + 1), W >> (i + 1), 64, 1));
