@@ -63,6 +63,8 @@ struct alignas(64) TcParams {
     int Hq, Wq, tiles_x, tiles_y, B, os, Hout, Wout, Cout, nchunks;
     uint32_t patch_bytes, patch_tx, btile_bytes, stage_bytes, tmem_cols, idesc;
     int npb, T;       // patch buffers (1 or 2), weight tiles per stage
+    int merged;       // Cout <= 16: weight rows interleave 8-row blocks of w_hi and w_lo (MMA N = 32, two
+                      // products per A read); the epilogue adds the two column blocks of every channel chunk
     int pitch;        // bytes per pixel of a record segment in shared memory: 128 (SWIZZLE_128B), or 32 for the
                       // 8-channel records [hi 8 | lo 8] of the network's input layers (SWIZZLE_32B)
     uint32_t zero;    // always 0 (opaque to the compiler: used to build false dependencies)
@@ -257,7 +259,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
                                               int b, int sub, int ty, int tx, int th, int tw, uint32_t colbase) {
     const Epilogue& ep = P.ep;
     constexpr int HB = NCH > 4 ? 2 : NCH;   // chunks per batch (register budget: 96 regs at 576 threads)
-    const int N = P.N, Cout = P.Cout, act = ep.act;
+    const int N = P.merged ? (P.N >> 1) : P.N, Cout = P.Cout, act = ep.act;   // channels per sub-tile
     const float acc_scale = ep.acc_scale;
     const int qy = ty * 16 + th;
     const int oy = qy * P.os + P.sub[sub].py;
@@ -681,7 +683,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const int sub = t % P.nsub;
             const int b = t / P.nsub;
             if constexpr (!PARK) {
-                tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+                if constexpr (NCH % 2 == 0) {
+                    if (P.merged) {
+                        // columns come in 8-wide blocks [w_hi products | w_lo products]: fold them
+#pragma unroll
+                        for (int i = 0; i < NCH / 2; ++i)
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) run[i * 8 + q] = run[2 * i * 8 + q] + run[(2 * i + 1) * 8 + q];
+                        tile_epilogue<NCH / 2, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase >> 1);
+                    } else {
+                        tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+                    }
+                } else {
+                    tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+                }
             } else {
                 // 48/64 running sums + the epilogue state do not fit 96 registers (ncu: spill reloads
                 // queued behind the epilogue's global stores were its main stall).  Park the upper half of
@@ -723,6 +738,7 @@ struct BTileInfo {
     int8_t r, s;       // kernel tap
     uint8_t kind;      // 0: hi(c0..c0+63)  1: lo(c0..c0+63)  2: [hi(0..31) | hi(0..31)]  3: [lo(0..31) | 0]
                        // 4: [hi(0..7) | hi(0..7)]  5: [lo(0..7) | 0]   (16-element rows)
+                       // 6, 7, 8: merged hi/lo row blocks (see k_tc_pack)
     uint8_t c0;
 };
 __global__ void k_absmax(const float* __restrict__ w, size_t n, float* __restrict__ out) {
@@ -767,10 +783,24 @@ __global__ void k_tc_pack(const float* __restrict__ w, e16* __restrict__ out, co
     } else if (bi.kind == 4) {   // [hi(0..7) | hi(0..7)] against [a_hi | a_lo]
         ci = col & 7;
         lo = false;
-    } else {                     // 5: [lo(0..7) | 0]
+    } else if (bi.kind == 5) {   // [lo(0..7) | 0]
         ci = col & 7;
         lo = true;
         zero = col >= 8;
+    } else {
+        // merged tiles (MMA N = 32 for <= 16 output channels): 8-row blocks alternate w_hi / w_lo rows
+        const bool lo_block = (row >> 3) & 1;
+        row = ((row >> 4) << 3) | (row & 7);          // output channel of this row
+        lo = lo_block;
+        if (bi.kind == 6) {                           // A = a_hi(c0..c0+63): w_hi and w_lo rows
+            ci = bi.c0 + col;
+        } else if (bi.kind == 7) {                    // A = a_lo(c0..c0+63): w_hi rows only
+            ci = bi.c0 + col;
+            zero = lo_block;
+        } else {                                      // 8: A = [a_hi(0..31) | a_lo(0..31)]
+            ci = col & 31;
+            zero = lo_block && col >= 32;
+        }
     }
     float v = 0.f;
     if (!zero && ci < Cin && row < Cout) {
@@ -838,8 +868,13 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     if (ep.out_act.p) chans = std::max(chans, ep.out_act.Cp);
     if (ep.out_act_relu.p) chans = std::max(chans, ep.out_act_relu.Cp);
     if (ep.out_act_sq.p) chans = std::max(chans, ep.out_act_sq.Cp);
-    const int N = std::max(16, cdiv(chans, 16) * 16);   // MMA N: every channel of an output record is produced
+    // Cout <= 16 ("merged"): padded channels of the output records are never written (the buffers are
+    // zero-initialised) and the MMA N = 32 carries w_hi and w_lo row blocks side by side.
+    const bool merged = L.Cout <= 16 && Cp >= 32 && env_int("FVC_TC_MERGED", 1) != 0;
+    if (merged) chans = 16;
+    const int N = merged ? 32 : std::max(16, cdiv(chans, 16) * 16);   // MMA N
     P.N = N;
+    P.merged = merged ? 1 : 0;
     P.nchunks = 0;
     P.Cout = L.Cout;
     P.nsub = L.nsub;
@@ -918,6 +953,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     for (int sx = std::max(1, sx_max); sx >= 1; --sx) {
         const int ct32 = sx * N / 32;
         if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
+        if (merged && (sx & 1)) continue;   // a thread must own both column blocks (hi, lo) of its channel chunks
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * pitch;
@@ -972,7 +1008,14 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // ---- segment passes -----------------------------------------------------------------------------
     struct SegPass { int seg, nbt, ks0, ks1, kind0, kind1, c0; };
     std::vector<SegPass> segp;
-    if (Cp == 8) segp.push_back({0, 2, 1, 1, 4, 5, 0});
+    if (merged) {
+        if (Cp == 32) segp.push_back({0, 1, 4, 0, 8, 0, 0});
+        else if (Cp == 64) { segp.push_back({0, 1, 4, 0, 6, 0, 0}); segp.push_back({1, 1, 4, 0, 7, 0, 0}); }
+        else {
+            segp.push_back({0, 1, 4, 0, 6, 0, 0}); segp.push_back({1, 1, 4, 0, 6, 0, 64});
+            segp.push_back({2, 1, 4, 0, 7, 0, 0}); segp.push_back({3, 1, 4, 0, 7, 0, 64});
+        }
+    } else if (Cp == 8) segp.push_back({0, 2, 1, 1, 4, 5, 0});
     else if (Cp == 32) segp.push_back({0, 2, 4, 2, 2, 3, 0});
     else if (Cp == 64) { segp.push_back({0, 2, 4, 4, 0, 1, 0}); segp.push_back({1, 1, 4, 0, 0, 0, 0}); }
     else {
