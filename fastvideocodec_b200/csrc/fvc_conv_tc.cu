@@ -870,9 +870,10 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     if (ep.out_act_sq.p) chans = std::max(chans, ep.out_act_sq.Cp);
     // Cout <= 16 ("merged"): padded channels of the output records are never written (the buffers are
     // zero-initialised) and the MMA N = 32 carries w_hi and w_lo row blocks side by side.
-    const bool merged = L.Cout <= 16 && Cp >= 32 && env_int("FVC_TC_MERGED", 1) != 0;
-    if (merged) chans = 16;
-    const int N = merged ? 32 : std::max(16, cdiv(chans, 16) * 16);   // MMA N
+    const int merge_max = env_int("FVC_TC_MERGED", 32);
+    const bool merged = L.Cout <= merge_max && Cp >= 32;
+    if (merged) chans = cdiv(L.Cout, 16) * 16;
+    const int N = merged ? 2 * chans : std::max(16, cdiv(chans, 16) * 16);   // MMA N
     P.N = N;
     P.merged = merged ? 1 : 0;
     P.nchunks = 0;
@@ -939,7 +940,8 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // with S = 3, the 7x7 N = 64 layer (SpyNet conv2) with S = 4
     const int ct_cap = N > 96 ? env_int("FVC_TC_CTMAX128", 128)
                               : env_int("FVC_TC_CTMAX", (N > 32 && L.k < 7) ? 192 : 256);
-    const int sx_max = std::min(env_int("FVC_TC_SX", 4), std::max(1, std::min(ct_cap, ep.res_act.p ? 192 : 256) / N));
+    const int sx_max = std::min(env_int("FVC_TC_SX", 4),
+                                std::max(1, std::min(merged ? 128 : ct_cap, ep.res_act.p ? 192 : 256) / N));
     const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), 256 / N));
     // S trades weight re-reads / per-tile overhead (cost ~ one sub-tile's worth per tile, calibrated on
     // SpyNet level 0/1) against filling the 148 SMs: score = wave efficiency * S / (S + 1).
