@@ -552,20 +552,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                                 if (dbg_on) w_bfull += clock64() - c0;
                                 blo = bst16 + st * stage16;
                             }
-                            const int nt = min((T - slot) >> 1, t1 - t);
+                            const int tpt = two ? 2 : 1;       // tiles per tap (1 with merged hi/lo rows)
+                            const int nt = min((T - slot) / tpt, t1 - t);
                             if (lead) {
                                 uint32_t toff = (uint32_t)toffp[t] >> 4;
                                 for (int u = 0; u < nt; ++u) {
                                     const uint32_t alo = pa16 + toff;
                                     toff = (uint32_t)toffp[min(t + u + 1, ntaps - 1)] >> 4;
-                                    const uint32_t b0 = blo + (uint32_t)(2 * u) * btile16;
+                                    const uint32_t b0 = blo + (uint32_t)(tpt * u) * btile16;
                                     issue_stage<1>(dcol, N, alo, ahi, b0, bhi, idesc, (t + u == t0) ? 0u : 1u, S, s_first, sstep);
-                                    issue_stage<1>(dcol, N, alo, ahi, b0 + btile16, bhi, idesc, 1u, S, s_first, sstep);
+                                    if (two) issue_stage<1>(dcol, N, alo, ahi, b0 + btile16, bhi, idesc, 1u, S, s_first, sstep);
                                 }
                             }
                             t += nt;
-                            slot += 2 * nt;
-                            blo += (uint32_t)(2 * nt) * btile16;
+                            slot += tpt * nt;
+                            blo += (uint32_t)(tpt * nt) * btile16;
                             if (slot >= T || t == ntaps) {
                                 if (lead) tc_commit(bar_bempty + 8 * st);
                                 if (++st == nst) { st = 0; stph ^= 1u; }
@@ -792,7 +793,10 @@ __global__ void k_tc_pack(const float* __restrict__ w, e16* __restrict__ out, co
         const bool lo_block = (row >> 3) & 1;
         row = ((row >> 4) << 3) | (row & 7);          // output channel of this row
         lo = lo_block;
-        if (bi.kind == 6) {                           // A = a_hi(c0..c0+63): w_hi and w_lo rows
+        if (bi.kind == 9) {                           // narrow records: A = [a_hi(0..7) | a_lo(0..7)]
+            ci = col & 7;
+            zero = lo_block && col >= 8;
+        } else if (bi.kind == 6) {                    // A = a_hi(c0..c0+63): w_hi and w_lo rows
             ci = bi.c0 + col;
         } else if (bi.kind == 7) {                    // A = a_lo(c0..c0+63): w_hi rows only
             ci = bi.c0 + col;
@@ -871,7 +875,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // Cout <= 16 ("merged"): padded channels of the output records are never written (the buffers are
     // zero-initialised) and the MMA N = 32 carries w_hi and w_lo row blocks side by side.
     const int merge_max = env_int("FVC_TC_MERGED", 32);
-    const bool merged = L.Cout <= merge_max && Cp >= 32;
+    const bool merged = (Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 0));
     if (merged) chans = cdiv(L.Cout, 16) * 16;
     const int N = merged ? 2 * chans : std::max(16, cdiv(chans, 16) * 16);   // MMA N
     P.N = N;
@@ -955,7 +959,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     for (int sx = std::max(1, sx_max); sx >= 1; --sx) {
         const int ct32 = sx * N / 32;
         if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
-        if (merged && (sx & 1)) continue;   // a thread must own both column blocks (hi, lo) of its channel chunks
+        if (merged && (ct32 & 1)) continue; // a thread must own both column blocks (hi, lo) of its channel chunks
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * pitch;
@@ -969,7 +973,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             const long want = nb == 2 ? std::min<long>(48 * 1024, 6L * tile_bytes) : 2L * tile_bytes;
             if (wroom < want) continue;
             int t = (int)std::max<long>(1, std::min<long>(tmax, wroom / (4L * tile_bytes)));
-            if (pitch == 32) t = std::max(2, t & ~1);   // narrow records: stages hold whole taps (2 tiles each)
+            if (pitch == 32 && !merged) t = std::max(2, t & ~1);   // narrow records: stages hold whole taps (2 tiles each)
             int st = (int)std::min<long>(8, wroom / ((long)t * tile_bytes));
             if (st < 2) continue;
             SX = sx; nst = st; PW = pw; npb = nb; T = t;
@@ -1011,7 +1015,8 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     struct SegPass { int seg, nbt, ks0, ks1, kind0, kind1, c0; };
     std::vector<SegPass> segp;
     if (merged) {
-        if (Cp == 32) segp.push_back({0, 1, 4, 0, 8, 0, 0});
+        if (Cp == 8) segp.push_back({0, 1, 1, 0, 9, 0, 0});
+        else if (Cp == 32) segp.push_back({0, 1, 4, 0, 8, 0, 0});
         else if (Cp == 64) { segp.push_back({0, 1, 4, 0, 6, 0, 0}); segp.push_back({1, 1, 4, 0, 7, 0, 0}); }
         else {
             segp.push_back({0, 1, 4, 0, 6, 0, 0}); segp.push_back({1, 1, 4, 0, 6, 0, 64});
