@@ -294,11 +294,30 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
             ss[j] = s0;
             if (RES) {
                 if (s0 != cur_s) enter_pixel(s0);
-                rh[j] = make_uint4(0, 0, 0, 0);
-                rl[j] = make_uint4(0, 0, 0, 0);
+                if (!((NCH % 2 == 0) && (HB % 2 == 0)) || (j & 1) == 0) {
+                    rh[j] = make_uint4(0, 0, 0, 0);
+                    rl[j] = make_uint4(0, 0, 0, 0);
+                    if ((NCH % 2 == 0) && (HB % 2 == 0)) {
+                        rh[j + 1 < HB ? j + 1 : j] = make_uint4(0, 0, 0, 0);
+                        rl[j + 1 < HB ? j + 1 : j] = make_uint4(0, 0, 0, 0);
+                    }
+                }
                 if (ok && c00 < ep.res_act.Cp) {
-                    rh[j] = __ldg(reinterpret_cast<const uint4*>(rec_res + c00));
-                    rl[j] = __ldg(reinterpret_cast<const uint4*>(rec_res + ep.res_act.Cp + c00));
+                    if ((NCH % 2 == 0) && (HB % 2 == 0)) {
+                        // chunk pairs: one 32-byte (full sector) load for the hi halves and one for the lo halves
+                        if ((j & 1) == 0) {
+                            uint32_t t8[8];
+                            ld_global_nc_v8(rec_res + c00, t8);
+                            rh[j] = make_uint4(t8[0], t8[1], t8[2], t8[3]);
+                            rh[j + 1 < HB ? j + 1 : j] = make_uint4(t8[4], t8[5], t8[6], t8[7]);
+                            ld_global_nc_v8(rec_res + ep.res_act.Cp + c00, t8);
+                            rl[j] = make_uint4(t8[0], t8[1], t8[2], t8[3]);
+                            rl[j + 1 < HB ? j + 1 : j] = make_uint4(t8[4], t8[5], t8[6], t8[7]);
+                        }
+                    } else {
+                        rh[j] = __ldg(reinterpret_cast<const uint4*>(rec_res + c00));
+                        rl[j] = __ldg(reinterpret_cast<const uint4*>(rec_res + ep.res_act.Cp + c00));
+                    }
                 }
             }
             c00 += 8;
@@ -646,6 +665,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const int tiles_xy = P.tiles_x * P.tiles_y;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int ng = P.sub[(tile / tiles_xy) % P.nsub].ngroups;
+            if (RES) {
+                // pull this thread's skip-connection records into L2 while the tile's MMAs run (the epilogue's
+                // loads then hit L2 instead of paying DRAM latency in the middle of the store stream)
+                int t = tile;
+                const int tx = t % P.tiles_x; t /= P.tiles_x;
+                const int ty = t % P.tiles_y; t /= P.tiles_y;
+                const int sub = t % P.nsub;
+                const int b = t / P.nsub;
+                const int Nv = P.merged ? (P.N >> 1) : P.N;
+                const int cb = P.merged ? (int)(colbase >> 1) : (int)colbase;
+                const int nc = P.merged ? NCH * 4 : NCH * 8;
+                const int qy = ty * 16 + th;
+                if (qy < P.Hq) {
+                    for (int s = cb / Nv; s <= (cb + nc - 1) / Nv; ++s) {
+                        const int qx = (tx * P.SX + s) * 8 + tw;
+                        if (qx >= P.Wq) continue;
+                        const e16* rec = P.ep.res_act.p + act_pixel_offset(P.ep.res_act, b, qy * P.os + P.sub[sub].py,
+                                                                         qx * P.os + P.sub[sub].px);
+                        const int c0 = max(cb - s * Nv, 0);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + c0));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + P.ep.res_act.Cp + c0));
+                    }
+                }
+            }
             for (int g = 0; g < ng; ++g, ++gg) {
                 const uint32_t pb = gg & 1u;
                 mbar_wait_sleep(bar_afull + 8 * pb, (gg >> 1) & 1u, P.acc_sleep_ns);
