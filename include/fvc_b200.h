@@ -43,7 +43,7 @@ extern "C" {
 
 /* convolution engines */
 #define FVC_IMPL_SIMT 0 /* fp32 CUDA-core implicit GEMM (checker / bring-up path) */
-#define FVC_IMPL_TC 1   /* tcgen05 + TMEM + TMA, split-bf16 x3 with fp32 accumulate */
+#define FVC_IMPL_TC 1   /* tcgen05 + TMEM + TMA, fp16 hi/lo operand pairs (3 MMAs per product), fp32 accumulate */
 
 FVC_API int fvc_version(void);
 FVC_API const char* fvc_last_error(void);
