@@ -8,6 +8,7 @@
 // column, so neighbouring threads read neighbouring float4s (conflict-free) and each input value loaded from
 // shared memory is used for up to 4 x CO x 4 FMAs.  Input channels are processed in chunks of 16.
 #include "fvc_kernels.cuh"
+#include "fvc_epilogue.cuh"
 
 namespace fvc {
 
@@ -61,12 +62,9 @@ __global__ void __launch_bounds__(128) k_conv_few(const __grid_constant__ FewPar
             float v[16];
             if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
                 const e16* rec = P.in.p + (((size_t)b * P.H + y) * P.W + x) * (size_t)(2 * Cp) + chunk * 16;
-                const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(rec));
-                const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(rec + 8));
-                const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(rec + Cp));
-                const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(rec + Cp + 8));
-                const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                uint32_t hh[8], ll[8];   // 16 channels = one 32-byte sector each for the hi and the lo halves
+                ld_global_nc_v8(rec, hh);
+                ld_global_nc_v8(rec + Cp, ll);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     float a0, a1, b0, b1;

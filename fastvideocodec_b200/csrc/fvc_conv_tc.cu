@@ -385,7 +385,10 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
                         if (c0 + q < Cout) w[q] += ep.res_f32[pixC + c0 + q];
                 }
                 if (ep.out_f32) {
-                    if ((Cout & 3) == 0) {
+                    if ((Cout & 7) == 0) {
+                        // 8 channels = one 32-byte sector per store
+                        if (c0 < Cout) st_global_v8(ep.out_f32 + pixC + c0, reinterpret_cast<const uint32_t*>(w));
+                    } else if ((Cout & 3) == 0) {
 #pragma unroll
                         for (int q = 0; q < 8; q += 4)
                             if (c0 + q < Cout)
