@@ -112,6 +112,9 @@ struct fvc_ctx {
     int* bits_counts = nullptr;                      // device [3]
     float* scalars = nullptr;                        // device [7] (internal copy)
     float *stage_cur = nullptr, *stage_ref = nullptr, *stage_rec = nullptr;  // GOP driver staging
+    cudaStream_t copy_stream = nullptr;              // H2D of the GOP's frames, overlapped with the computation
+    cudaEvent_t copy_fence = nullptr;
+    std::vector<cudaEvent_t> copy_events;
     int stage_G = 0;
     float* stage_frames = nullptr;
     float* stage_scalars = nullptr;
@@ -644,6 +647,9 @@ void fvc_ctx_destroy(fvc_ctx* c) {
     if (c->stage_frames) cudaFree(c->stage_frames);
     if (c->stage_rec) cudaFree(c->stage_rec);
     if (c->stage_scalars) cudaFree(c->stage_scalars);
+    for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+    if (c->copy_fence) cudaEventDestroy(c->copy_fence);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -831,10 +837,30 @@ int fvc_gop_forward_host(fvc_ctx* c, const float* frames_host, int G, float* rec
         FVC_CUDA(cudaMalloc(&c->stage_scalars, (size_t)(G - 1) * 7 * 4));
         c->stage_G = G;
     }
-    FVC_CUDA(cudaMemcpyAsync(c->stage_frames, frames_host, fsz * G * 4, cudaMemcpyHostToDevice, s));
+    // Frames are uploaded one by one on a copy stream; P-frame i only waits for frames i-1 and i, so the
+    // upload of the rest of the GOP overlaps the computation (10 x 25 MB at 1080p = ~5 ms over PCIe otherwise).
+    if (!c->copy_stream) {
+        FVC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        FVC_CUDA(cudaEventCreateWithFlags(&c->copy_fence, cudaEventDisableTiming));
+    }
+    while ((int)c->copy_events.size() < G) {
+        cudaEvent_t e;
+        FVC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->copy_events.push_back(e);
+    }
+    // the staging buffer may still be read by work queued on `s` from a previous call
+    FVC_CUDA(cudaEventRecord(c->copy_fence, s));
+    FVC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_fence, 0));
+    for (int i = 0; i < G; ++i) {
+        FVC_CUDA(cudaMemcpyAsync(c->stage_frames + (size_t)i * fsz, frames_host + (size_t)i * fsz, fsz * 4,
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+        FVC_CUDA(cudaEventRecord(c->copy_events[i], c->copy_stream));
+    }
+    FVC_CUDA(cudaStreamWaitEvent(s, c->copy_events[0], 0));
     const float* prev = c->stage_frames;  // decoded I-frame (models.py:370)
     for (int i = 1; i < G; ++i) {
         float* rec = c->stage_rec + (size_t)(i - 1) * fsz;
+        FVC_CUDA(cudaStreamWaitEvent(s, c->copy_events[i], 0));
         int rc = fvc_pframe_forward(c, c->stage_frames + (size_t)i * fsz, prev, rec, c->stage_scalars + (i - 1) * 7,
                                     stream);
         if (rc) return rc;
