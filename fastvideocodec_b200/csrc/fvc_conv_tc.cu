@@ -47,6 +47,11 @@ struct TcPass {
     int8_t nbt, ks0, ks1;  // weight tiles per tap and their k-step counts (16 channels per k-step)
     int8_t gtaps;          // taps per accumulation group (one TMEM chain, drained to registers)
     uint32_t btile_first;  // first weight tile of the pass in the stream
+    // accumulation groups (TMEM chains of <= chain_max MMAs) may run across the segment passes of a tile:
+    // bit t of gmask = a new group starts at tap t; gend = the group is closed after the last tap
+    // (low-tap layers, e.g. stride-2 transposed convolutions, otherwise drain TMEM once per pass)
+    uint32_t gmask_lo, gmask_hi;
+    int32_t gend;
 };
 struct TcSub {
     int pass_first, npass, py, px;
@@ -529,6 +534,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             PassIter cur;
             cur.tile = blockIdx.x; cur.pass = 0; cur.decode(P);
             uint32_t gg = 0;                    // accumulation-group counter
+            bool gopen = false;                 // a group (TMEM chain) is open; it may span segment passes
+            uint32_t gpb = 0, gdcol = 0, gacc0 = 0;
             uint32_t set = 0, pph = 0;          // patch ring
             uint32_t st = 0, stph = 0;          // weight-stage ring position and its phase bit
             // descriptors: everything but the start address is fixed; per MMA only the low word moves
@@ -600,46 +607,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     }
                 }
                 uint32_t toff = (uint32_t)toffp[0] >> 4;
-                while (t < ntaps) {
-                    const int t1 = min(t + gtaps, ntaps);
-                    // partial buffer must have been drained by the accumulator warps
-                    const uint32_t pb = gg & 1u;
-                    { const long long c0 = dbg_on ? clock64() : 0;
-                      mbar_wait(bar_aempty + 8 * pb, ((gg >> 1) & 1u) ^ 1u);
-                      if (dbg_on) w_aempty += clock64() - c0; }
-                    tc_fence_after();
-                    const uint32_t dcol = tmem_u + pb * CT;
-                    uint32_t acc0 = 0u;
-                    for (; t < t1; ++t) {
-                        const uint32_t alo = pa16 + toff;
-                        toff = (uint32_t)toffp[min(t + 1, ntaps - 1)] >> 4;   // prefetched for the next tap
+                const unsigned long long gmask = ((unsigned long long)ps.gmask_hi << 32) | ps.gmask_lo;
+                for (; t < ntaps; ++t) {
+                    if ((gmask >> t) & 1ull) {
+                        // a new accumulation group starts here: hand the finished chain to the accumulator
+                        // warps; the next partial buffer must have been drained by them
+                        if (gopen) {
+                            if (lead) tc_commit(bar_afull + 8 * gpb);
+                            ++gg;
+                        }
+                        gpb = gg & 1u;
+                        { const long long c0 = dbg_on ? clock64() : 0;
+                          mbar_wait(bar_aempty + 8 * gpb, ((gg >> 1) & 1u) ^ 1u);
+                          if (dbg_on) w_aempty += clock64() - c0; }
+                        tc_fence_after();
+                        gdcol = tmem_u + gpb * CT;
+                        gacc0 = 0u;
+                        gopen = true;
+                    }
+                    const uint32_t alo = pa16 + toff;
+                    toff = (uint32_t)toffp[min(t + 1, ntaps - 1)] >> 4;   // prefetched for the next tap
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            if (j == 1 && !two) break;
-                            if (slot == 0) {
-                                const long long c0 = dbg_on ? clock64() : 0;
-                                mbar_wait(bar_bfull + 8 * st, stph);
-                                if (dbg_on) w_bfull += clock64() - c0;
-                                blo = bst16 + st * stage16;
-                            }
-                            const long long ci0 = dbg_on ? clock64() : 0;
-                            if (lead) {
-                                // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
-                                if (j == 1 && short2) issue_stage<2>(dcol, N, alo, ahi, blo, bhi, idesc, acc0, S, s_first, sstep);
-                                else issue_stage<4>(dcol, N, alo, ahi, blo, bhi, idesc, acc0, S, s_first, sstep);
-                            }
-                            if (dbg_on) { w_issue += clock64() - ci0; n_issue += 1; }
-                            acc0 = 1u;
-                            blo += btile16;
-                            if (++slot == T || (t == ntaps - 1 && (j == 1 || !two))) {
-                                if (lead) tc_commit(bar_bempty + 8 * st);   // frees the stage when these MMAs retire
-                                if (++st == nst) { st = 0; stph ^= 1u; }
-                                slot = 0;
-                            }
+                    for (int j = 0; j < 2; ++j) {
+                        if (j == 1 && !two) break;
+                        if (slot == 0) {
+                            const long long c0 = dbg_on ? clock64() : 0;
+                            mbar_wait(bar_bfull + 8 * st, stph);
+                            if (dbg_on) w_bfull += clock64() - c0;
+                            blo = bst16 + st * stage16;
+                        }
+                        if (lead) {
+                            // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
+                            if (j == 1 && short2) issue_stage<2>(gdcol, N, alo, ahi, blo, bhi, idesc, gacc0, S, s_first, sstep);
+                            else issue_stage<4>(gdcol, N, alo, ahi, blo, bhi, idesc, gacc0, S, s_first, sstep);
+                        }
+                        gacc0 = 1u;
+                        blo += btile16;
+                        if (++slot == T || (t == ntaps - 1 && (j == 1 || !two))) {
+                            if (lead) tc_commit(bar_bempty + 8 * st);   // frees the stage when these MMAs retire
+                            if (++st == nst) { st = 0; stph ^= 1u; }
+                            slot = 0;
                         }
                     }
-                    if (lead) tc_commit(bar_afull + 8 * pb);  // short chain complete -> accumulator warps
+                }
+                if (ps.gend && gopen) {
+                    if (lead) tc_commit(bar_afull + 8 * gpb);      // chain complete -> accumulator warps
                     ++gg;
+                    gopen = false;
                 }
                 if (lead) tc_commit(bar_pempty + 8 * set);    // patch buffer reusable
                 __syncwarp();
@@ -1106,7 +1120,28 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         }
         sb.npass = npass - sb.pass_first;
         sb.ngroups = 0;
-        for (int q = sb.pass_first; q < npass; ++q) sb.ngroups += cdiv(P.pass[q].ntaps, P.pass[q].gtaps);
+        {
+            const int chain_max = env_int("FVC_TC_CHAIN", 48);
+            const bool span = env_int("FVC_TC_SPAN", 1) != 0;
+            int chain = 0;
+            for (int q = sb.pass_first; q < npass; ++q) {
+                TcPass& ps = P.pass[q];
+                const int per_tap = ps.ks0 + (ps.nbt == 2 ? ps.ks1 : 0);
+                unsigned long long mask = 0;
+                const bool narrow_pass = ps.ks0 == 1;   // the narrow-record loop keeps per-pass groups of gtaps taps
+                for (int t = 0; t < ps.ntaps; ++t) {
+                    bool start;
+                    if (narrow_pass || !span) start = (t % ps.gtaps) == 0;
+                    else start = (q == sb.pass_first && t == 0) || chain + per_tap > chain_max;
+                    if (start) { mask |= 1ull << t; chain = 0; sb.ngroups++; }
+                    chain += per_tap;
+                }
+                ps.gmask_lo = (uint32_t)mask;
+                ps.gmask_hi = (uint32_t)(mask >> 32);
+                ps.gend = (narrow_pass || !span || q == npass - 1) ? 1 : 0;
+                if (ps.gend) chain = 0;
+            }
+        }
     }
 
     // ---- weight stream -------------------------------------------------------------------------------
