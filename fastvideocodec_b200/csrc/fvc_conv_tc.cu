@@ -1,28 +1,30 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (sm_100a).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (sm_100a).  Design notes and measurements: DESIGN.md 4.1.
 //
 // GEMM view: M = 128 output pixels (a 16x8 sub-tile), N = output channels, K = taps x input channels.
-//   * A (activations) is never im2col'ed.  A CTA loads ONE halo'ed input patch [PH][PW][128 B] per
-//     128-byte record segment with a single 5-D TMA box (zero fill outside the image = conv
-//     padding) and every filter tap is just a different start address into that patch: the 8-row
-//     core groups of the UMMA K-major SWIZZLE_128B layout are 8 consecutive pixels of one image
-//     row (128 B pitch) and successive groups are successive image rows (SBO = PW*128 B).
-//   * B (weights) is a pre-packed bf16 stream in exactly the order the K loop consumes it, pulled
-//     by 2-D TMA boxes through a multi-stage mbarrier ring.
-//   * Precision: activations and weights are hi/lo bf16 pairs; each product is issued as
-//     a_hi*w_hi + a_hi*w_lo + a_lo*w_hi on kind::f16 MMAs with fp32 accumulation in TMEM
-//     (>= 16 operand mantissa bits, the parity contract of SURVEY 7.2-1).
-//   * S sub-tiles (S*N accumulator columns in TMEM) share every weight stage, cutting the weight
-//     traffic per pixel S-fold; stride-2 convs read the four parity planes of a parity-planar
-//     input; stride-2 transposed convs run as 4 output-phase sub-convolutions.
-//   * Accumulation: tcgen05 adds into its fp32 TMEM accumulator with TRUNCATION (measured: relative
-//     bias -4.9e-8 per MMA in the chain, -2.9e-5 after the 588 MMAs of a 7x7x64 filter; see
-//     tools/tc_bias.py and DESIGN.md).  So TMEM only ever holds SHORT chains (<= ~24 MMAs, a group
-//     of taps): two partial-accumulator buffers ping-pong, and 16 accumulator warps drain each
-//     finished partial with tcgen05.ld and add it to a running sum in registers in fp32
-//     round-to-nearest, overlapped with the MMAs of the next group.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..17 =
-//     accumulator/epilogue warps (drain -> running sum -> bias/activation/residual -> hi/lo split
-//     -> global).  Persistent over tiles.
+//   * A (activations) is never im2col'ed.  A CTA loads ONE halo'ed input patch [PH][PW][pitch] per record
+//     segment with a single 5-D TMA box (zero fill outside the image = conv padding) and every filter tap is
+//     just a different start address into that patch: the 8-row core groups of the UMMA K-major swizzled
+//     layout are 8 consecutive pixels of one image row and successive groups are successive image rows
+//     (SBO = PW*pitch).  pitch = 128 B (SWIZZLE_128B) or 32 B (SWIZZLE_32B, narrow [hi 8 | lo 8] records).
+//   * B (weights) is a pre-packed 16-bit stream in exactly the order the K loop consumes it, pulled by 2-D TMA
+//     boxes of T tiles through a multi-stage mbarrier ring.
+//   * Precision: activations and weights are hi/lo fp16 pairs (bf16 pairs with FVC_SPLIT=bf16); each product
+//     is issued as a_hi*w_hi + a_hi*w_lo + a_lo*w_hi on kind::f16 MMAs with fp32 accumulation in TMEM.  For
+//     Cout <= 32 the w_hi and w_lo rows sit side by side in one tile (MMA N = 2*Cout, "merged"): a_hi is read
+//     once for two products and the epilogue adds the two column blocks.
+//   * S sub-tiles (S*N accumulator columns in TMEM) share every weight stage, cutting the weight traffic per
+//     pixel S-fold; stride-2 convs read the four parity planes of a parity-planar input; stride-2 transposed
+//     convs run as 4 output-phase sub-convolutions.
+//   * Accumulation: tcgen05 adds into its fp32 TMEM accumulator with TRUNCATION (measured: relative bias
+//     -4.9e-8 per MMA in the chain, -2.9e-5 after the 588 MMAs of a 7x7x64 filter; tools/tc_bias.py).  So
+//     TMEM only ever holds SHORT chains (<= 48 MMAs, a "group" of taps, possibly spanning the segment passes
+//     of a tile): two partial-accumulator buffers ping-pong, and 16 accumulator warps drain each finished
+//     partial with tcgen05.ld and add it to a running sum in registers in fp32 round-to-nearest, overlapped
+//     with the MMAs of the next group.
+//   * Warp roles (19 warps): warp 0 = TMA producer (polls the weight ring and the patch ring), warps 1-2 =
+//     MMA issuers (even / odd sub-tiles; warp 1 owns the TMEM allocation), warps 3..18 = accumulator /
+//     epilogue warps (drain -> running sum -> bias/activation/skip/GDN -> hi/lo split -> global).
+//     Persistent over tiles.
 #include <cuda.h>
 #include <vector>
 #include <cstring>
