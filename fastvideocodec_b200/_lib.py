@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfvc_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fvc_b200.h")
 
-ACT_NONE, ACT_RELU, ACT_LRELU01, ACT_EXP = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LRELU01, ACT_EXP, ACT_LRELU001 = 0, 1, 2, 3, 4
 IMPL_SIMT, IMPL_TC = 0, 1
 
 _lib = None

@@ -363,6 +363,9 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
                 } else if (act == FVC_ACT_EXP) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) w[q] = expf(w[q]);
+                } else if (act == FVC_ACT_LRELU001) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) w[q] = w[q] > 0.f ? w[q] : w[q] * 0.01f;
                 }
                 if (RES) {
                     const uint32_t hh[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w}, ll[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};

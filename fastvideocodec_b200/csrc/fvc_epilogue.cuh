@@ -105,6 +105,7 @@ __device__ __forceinline__ float ep_act(float v, int act) {
     switch (act) {
         case FVC_ACT_RELU: return fmaxf(v, 0.f);
         case FVC_ACT_LRELU01: return v > 0.f ? v : v * 0.1f;
+        case FVC_ACT_LRELU001: return v > 0.f ? v : v * 0.01f;
         case FVC_ACT_EXP: return expf(v);
         default: return v;
     }

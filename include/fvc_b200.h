@@ -40,6 +40,7 @@ extern "C" {
 #define FVC_ACT_RELU 1
 #define FVC_ACT_LRELU01 2 /* LeakyReLU(0.1) — analysis_mv.py:17 */
 #define FVC_ACT_EXP 3     /* synthesis_prior.py:57 */
+#define FVC_ACT_LRELU001 4 /* nn.LeakyReLU() default slope 0.01 — entropy_models.py:166-188 */
 
 /* convolution engines */
 #define FVC_IMPL_SIMT 0 /* fp32 CUDA-core implicit GEMM (checker / bring-up path) */

@@ -300,6 +300,47 @@ def gaussian_forward(x, scales, means, scale_bound=0.11, likelihood_bound=1e-9):
     return xh, (upper - lower).clamp(min=likelihood_bound)
 
 
+def estimate_bits_clamped(likelihoods):
+    """RecProbModel.get_estimate_bits — entropy_models.py:74-78."""
+    return torch.sum(torch.clamp(-1.0 * torch.log(likelihoods + 1e-5) / math.log(2.0), 0, 50))
+
+
+def _eb_params(sd, prefix):
+    m = [sd[prefix + "_matrix%d" % i] for i in range(5)]
+    b = [sd[prefix + "_bias%d" % i] for i in range(5)]
+    f = [sd[prefix + "_factor%d" % i] for i in range(4)]
+    return m, b, f, sd[prefix + "quantiles"][:, 0, 1]
+
+
+def recprob_forward(sd, x):
+    """RecProbModel.forward with RPM_flag False — entropy_models.py:55-68: (x_hat, likelihood, prior_latent)."""
+    m, b, f, med = _eb_params(sd, "entropy_bottleneck.")
+    xh, lik = eb_forward(m, b, f, med, x)
+    return xh, lik, torch.round(x)
+
+
+def meanscale_forward(sd, x, channels):
+    """MeanScaleHyperPriors.forward — entropy_models.py:202-219 (nn.LeakyReLU() default slope 0.01)."""
+    def hconv(prefix, t, last_act):
+        t = F.leaky_relu(F.conv2d(t, sd[prefix + ".0.weight"], sd[prefix + ".0.bias"], padding=1), 0.01)
+        t = F.conv2d(t, sd[prefix + ".2.weight"], sd[prefix + ".2.bias"], padding=1)
+        return F.leaky_relu(t, 0.01) if last_act else t
+    z = hconv("h_a2", hconv("h_a1", x, True), False)
+    m, b, f, med = _eb_params(sd, "entropy_bottleneck.")
+    z_hat, z_lik = eb_forward(m, b, f, med, z)
+    gp = hconv("h_s2", hconv("h_s1", z_hat, True), False)
+    sigma, mu = torch.split(gp, channels, dim=1)
+    sigma = torch.exp(torch.maximum(sigma, torch.tensor(-7.0)))
+    x_hat, x_lik = gaussian_forward(x, sigma, mu)
+    return x_hat, x_lik, z_lik, z, sigma, mu
+
+
+def meanscale_bits(x_lik, z_lik):
+    """MeanScaleHyperPriors.get_estimate_bits — entropy_models.py:228-235."""
+    bs = x_lik.size(0)
+    return (torch.sum(torch.log(x_lik.view(bs, -1)), -1) + torch.sum(torch.log(z_lik.view(bs, -1)), -1)) / (-math.log(2.0))
+
+
 # --------------------------------------------------------------------------------------
 # whole P-frame
 # --------------------------------------------------------------------------------------

@@ -460,3 +460,79 @@ def test_config5_multiview_batch8(model, dev):
             bpps.append(float(one[7]))
     assert math.isfinite(float(both[7])) and float(both[0].min()) >= 0.0 and float(both[0].max()) <= 1.0
     model.release()
+
+
+def _randomize_eb(module, gen):
+    """Non-trivial EntropyBottleneck parameters (fresh init has zero factors and symmetric matrices)."""
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if "_matrix" in name or "_factor" in name:
+                p.add_(torch.randn(p.shape, generator=gen) * 0.3)
+            elif "quantiles" in name:
+                p[:, 0, 1] = torch.randn(p.shape[0], generator=gen) * 0.4
+
+
+def test_entropy_models_recprob_forward(dev):
+    """entropy_models.RecProbModel.forward / get_estimate_bits (entropy_models.py:55-78), RPM_flag False, against
+    the oracle's restatement of the CompressAI algorithm (parity UNPINNED: CompressAI is not vendored)."""
+    from fastvideocodec_b200.entropy_models import RecProbModel
+    g = torch.Generator().manual_seed(21)
+    m = RecProbModel(128)
+    _randomize_eb(m.entropy_bottleneck, g)
+    x = torch.randn((2, 128, 17, 30), generator=g) * 4
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    want_xh, want_lik, want_prior = O.recprob_forward(sd, x)
+    m = m.to(dev).eval()
+    m.set_RPM(False)
+    hidden = torch.zeros(1)
+    with torch.no_grad():
+        xh, lik, hid, prior = m(x.to(dev), hidden, training=False)
+    assert torch.equal(xh.cpu(), want_xh) and torch.equal(prior.cpu(), want_prior)
+    assert (lik.cpu() - want_lik).abs().max().item() <= 2e-6
+    bits, want_bits = float(m.get_estimate_bits(lik)), float(O.estimate_bits_clamped(want_lik))
+    assert abs(bits - want_bits) <= 1e-5 * want_bits
+    # fused kernel: the same bits without materialising the reduction in PyTorch
+    _, _, fused = m.entropy_bottleneck.forward_bits(x.to(dev))
+    assert abs(float(fused) - want_bits) <= 1e-5 * want_bits
+
+
+def test_entropy_models_meanscale_forward(dev):
+    """entropy_models.MeanScaleHyperPriors.forward / get_estimate_bits (entropy_models.py:202-235): hyper convs on
+    the tcgen05 engine, EntropyBottleneck + GaussianConditional kernels (parity UNPINNED, see above)."""
+    from fastvideocodec_b200.entropy_models import MeanScaleHyperPriors
+    g = torch.Generator().manual_seed(22)
+    C = 64
+    m = MeanScaleHyperPriors(C)
+    _randomize_eb(m.entropy_bottleneck, g)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.startswith("h_"):
+                p.copy_(torch.randn(p.shape, generator=g) * (0.04 if p.dim() == 4 else 0.1))
+    x = torch.randn((1, C, 32, 48), generator=g) * 3
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    want_xh, want_xl, want_zl, want_z, want_sigma, want_mu = O.meanscale_forward(sd, x, C)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        xh, (xl, zl) = m(x.to(dev), training=False)
+    assert (m.z.cpu() - want_z).abs().max().item() <= 5e-5 * max(1.0, want_z.abs().max().item())
+    # Everything after the hyper-latent quantiser is compared outside the receptive field (4 convs 3x3 -> +-4 px)
+    # of hyper-latents that sat on a rounding tie (fp32 evaluation order moves those across the tie).
+    med = sd["entropy_bottleneck.quantiles"][:, 0, 1].view(1, C, 1, 1)
+    flips = (torch.round(m.z.cpu() - med) != torch.round(want_z - med)).any(dim=1, keepdim=True).float()
+    assert flips.sum().item() <= 2
+    keep = torch.nn.functional.max_pool2d(flips, 9, 1, 4) == 0
+
+    def err(a, b):
+        return ((a.cpu() - b).abs() * keep).max().item()
+
+    assert err(m.sigma, want_sigma) <= 1e-4 * want_sigma.abs().max().item()
+    assert err(m.mu, want_mu) <= 1e-4 * max(1.0, want_mu.abs().max().item())
+    assert err(zl, want_zl) <= 1e-5
+    # x_hat = round(x - mu) + mu: identical up to mu's rounding noise except at ties of (x - mu)
+    d = (xh.cpu() - want_xh).abs() * keep
+    assert (d > 1e-3).float().mean().item() <= 1e-4 and d.max().item() <= 1.0 + 1e-3
+    same = keep & (d <= 1e-3)
+    assert ((xl.cpu() - want_xl).abs() * same).max().item() <= 1e-4
+    if flips.sum().item() == 0 and (d > 1e-3).sum().item() == 0:
+        bits, want_bits = float(m.get_estimate_bits((xl, zl))[0]), float(O.meanscale_bits(want_xl, want_zl)[0])
+        assert abs(bits - want_bits) <= 0.005 * want_bits

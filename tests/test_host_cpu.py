@@ -189,3 +189,33 @@ def test_stats_reduce_world_size_2_gloo(tmp_path):
     assert int(line[1]) == 15
     assert abs(float(line[2]) - sum(b for _, b in rows) / 15) < 1e-6
     assert abs(float(line[3]) - sum(10 * math.log10(1 / m) for m, _ in rows) / 15) < 1e-4
+
+
+def test_entropy_models_surface():
+    """Host-side mirror of reference entropy_models.py: class / method names, CompressAI parameter names,
+    get_estimate_bits arithmetic (entropy_models.py:74-78, 228-235) and loud failure of the out-of-scope paths."""
+    import math
+    from fastvideocodec_b200 import entropy_models as em
+    m = em.RecProbModel(8)
+    keys = set(m.state_dict().keys())
+    for i in range(5):
+        assert "entropy_bottleneck._matrix%d" % i in keys and "entropy_bottleneck._bias%d" % i in keys
+    for i in range(4):
+        assert "entropy_bottleneck._factor%d" % i in keys
+    assert "entropy_bottleneck.quantiles" in keys and m.state_dict()["entropy_bottleneck.quantiles"].shape == (8, 1, 3)
+    lik = torch.tensor([[0.5, 0.25, 1e-30, 1.0]])
+    want = 1.0 + 2.0 + min(50.0, -math.log2(1e-30 + 1e-5)) + max(0.0, -math.log2(1.0 + 1e-5))
+    assert abs(float(m.get_estimate_bits(lik)) - want) < 1e-4
+    h = em.MeanScaleHyperPriors(8)
+    assert {"h_a1.0.weight", "h_a2.2.bias", "h_s2.2.weight"} <= set(h.state_dict().keys())
+    assert h.state_dict()["h_s2.2.weight"].shape == (16, 8, 3, 3)
+    bits = h.get_estimate_bits((torch.full((2, 1, 2, 2), 0.5), torch.full((2, 1, 1, 1), 0.25)))
+    assert torch.allclose(bits, torch.tensor([6.0, 6.0]))
+    assert em.get_scale_table().shape == (64,) and abs(float(em.get_scale_table()[0]) - 0.11) < 1e-6
+    m.set_RPM(True)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 8, 2, 2), torch.zeros(1), prior_latent=torch.zeros(1, 8, 2, 2))
+    m.train()
+    m.set_RPM(False)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 8, 2, 2), torch.zeros(1))
