@@ -8,4 +8,6 @@ from .net import VideoCompressor, load_model, save_model  # noqa: F401
 from .gop import (AverageMeter, PSNR, get_codec_model, get_DVC_pretrained, parallel_compression,  # noqa: F401
                   reduce_stats, shard_gops, stats_vector, summarize)
 
+from .lsvc import LSVC, generate_graph, graph_from_batch, refidx_from_graph  # noqa: F401
+
 __version__ = "0.1.0"

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "fvc_pframe_forward": (_i, [C.c_void_p, _f, _f, _f, _f, _s]),
     "fvc_ctx_get_tensor": (_l, [C.c_void_p, C.c_char_p, _f, _l, _s]),
     "fvc_gop_forward_host": (_i, [C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, _s]),
+    "fvc_lsvc_mv_forward": (_i, [C.c_void_p, _f, _f, _f, _f, _s]),
+    "fvc_lsvc_mc_res_forward": (_i, [C.c_void_p, _f, _f, _f, _f, _f, _f, _f, _s]),
     "fvc_ctx_launch_count": (_l, [C.c_void_p]),
     "fvc_ctx_last_conv_seconds": (C.c_double, [C.c_void_p]),
     "fvc_ctx_profile_text": (C.c_char_p, [C.c_void_p]),

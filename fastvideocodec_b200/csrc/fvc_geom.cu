@@ -498,9 +498,11 @@ int launch_gdn_act(ActT in, int C, const float* beta_eff, const float* gamma_eff
 // ----------------------------------------------------------------------------------------------
 // reconstruction + the three distortion terms (net.py:103-116), fused, with block partial sums
 // ----------------------------------------------------------------------------------------------
+// clip_mse = 0: first sum over the unclipped reconstruction (DVC, net.py:103-109); 1: over the clipped one
+// (LSVC.forward, models.py:1383, 1400)
 __global__ void k_recon_losses(const float* __restrict__ cur, const float* __restrict__ pred,
                                const float* __restrict__ warp, const float* __restrict__ res, int res_nhwc3, int B,
-                               int HW, float* __restrict__ clipped, float* __restrict__ partials) {
+                               int HW, float* __restrict__ clipped, float* __restrict__ partials, int clip_mse) {
     __shared__ float red[32];
     int64_t n = (int64_t)B * 3 * HW;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -516,8 +518,9 @@ __global__ void k_recon_losses(const float* __restrict__ cur, const float* __res
         }
         float c0 = cur[i], p0 = pred[i], w0 = warp[i];
         float rec = p0 + r;
-        clipped[i] = fminf(fmaxf(rec, 0.f), 1.f);
-        float d0 = rec - c0, d1 = w0 - c0, d2 = p0 - c0;
+        const float cl = fminf(fmaxf(rec, 0.f), 1.f);
+        clipped[i] = cl;
+        float d0 = (clip_mse ? cl : rec) - c0, d1 = w0 - c0, d2 = p0 - c0;
         s0 = fmaf(d0, d0, s0);
         s1 = fmaf(d1, d1, s1);
         s2 = fmaf(d2, d2, s2);
@@ -532,11 +535,12 @@ __global__ void k_recon_losses(const float* __restrict__ cur, const float* __res
     }
 }
 int launch_recon_losses(const float* cur, const float* pred, const float* warp, const float* res, int res_nhwc3,
-                        int B, int HW, float* clipped, float* partials, int* nblocks_out, cudaStream_t s) {
+                        int B, int HW, float* clipped, float* partials, int* nblocks_out, cudaStream_t s,
+                        int clip_mse) {
     int64_t n = (int64_t)B * 3 * HW;
     int blocks = (int)std::min<int64_t>(cdiv64(n, 256 * 4), 148 * 8);
     if (blocks < 1) blocks = 1;
-    k_recon_losses<<<blocks, 256, 0, s>>>(cur, pred, warp, res, res_nhwc3, B, HW, clipped, partials);
+    k_recon_losses<<<blocks, 256, 0, s>>>(cur, pred, warp, res, res_nhwc3, B, HW, clipped, partials, clip_mse);
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     *nblocks_out = blocks;

@@ -27,7 +27,8 @@ int launch_gdn_reparam(const float* beta, const float* gamma, float* beta_eff, f
                        cudaStream_t s);
 // losses.  res_nhwc3 != 0: res is fp32 NHWC with 3 channels, everything else planar [B,3,H,W].
 int launch_recon_losses(const float* cur, const float* pred, const float* warp, const float* res, int res_nhwc3,
-                        int B, int HW, float* clipped, float* partials, int* nblocks_out, cudaStream_t s);
+                        int B, int HW, float* clipped, float* partials, int* nblocks_out, cudaStream_t s,
+                        int clip_mse = 0);
 int launch_finalize_scalars(const float* sums6, float n_pix, float* scalars7, cudaStream_t s);
 int launch_reduce_partials(const float* partials, int n, int groups, double scale, float* out, cudaStream_t s);
 // layout conversion

@@ -438,12 +438,12 @@ static int res_block(fvc_ctx* c, int idx, ActT x_relu, ActT x_skip, ActT tmp, Ac
     return run_conv(c, n2, tmp, out.H, out.W, ep, s);
 }
 
-static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_out, float* scalars_out,
-                   cudaStream_t s) {
+// Phase A of the path: opticFlow + mvEncoder + quantiser/bits + mvDecoder (net.py:71-77; LSVC: models.py:1350-1351,
+// 1333-1342).  Leaves mv_hat in c->mv_hat (fp32 NHWC2) and the mv bit partials in c->bits_partials[2].
+static int forward_mv(fvc_ctx* c, const float* cur, const float* ref, int* nb_mv_out, cudaStream_t s) {
     const int B = c->B, H = c->H, W = c->W, L = c->levels;
     char nm[96];
     int rc;
-    c->conv_event_used = 0;
 #define R(expr) do { rc = (expr); if (rc) return rc; } while (0)
     // ---- SpyNet (endecoder.py:337-356) --------------------------------------------------------
     const float* p1 = cur;
@@ -488,7 +488,7 @@ static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_
             if (i < 8) in = c->e[i];
         }
     }
-    int nb_mv = 0, nb_z = 0, nb_f = 0;
+    int nb_mv = 0;
     const int maxb = bits_max_blocks();
     {
         FactorizedParams prm;
@@ -509,6 +509,21 @@ static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_
             if (i < 8) in = c->d[i];
         }
     }
+    *nb_mv_out = nb_mv;
+#undef R
+    return 0;
+}
+
+// Phase B: motion compensation + residual codec + reconstruction (net.py:79-116; LSVC: models.py:1375-1383,
+// 1300-1331) with the motion field in c->mv_hat.  sums: 3 loss partial sums reduced with `loss_scale`,
+// bits_feature, bits_z in c->scalars[0..4].
+static int forward_mc_res(fvc_ctx* c, const float* cur, const float* ref, float* recon_out, double loss_scale,
+                          int clip_mse, cudaStream_t s) {
+    const int B = c->B, H = c->H, W = c->W;
+    int rc;
+    int nb_z = 0, nb_f = 0;
+    const int maxb = bits_max_blocks();
+#define R(expr) do { rc = (expr); if (rc) return rc; } while (0)
     // ---- motion compensation (net.py:64-68, endecoder.py:282-296) ------------------------------
     R(launch_mc_prep(ref, c->mv_hat, c->warpframe, c->xmc, s));
     {
@@ -585,14 +600,27 @@ static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_
     // ---- reconstruction, distortion, rate (net.py:103-116, 207-217) -------------------------------
     int nloss = 0;
     R(launch_recon_losses(cur, c->prediction, c->warpframe, c->recon_res, 1, B, H * W, recon_out, c->loss_partials,
-                          &nloss, s));
-    R(launch_reduce_partials(c->loss_partials, nloss, 3, 1.0 / ((double)B * 3 * H * W), c->scalars, s));
+                          &nloss, s, clip_mse));
+    R(launch_reduce_partials(c->loss_partials, nloss, 3, loss_scale, c->scalars, s));
     R(launch_reduce_partials(c->bits_partials + 0 * maxb, nb_f, 1, 1.0, c->scalars + 3, s));
     R(launch_reduce_partials(c->bits_partials + 1 * maxb, nb_z, 1, 1.0, c->scalars + 4, s));
-    R(launch_reduce_partials(c->bits_partials + 2 * maxb, nb_mv, 1, 1.0, c->scalars + 5, s));
-    R(launch_finalize_scalars(c->scalars, (float)((double)B * H * W), scalars_out, s));
 #undef R
     return 0;
+}
+
+// VideoCompressor.forward (net.py:70-220) = phase A + phase B + bpp bookkeeping
+static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_out, float* scalars_out,
+                   cudaStream_t s) {
+    const int B = c->B, H = c->H, W = c->W;
+    c->conv_event_used = 0;
+    int nb_mv = 0;
+    int rc = forward_mv(c, cur, ref, &nb_mv, s);
+    if (rc) return rc;
+    rc = forward_mc_res(c, cur, ref, recon_out, 1.0 / ((double)B * 3 * H * W), 0, s);
+    if (rc) return rc;
+    rc = launch_reduce_partials(c->bits_partials + 2 * bits_max_blocks(), nb_mv, 1, 1.0, c->scalars + 5, s);
+    if (rc) return rc;
+    return launch_finalize_scalars(c->scalars, (float)((double)B * H * W), scalars_out, s);
 }
 
 }  // namespace fvc
@@ -767,6 +795,48 @@ int fvc_pframe_forward(fvc_ctx* c, const float* cur, const float* ref, float* re
         }
         c->last_conv_seconds = tot;
     }
+    return rc;
+}
+
+/* LSVC two-phase use of the path (reference models.py:1344-1411): phase A on a batch of frames against their
+ * ORIGINAL reference frames, phase B per tree layer against RECONSTRUCTED references. */
+int fvc_lsvc_mv_forward(fvc_ctx* c, const float* cur, const float* ref, float* mv_hat_out, float* bits_mv_out,
+                        void* stream) {
+    FVC_ARG(c && cur && ref && mv_hat_out && bits_mv_out);
+    if (fvc_ctx_missing_params(c) != 0) {
+        set_error("fvc_lsvc_mv_forward: %d parameters not set", fvc_ctx_missing_params(c));
+        return FVC_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t before = g_launch_count;
+    c->conv_event_used = 0;
+    int nb_mv = 0;
+    int rc = forward_mv(c, cur, ref, &nb_mv, s);
+    if (!rc) rc = launch_reduce_partials(c->bits_partials + 2 * bits_max_blocks(), nb_mv, 1, 1.0, bits_mv_out, s);
+    if (!rc) rc = launch_nhwc_to_nchw(c->mv_hat, mv_hat_out, c->B, 2, c->H, c->W, s);
+    c->launches += g_launch_count - before;
+    return rc;
+}
+
+int fvc_lsvc_mc_res_forward(fvc_ctx* c, const float* cur, const float* ref, const float* mv_hat, float* com_out,
+                            float* mc_out, float* warp_out, float* sums_out, void* stream) {
+    FVC_ARG(c && cur && ref && mv_hat && com_out && mc_out && warp_out && sums_out);
+    if (fvc_ctx_missing_params(c) != 0) {
+        set_error("fvc_lsvc_mc_res_forward: %d parameters not set", fvc_ctx_missing_params(c));
+        return FVC_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t before = g_launch_count;
+    c->conv_event_used = 0;
+    const size_t n = (size_t)c->B * 3 * c->H * c->W;
+    int rc = launch_nchw_to_nhwc(mv_hat, c->mv_hat, c->B, 2, c->H, c->W, s);
+    if (!rc) rc = forward_mc_res(c, cur, ref, com_out, 1.0, 1, s);   // sums (not means) of the squared errors
+    if (!rc) {
+        FVC_CUDA(cudaMemcpyAsync(mc_out, c->prediction, n * 4, cudaMemcpyDeviceToDevice, s));
+        FVC_CUDA(cudaMemcpyAsync(warp_out, c->warpframe, n * 4, cudaMemcpyDeviceToDevice, s));
+        FVC_CUDA(cudaMemcpyAsync(sums_out, c->scalars, 5 * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    c->launches += g_launch_count - before;
     return rc;
 }
 

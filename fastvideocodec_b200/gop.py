@@ -68,10 +68,14 @@ def get_DVC_pretrained(level, snapshot_dir="DVC/snapshot", device="cuda"):
 
 def get_codec_model(name, loss_type='P', compression_level=2, noMeasure=True, use_split=True, num_views=0,
                     resilience=0, use_attn=True, load_with_copy=False):
-    """reference models.py:32-66 — only the 'DVC-pretrained' family is on the B200 hot path."""
+    """reference models.py:32-66 — 'DVC-pretrained' (the hot path) and the LSVC names that share its
+    sub-networks are built."""
     if name in ['DVC-pretrained']:
         return get_DVC_pretrained(compression_level)
-    raise ValueError("codec %r is outside the B200 hot path (only 'DVC-pretrained' is built)" % (name,))
+    if 'LSVC' in name:
+        from .lsvc import LSVC
+        return LSVC(name, loss_type=loss_type, compression_level=compression_level, use_split=use_split)
+    raise ValueError("codec %r is outside the B200 hot path ('DVC-pretrained' and 'LSVC*-128' are built)" % (name,))
 
 
 def parallel_compression(args, model, data, compressI=False, level=0, batch_idx=0, i_codec=None):
@@ -91,6 +95,8 @@ def parallel_compression(args, model, data, compressI=False, level=0, batch_idx=
         if compressI:
             bpp_list += [bpp0.to(data.device)]
             psnr_list += [psnr0.to(data.device)]
+    if 'LSVC' in getattr(model, 'name', ''):
+        return _parallel_compression_lsvc(model, data, bpp_list, psnr_list)
     log10 = torch.log(torch.FloatTensor([10])).squeeze(0).to(data.device)
     B = data.size(0)
     x_prev = data[0:1]
@@ -114,6 +120,26 @@ def parallel_compression(args, model, data, compressI=False, level=0, batch_idx=
     aux2_loss = torch.stack(aux2_loss_list, dim=0).mean(dim=0).cpu().data.item() if aux2_loss_list else 0
     return (x_hat, loss, img_loss, be_loss, be_res_loss, psnr, torch.stack(psnr_list, dim=0).tolist(), aux_loss,
             aux2_loss, 0, 0)
+
+
+def _parallel_compression_lsvc(model, data, bpp_list, psnr_list):
+    """reference models.py:384-398: one batched / tree forward for the whole GOP."""
+    B = data.size(0)
+    x_hat, x_mc, x_wp, rec_loss, warp_loss, mc_loss, bpp_res, bpp = model(data.detach())
+    img_loss_list = [rec_loss * model.r]
+    all_loss_list = [(rec_loss * model.r + bpp).to(data.device)]
+    psnr_list += PSNR(data[1:], x_hat, use_list=True)
+    aux2_loss_list = PSNR(data[1:], x_mc, use_list=True)
+    aux_loss_list = PSNR(data[1:], x_wp, use_list=True)
+    x_hat = torch.cat([data[0:1], x_hat], dim=0)
+    bpp_list += [bpp.to(data.device) for _ in range(B - 1)]
+    loss = torch.stack(all_loss_list, dim=0).sum(dim=0)
+    be_loss = torch.stack(bpp_list, dim=0).mean(dim=0).cpu().data.item()
+    img_loss = torch.stack(img_loss_list, dim=0).mean(dim=0).cpu().data.item()
+    psnr = torch.stack(psnr_list, dim=0).mean(dim=0).cpu().data.item()
+    aux_loss = torch.stack(aux_loss_list, dim=0).mean(dim=0).cpu().data.item()
+    aux2_loss = torch.stack(aux2_loss_list, dim=0).mean(dim=0).cpu().data.item()
+    return (x_hat, loss, img_loss, be_loss, 0, psnr, torch.stack(psnr_list, dim=0).tolist(), aux_loss, aux2_loss, 0, 0)
 
 
 # ----------------------------------------------------------------------------------------------

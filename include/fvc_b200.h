@@ -144,6 +144,20 @@ FVC_API int64_t fvc_ctx_get_tensor(fvc_ctx* ctx, const char* name, float* out, i
 FVC_API int fvc_gop_forward_host(fvc_ctx* ctx, const float* frames_host, int G, float* recon_host, float* scalars_host,
                          void* stream);
 
+/* LSVC (reference models.py:1157-1411, non-attention "-128" variants: the same sub-networks as DVC) codes the
+ * P-frames of a GOP in two phases (LSVC.forward, models.py:1344-1411):
+ *   phase A: opticFlow + mv_codec on ALL frames at once against their ORIGINAL reference frames
+ *            cur, ref: [B,3,H,W] -> mv_hat_out: [B,2,H,W] (decoded motion), bits_mv_out: 1 float (sum over B);
+ *   phase B: per tree layer, motioncompensation + res_codec against the RECONSTRUCTED references
+ *            cur, ref, mv_hat -> com_out = clip(MC + res_hat), mc_out = MC frames, warp_out = warped frames
+ *            (all [B,3,H,W]); sums_out: 5 floats = sum((com-cur)^2), sum((warp-cur)^2), sum((mc-cur)^2),
+ *            bits_feature, bits_z (sums over B).
+ * B is the context's batch; use one context per batch size. */
+FVC_API int fvc_lsvc_mv_forward(fvc_ctx* ctx, const float* cur, const float* ref, float* mv_hat_out,
+                                float* bits_mv_out, void* stream);
+FVC_API int fvc_lsvc_mc_res_forward(fvc_ctx* ctx, const float* cur, const float* ref, const float* mv_hat,
+                                    float* com_out, float* mc_out, float* warp_out, float* sums_out, void* stream);
+
 /* Launch statistics since creation: kernels launched by this library through ctx. */
 FVC_API int64_t fvc_ctx_launch_count(fvc_ctx* ctx);
 /* Dominant-kernel timing hook for bench.py: seconds spent in convolution kernels during the last

@@ -383,6 +383,49 @@ def pframe_forward(sd, cur, ref, levels=4, capture=False):
     return out
 
 
+def lsvc_forward(sd, x, layers, parents, ref_index, levels=4):
+    """LSVC.forward in eval mode (128-channel, non-attention variants) — models.py:1344-1411.  ``layers``,
+    ``parents``, ``ref_index`` are the reference's GOP graph (models.py:683-728, 923-949)."""
+    inp = x[1:]
+    bs, c, h, w = inp.shape
+    estmv = me_spynet(sd, inp, x[torch.as_tensor(ref_index)], levels)      # flow against ORIGINAL references
+    mvfeature = analysis_mv(sd, estmv)
+    quant_mv = torch.round(mvfeature)
+    mv_up = synthesis_mv(sd, quant_mv)
+    bits_mv, _ = factorized_bits(sd, "bitEstimator_mv", quant_mv)
+    com = [None] * bs
+    mc = [None] * bs
+    wp = [None] * bs
+    bits_res = 0.0
+    for layer in layers:
+        tars = [t for t in layer if t <= bs]
+        if not tars:
+            continue
+        ref = torch.cat([x[:1] if parents[t] == 0 else com[parents[t] - 1] for t in tars], 0)
+        diff = torch.cat([mv_up[t - 1:t] for t in tars], 0)
+        target = torch.cat([inp[t - 1:t] for t in tars], 0)
+        warpframe = flow_warp(ref, diff)
+        pred = warp_net(sd, torch.cat((warpframe, ref), 1)) + warpframe
+        feature = analysis(sd, target - pred)
+        z_hat = torch.round(analysis_prior(sd, feature))
+        sigma = synthesis_prior(sd, z_hat)
+        feat_hat = torch.round(feature)
+        res_hat = synthesis(sd, feat_hat)
+        bf, _ = laplace_bits(feat_hat, sigma)
+        bz, _ = factorized_bits(sd, "bitEstimator_z", z_hat)
+        bits_res = bits_res + bf + bz
+        cf = torch.clip(res_hat + pred, min=0, max=1)
+        for i, t in enumerate(tars):
+            com[t - 1], mc[t - 1], wp[t - 1] = cf[i:i + 1], pred[i:i + 1], warpframe[i:i + 1]
+    com, mc, wp = torch.cat(com, 0), torch.cat(mc, 0), torch.cat(wp, 0)
+    rec_loss = torch.mean((com - inp).pow(2))
+    warp_loss = torch.mean((wp - inp).pow(2))
+    mc_loss = torch.mean((mc - inp).pow(2))
+    bpp_res = bits_res / (bs * h * w)
+    bpp = bpp_res + bits_mv / (bs * h * w)
+    return com, mc, wp, rec_loss, warp_loss, mc_loss, bpp_res, bpp
+
+
 def gop_forward(sd, frames, levels=4):
     """parallel_compression, 'DVC-pretrained' branch — models.py:368-383, 400-410.
 

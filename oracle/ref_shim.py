@@ -126,3 +126,38 @@ def run_reference_with_capture(model, cur, ref):
     cap["recon"] = cap["prediction"] + cap["recon_res"]
     del cap["warp_in"], cap["warpnet_out"]
     return out, cap
+
+
+class _AnyModule(types.ModuleType):
+    """Stub package for the reference's un-vendored imports (compressai, pytorch_msssim): every attribute is a
+    placeholder nn.Module subclass, which is enough for ``models.py`` to define (not run) the codecs built on them."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        cls = type(name, (torch.nn.Module,), {"__init__": lambda self, *a, **k: torch.nn.Module.__init__(self)})
+        setattr(self, name, cls)
+        return cls
+
+
+def load_reference_models():
+    """Imports the reference ``models.py`` (GOP driver, LSVC, ...) with import-time stubs only: compressai and
+    pytorch_msssim placeholders (none of them is touched by the DVC / LSVC-128 paths), torchac, and the
+    device-agnostic copy of ``torch_warp`` (models.py:732-741 has the same 4 statements as endecoder.py:52-67)."""
+    load_reference()
+    names = ["compressai", "compressai.entropy_models", "compressai.models", "compressai.models.waseda",
+             "compressai.models.video", "compressai.models.video.google", "compressai.models.utils",
+             "compressai.layers", "compressai.ops", "compressai.zoo", "compressai.ans", "pytorch_msssim"]
+    for name in names:
+        if name not in sys.modules:
+            sys.modules[name] = _AnyModule(name)
+    for name in names:
+        if "." in name:
+            parent, child = name.rsplit(".", 1)
+            setattr(sys.modules[parent], child, sys.modules[name])
+    sys.modules["torchac"] = _AnyModule("torchac")
+    with _cwd(REF_ROOT):
+        import models as refmodels  # noqa
+    refmodels.torch_warp = _torch_warp_any_device
+    refmodels.flow_warp = _torch_warp_any_device
+    return refmodels

@@ -536,3 +536,57 @@ def test_entropy_models_meanscale_forward(dev):
     if flips.sum().item() == 0 and (d > 1e-3).sum().item() == 0:
         bits, want_bits = float(m.get_estimate_bits((xl, zl))[0]), float(O.meanscale_bits(want_xl, want_zl)[0])
         assert abs(bits - want_bits) <= 0.005 * want_bits
+
+
+@pytest.mark.parametrize("tag,name", [("tree", "LSVC-128"), ("chain", "LSVC-L-128")])
+def test_lsvc_forward_matches_reference_golden(dev, state_dict, tag, name):
+    """SURVEY 8f N1 — LSVC batched / tree GOP forward (models.py:1344-1411) through fvc_lsvc_mv_forward /
+    fvc_lsvc_mc_res_forward against the unmodified reference's outputs (tests/golden/lsvc_64.npz)."""
+    from conftest import load_golden
+    from fastvideocodec_b200.lsvc import LSVC
+    gold = load_golden("lsvc_64.npz")
+    m = LSVC(name)
+    m.load_state_dict(state_dict)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        out = m(gold["x"].to(dev))
+    # warped / MC frames of the first tree layer depend on no quantiser of this GOP other than the MV latents
+    for i, n in enumerate(["com", "mc", "warped"]):
+        d = (out[i].cpu() - gold["%s_%s" % (tag, n)]).abs()
+        # metric-level closed-loop gate (a tie flip in a parent frame moves its children, see DESIGN.md 3)
+        assert d.mean().item() <= 2e-3, (n, d.mean().item())
+    for i, n in enumerate(["rec_loss", "warp_loss", "mc_loss", "bpp_res", "bpp"], start=3):
+        a, b = float(out[i]), float(gold["%s_%s" % (tag, n)])
+        assert abs(a - b) <= 0.005 * abs(b), (n, a, b)
+    # GOP driver, LSVC branch (models.py:384-398)
+    from fastvideocodec_b200 import parallel_compression
+    with torch.no_grad():
+        pc = parallel_compression(None, m, gold["x"].to(dev))
+    x = gold["x"][1:]
+    ref_psnr = [float(10 * torch.log10(1 / torch.mean((gold["%s_com" % tag][i] - x[i]) ** 2))) for i in range(4)]
+    assert pc[0].shape == (5, 3, 64, 64) and all(abs(a - b) <= 0.02 for a, b in zip(pc[6], ref_psnr))
+    assert abs(pc[3] - float(gold["%s_bpp" % tag])) <= 0.005 * float(gold["%s_bpp" % tag])
+    m.release()
+
+
+def test_lsvc_tree_equals_dvc_building_blocks(dev, state_dict):
+    """Element level: LSVC with the linear graph on a 2-frame clip is one DVC P-frame whose flow is estimated
+    against the ORIGINAL reference — identical to VideoCompressor.forward when reference == original (frame 1)."""
+    from fastvideocodec_b200 import VideoCompressor
+    from fastvideocodec_b200.lsvc import LSVC
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    x = synthetic_gop(128, 192, gop=2, gop_id=6)[:, 0].to(dev)
+    l = LSVC("LSVC-L-128")
+    l.load_state_dict(state_dict)
+    l = l.to(dev).eval()
+    v = VideoCompressor()
+    v.load_state_dict(state_dict)
+    v = v.to(dev).eval()
+    with torch.no_grad():
+        lo = l(x)
+        vo = v(x[1:2], x[0:1])
+    assert torch.equal(lo[0], vo[0])                        # clipped reconstruction, bit for bit
+    assert abs(float(lo[7]) - float(vo[7])) <= 1e-6 * float(vo[7])
+    assert abs(float(lo[5]) - float(vo[3])) <= 1e-6 * float(vo[3]) and abs(float(lo[4]) - float(vo[2])) <= 1e-6 * float(vo[2])
+    l.release()
+    v.release()

@@ -153,6 +153,43 @@ def test_parallel_compression_matches_reference_aggregation():
     assert all(abs(a - b) < 1e-4 for a, b in zip(psnr_list, psnrs))
 
 
+class _FakeLSVC(torch.nn.Module):
+    """Stands in for LSVC (one forward per GOP, models.py:384-398)."""
+    r, name = 2048, 'LSVC-128'
+
+    def forward(self, x):
+        com = 0.5 * (x[1:] + x[:-1])
+        mse = torch.mean((com - x[1:]) ** 2)
+        return com, x[:-1].clone(), x[:-1] * 0.9, mse, mse * 3, mse * 2, torch.tensor(0.125), torch.tensor(0.5)
+
+
+def test_parallel_compression_lsvc_branch():
+    from fastvideocodec_b200 import LSVC, get_codec_model, parallel_compression
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    data = synthetic_gop(64, 64, gop=4, gop_id=2)[:, 0]
+    out = parallel_compression(None, _FakeLSVC(), data.clone())
+    x_hat, loss, img_loss, be_loss, be_res_loss, psnr, psnr_list, aux, aux2 = out[:9]
+    assert x_hat.shape == (4, 3, 64, 64) and torch.equal(x_hat[0], data[0]) and len(out) == 11
+    com = 0.5 * (data[1:] + data[:-1])
+    mse = torch.mean((com - data[1:]) ** 2)
+    assert abs(be_loss - 0.5) < 1e-7 and be_res_loss == 0 and abs(img_loss - 2048 * float(mse)) < 1e-4
+    assert abs(float(loss) - (2048 * float(mse) + 0.5)) < 1e-4 and len(psnr_list) == 3
+    per = [float(10 * torch.log10(1 / torch.mean((com[i] - data[i + 1]) ** 2))) for i in range(3)]
+    assert all(abs(a - b) < 1e-4 for a, b in zip(psnr_list, per)) and abs(psnr - sum(per) / 3) < 1e-4
+    assert abs(aux2 - sum(float(10 * torch.log10(1 / torch.mean((data[i] - data[i + 1]) ** 2))) for i in range(3)) / 3) < 1e-4
+    # constructor surface (models.py:1157-1180): 128-channel non-attention names only
+    m = get_codec_model('LSVC-L-128', compression_level=3)
+    assert isinstance(m, LSVC) and m.r == 2048 and m.I_level == 22 and set(m.state_dict()) == set(
+        __import__('fastvideocodec_b200').VideoCompressor().state_dict())
+    for bad in ('LSVC-A', 'LSVC-S-128', 'LSVC'):
+        with pytest.raises(NotImplementedError):
+            LSVC(bad)
+    with pytest.raises(NotImplementedError):
+        m.train()(data)
+    with pytest.raises(TypeError):
+        m.eval()(data)                       # CPU tensor: no CPU fallback
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)

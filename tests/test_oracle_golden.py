@@ -94,3 +94,35 @@ def test_live_reference_real_spynet_weights():
         assert (cap[name] != cap_ref[name]).float().mean().item() <= 1e-4
     assert abs(float(out[7]) - float(out_ref[7])) <= 1e-4 * float(out_ref[7])
     assert abs(10 * math.log10(1 / float(out[1])) - 10 * math.log10(1 / float(out_ref[1]))) <= 0.02
+
+
+def test_oracle_lsvc_matches_reference(state_dict):
+    """the oracle's LSVC.forward restatement (tree and chain GOP graphs) against outputs of the
+    unmodified reference models.LSVC('LSVC-128' / 'LSVC-L-128') — tests/golden/lsvc_64.npz (oracle/gen_golden_lsvc.py)."""
+    from conftest import load_golden
+    from fastvideocodec_b200.lsvc import graph_from_batch, refidx_from_graph
+    gold = load_golden("lsvc_64.npz")
+    x = gold["x"]
+    for tag, linear in (("tree", False), ("chain", True)):
+        g, layers, parents = graph_from_batch(4, isLinear=linear)
+        out = O.lsvc_forward(state_dict, x, layers, parents, refidx_from_graph(g, 4))
+        for i, n in enumerate(["com", "mc", "warped"]):
+            assert (out[i] - gold["%s_%s" % (tag, n)]).abs().max().item() <= 2e-5, (tag, n)
+        for i, n in enumerate(["rec_loss", "warp_loss", "mc_loss", "bpp_res", "bpp"], start=3):
+            a, b = float(out[i]), float(gold["%s_%s" % (tag, n)])
+            assert abs(a - b) <= 1e-5 * abs(b), (tag, n, a, b)
+
+
+def test_lsvc_graph_helpers():
+    """generate_graph / graph_from_batch / refidx_from_graph (models.py:683-728, 923-949)."""
+    from fastvideocodec_b200.lsvc import graph_from_batch, refidx_from_graph
+    g, layers, parents = graph_from_batch(6)
+    assert layers == [[1, 4], [2, 3, 5, 6]] and refidx_from_graph(g, 6) == [0, 1, 1, 0, 4, 4]
+    g, layers, parents = graph_from_batch(4)
+    assert refidx_from_graph(g, 4) == [0, 1, 1, 0]
+    g, layers, parents = graph_from_batch(9, isLinear=True)
+    assert refidx_from_graph(g, 9) == list(range(9)) and layers[:3] == [[1], [2], [3]]
+    g, layers, parents = graph_from_batch(14)
+    assert len(layers) == 3 and parents[14] == 12 and refidx_from_graph(g, 14)[7] == 0
+    g, layers, parents = graph_from_batch(5, isOnehop=True)
+    assert refidx_from_graph(g, 5) == [0] * 5
