@@ -20,7 +20,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 SPLIT = os.environ.get("FVC_SPLIT", "fp16").lower()   # fp16 (default, 22-bit pairs) | bf16 (16-bit pairs)
 FLAGS = ["-DFVC_SPLIT_FP16=%d" % (0 if SPLIT == "bf16" else 1), "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-         "-Xptxas", "-v"]
+         "-Xptxas", "-v"] + os.environ.get("FVC_NVCC_EXTRA", "").split()   # e.g. -DFVC_TC_ACCDBG (accumulator-warp counters)
 
 
 def sources():

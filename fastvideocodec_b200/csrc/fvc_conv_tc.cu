@@ -70,6 +70,9 @@ struct alignas(64) TcParams {
     int Hq, Wq, tiles_x, tiles_y, B, os, Hout, Wout, Cout, nchunks;
     uint32_t patch_bytes, patch_tx, btile_bytes, stage_bytes, tmem_cols, idesc;
     int npb, T;       // patch buffers (1 or 2), weight tiles per stage
+    int pair;         // CTA-pair mode: tcgen05 cta_group::2, M = 256 (two CTAs x 128 pixels), each CTA stages half of
+                      // every weight tile; tiles_x then counts PAIRS of tiles along x
+    int nab_log2;     // log2 of the number of partial-accumulator buffers in TMEM (2 or 4 buffers of CT columns)
     int merged;       // Cout <= 16: weight rows interleave 8-row blocks of w_hi and w_lo (MMA N = 32, two
                       // products per A read); the epilogue adds the two column blocks of every channel chunk
     int pitch;        // bytes per pixel of a record segment in shared memory: 128 (SWIZZLE_128B), or 32 for the
@@ -136,10 +139,55 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    // default semantics (release at CTA scope), as for a local arrive: a cluster-scope release costs an ERRBAR that
+    // waits for the epilogue's outstanding global stores (ncu: 14 % of the kernel's stall samples)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+// TMA loads of a CTA pair: the bytes complete on the barrier `bar_cluster` (a shared::cluster address, here
+// always the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// commit of the leader's MMAs, delivered to the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void tc_commit_t(uint32_t bar) {
+    if (PAIR) tc_commit_pair(bar);
+    else tc_commit(bar);
 }
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -216,10 +264,22 @@ __device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t alo, uint32_t 
         : "memory");
 }
 
+__device__ __forceinline__ void tc_mma2_pair(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                             uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
 // All MMAs of one weight tile: S sub-tiles x KS k-steps, straight-line (the issuing thread is the
 // bottleneck otherwise: the MMA queue is shallow, every scalar instruction between MMAs shows up as
 // tensor-pipe idle time).
-template <int KS>
+template <int KS, bool PAIR>
 __device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint32_t alo, uint32_t ahi, uint32_t blo,
                                             uint32_t bhi, uint32_t idesc, uint32_t acc0, int S, int s_first,
                                             uint32_t sstep) {
@@ -227,9 +287,14 @@ __device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint32_t 
     for (int s = 0; s < 4; ++s) {
         if (s < S && (s & 1) == s_first) {   // two issuer warps: even / odd sub-tiles
 #pragma unroll
-            for (int k = 0; k < KS; ++k)
-                tc_mma2(dcol + (uint32_t)s * N, alo + (uint32_t)s * sstep + (uint32_t)(2 * k), ahi, blo + (uint32_t)(2 * k), bhi,
-                        idesc, k == 0 ? acc0 : 1u);
+            for (int k = 0; k < KS; ++k) {
+                if (PAIR)
+                    tc_mma2_pair(dcol + (uint32_t)s * N, alo + (uint32_t)s * sstep + (uint32_t)(2 * k), ahi,
+                                 blo + (uint32_t)(2 * k), bhi, idesc, k == 0 ? acc0 : 1u);
+                else
+                    tc_mma2(dcol + (uint32_t)s * N, alo + (uint32_t)s * sstep + (uint32_t)(2 * k), ahi, blo + (uint32_t)(2 * k), bhi,
+                            idesc, k == 0 ? acc0 : 1u);
+            }
         }
     }
 }
@@ -240,9 +305,10 @@ __device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint32_t 
 struct PassIter {
     int tile, pass;     // current tile id, pass index inside the tile's sub-convolution
     int b, sub, ty, tx;
+    int xmul, xadd;     // CTA pairs: tile column = 2 * (pair column) + CTA rank
     __device__ __forceinline__ void decode(const TcParams& P) {
         int t = tile;
-        tx = t % P.tiles_x; t /= P.tiles_x;
+        tx = (t % P.tiles_x) * xmul + xadd; t /= P.tiles_x;
         ty = t % P.tiles_y; t /= P.tiles_y;
         sub = t % P.nsub;
         b = t / P.nsub;
@@ -434,7 +500,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
 // quarter 4 times).
 // NCH: 8-column chunks of the running sum each accumulator thread owns (CT/4 = 8*NCH);
 // RES: the epilogue adds an ACT-format residual (ResBlock skip connection)
-template <int NCH, bool RES>
+template <int NCH, bool RES, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: SWIZZLE_128B atoms
@@ -444,19 +510,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const uint32_t bars = bst0 + P.nst * P.stage_bytes;             // mbarriers (8 B each)
     const uint32_t bar_pfull = bars, bar_pempty = bars + 16;        // [npb <= 2] each
     const uint32_t bar_bfull = bars + 32, bar_bempty = bars + 32 + 8 * 8;   // [nst <= 8] each
-    const uint32_t bar_afull = bars + 32 + 16 * 8, bar_aempty = bar_afull + 16;  // partial buffers [2] each
-    const uint32_t tmem_slot = bar_aempty + 16;
+    const uint32_t bar_afull = bars + 32 + 16 * 8, bar_aempty = bar_afull + 32;  // partial buffers [<= 4] each
+    const uint32_t tmem_slot = bar_aempty + 32;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 256);   // [N <= 128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;
+    const int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;   // PAIR: pairs of tiles (x-neighbours)
+    // CTA pair: both CTAs walk the same (pair-tile, pass) sequence; rank 0 ("leader") issues every MMA for both
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int xmul = PAIR ? 2 : 1, xadd = (int)rank;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_pfull + 8 * i, 1);
             mbar_init(bar_pempty + 8 * i, 2);   // one commit per MMA issuer warp
+        }
+        for (int i = 0; i < 4; ++i) {
             mbar_init(bar_afull + 8 * i, 2);
-            mbar_init(bar_aempty + 8 * i, 16);  // one arrive per accumulator warp
+            mbar_init(bar_aempty + 8 * i, PAIR ? 32 : 16);  // one arrive per accumulator warp (of both CTAs)
         }
         for (int i = 0; i < P.nst; ++i) {
             mbar_init(bar_bfull + 8 * i, 1);
@@ -465,10 +538,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"(P.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {   // executed by one warp of each CTA of the pair
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"(P.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"(P.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (threadIdx.x >= 96 && (int)threadIdx.x - 96 < P.N) {
         const int c = (int)threadIdx.x - 96;
@@ -476,6 +556,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before any remote signal
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -486,8 +567,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         // ring would starve the other: the patch of the next pass frees only when the current pass ends).
         if (elect_one()) {
             PassIter wc, pc;
-            wc.tile = blockIdx.x; wc.pass = 0; wc.decode(P);
+            wc.xmul = xmul; wc.xadd = xadd;
+            wc.tile = tile0; wc.pass = 0; wc.decode(P);
             pc = wc;
+            // PAIR: all loads complete on the LEADER's "full" barriers, which expect the bytes of both CTAs
+            const uint32_t pfull_l = PAIR ? mapa_u32(bar_pfull, 0) : bar_pfull;
+            const uint32_t bfull_l = PAIR ? mapa_u32(bar_bfull, 0) : bar_bfull;
+            const int Nh = P.N >> 1;
             uint32_t st = 0, stph = 0;   // weight-stage ring position and its phase bit
             uint32_t set = 0, pph = 0;   // patch ring
             const uint32_t nst = (uint32_t)P.nst, npb = (uint32_t)P.npb;
@@ -498,30 +584,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 bool progress = false;
                 if (pc.valid(ntiles) && mbar_try_wait(bar_pempty + 8 * set, pph ^ 1u)) {
                     const TcPass& ps = P.pass[P.sub[pc.sub].pass_first + pc.pass];
-                    mbar_expect_tx(bar_pfull + 8 * set, P.patch_tx);
                     const int x0 = pc.tx * 8 * P.SX + ps.ox, y0 = pc.ty * 16 + ps.oy;
-                    tma_load_5d(patch0 + set * P.patch_bytes, &P.mapA, bar_pfull + 8 * set, 0, ps.seg, x0, y0,
-                                pc.b * P.planes + ps.plane);
+                    if (PAIR) {
+                        if (rank == 0) mbar_expect_tx(bar_pfull + 8 * set, 2u * P.patch_tx);
+                        tma_load_5d_pair(patch0 + set * P.patch_bytes, &P.mapA, pfull_l + 8 * set, 0, ps.seg, x0, y0,
+                                         pc.b * P.planes + ps.plane);
+                    } else {
+                        mbar_expect_tx(bar_pfull + 8 * set, P.patch_tx);
+                        tma_load_5d(patch0 + set * P.patch_bytes, &P.mapA, bar_pfull + 8 * set, 0, ps.seg, x0, y0,
+                                    pc.b * P.planes + ps.plane);
+                    }
                     if (++set == npb) { set = 0; pph ^= 1u; }
-                    pc.next(P, gridDim.x);
+                    pc.next(P, tstride);
                     progress = true;
                 }
                 if (wc.valid(ntiles) && mbar_try_wait(bar_bempty + 8 * st, stph ^ 1u)) {
                     const TcPass& ps = P.pass[P.sub[wc.sub].pass_first + wc.pass];
                     // T weight tiles per stage; the last stage of a pass over-reads (the stream is padded)
-                    mbar_expect_tx(bar_bfull + 8 * st, P.stage_bytes);
-                    tma_load_2d(bst0 + st * P.stage_bytes, &P.mapB, bar_bfull + 8 * st, 0,
-                                (int)((ps.btile_first + (uint32_t)wi) * (uint32_t)P.N));
+                    if (PAIR) {
+                        // this CTA stages rows [rank * N/2, (rank + 1) * N/2) of each of the stage's T tiles
+                        if (rank == 0) mbar_expect_tx(bar_bfull + 8 * st, 2u * P.stage_bytes);
+                        for (int u = 0; u < T; ++u)
+                            tma_load_2d_pair(bst0 + st * P.stage_bytes + (uint32_t)u * P.btile_bytes, &P.mapB, bfull_l + 8 * st, 0,
+                                             (int)((ps.btile_first + (uint32_t)(wi + u)) * (uint32_t)P.N) + (int)rank * Nh);
+                    } else {
+                        mbar_expect_tx(bar_bfull + 8 * st, P.stage_bytes);
+                        tma_load_2d(bst0 + st * P.stage_bytes, &P.mapB, bar_bfull + 8 * st, 0,
+                                    (int)((ps.btile_first + (uint32_t)wi) * (uint32_t)P.N));
+                    }
                     if (++st == nst) { st = 0; stph ^= 1u; }
                     wi += T;
-                    if (wi >= ps.ntaps * ps.nbt) { wi = 0; wc.next(P, gridDim.x); }
+                    if (wi >= ps.ntaps * ps.nbt) { wi = 0; wc.next(P, tstride); }
                     progress = true;
                 }
                 if (progress) spins = 0;
                 else if (++spins > (1u << 25)) __trap();
             }
         }
-    } else if (warp == 1 || warp == 2) {
+    } else if ((warp == 1 || warp == 2) && rank == 0) {
         // ================================ MMA issuers ============================================
         // Two warps run the same loop nest and issue the MMAs of the even / odd sub-tiles (disjoint
         // accumulator columns, so no ordering hazard): the tensor-pipe queue is shallow and one warp's
@@ -534,10 +634,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const int s_first = warp - 1;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform copy
             const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0 && warp == 1;
-            long long w_pfull = 0, w_aempty = 0, w_bfull = 0, w_issue = 0, n_issue = 0;
+            long long w_pfull = 0, w_aempty = 0, w_bfull = 0;
             const long long t_begin = dbg_on ? clock64() : 0;
             PassIter cur;
-            cur.tile = blockIdx.x; cur.pass = 0; cur.decode(P);
+            cur.xmul = xmul; cur.xadd = xadd;
+            cur.tile = tile0; cur.pass = 0; cur.decode(P);
             uint32_t gg = 0;                    // accumulation-group counter
             bool gopen = false;                 // a group (TMEM chain) is open; it may span segment passes
             uint32_t gpb = 0, gdcol = 0, gacc0 = 0;
@@ -554,6 +655,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const uint32_t N = (uint32_t)P.N, nst = (uint32_t)P.nst, CT = (uint32_t)P.CT, npb = (uint32_t)P.npb;
             const uint32_t idesc = P.idesc, btile16 = P.btile_bytes >> 4, stage16 = P.stage_bytes >> 4;
             const uint32_t bst16 = lo0 + (bst0 >> 4);
+            const uint32_t nabs = (uint32_t)P.nab_log2, nabm = (1u << nabs) - 1u;
             while (cur.valid(ntiles)) {
                 const TcSub& sb = P.sub[cur.sub];
                 const TcPass& ps = P.pass[sb.pass_first + cur.pass];
@@ -573,9 +675,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     // sub-tiles) are issued per loop iteration; per-tile loop control would dominate otherwise
                     while (t < ntaps) {
                         const int t0 = t, t1 = min(t + gtaps, ntaps);
-                        const uint32_t pb = gg & 1u;
+                        const uint32_t pb = gg & nabm;
                         { const long long c0 = dbg_on ? clock64() : 0;
-                          mbar_wait(bar_aempty + 8 * pb, ((gg >> 1) & 1u) ^ 1u);
+                          mbar_wait(bar_aempty + 8 * pb, ((gg >> nabs) & 1u) ^ 1u);
                           if (dbg_on) w_aempty += clock64() - c0; }
                         tc_fence_after();
                         const uint32_t dcol = tmem_u + pb * CT;
@@ -594,20 +696,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                                     const uint32_t alo = pa16 + toff;
                                     toff = (uint32_t)toffp[min(t + u + 1, ntaps - 1)] >> 4;
                                     const uint32_t b0 = blo + (uint32_t)(tpt * u) * btile16;
-                                    issue_stage<1>(dcol, N, alo, ahi, b0, bhi, idesc, (t + u == t0) ? 0u : 1u, S, s_first, sstep);
-                                    if (two) issue_stage<1>(dcol, N, alo, ahi, b0 + btile16, bhi, idesc, 1u, S, s_first, sstep);
+                                    issue_stage<1, PAIR>(dcol, N, alo, ahi, b0, bhi, idesc, (t + u == t0) ? 0u : 1u, S, s_first, sstep);
+                                    if (two) issue_stage<1, PAIR>(dcol, N, alo, ahi, b0 + btile16, bhi, idesc, 1u, S, s_first, sstep);
                                 }
                             }
                             t += nt;
                             slot += tpt * nt;
                             blo += (uint32_t)(tpt * nt) * btile16;
                             if (slot >= T || t == ntaps) {
-                                if (lead) tc_commit(bar_bempty + 8 * st);
+                                if (lead) tc_commit_t<PAIR>(bar_bempty + 8 * st);
                                 if (++st == nst) { st = 0; stph ^= 1u; }
                                 slot = 0;
                             }
                         }
-                        if (lead) tc_commit(bar_afull + 8 * pb);
+                        if (lead) tc_commit_t<PAIR>(bar_afull + 8 * pb);
                         ++gg;
                     }
                 }
@@ -618,12 +720,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         // a new accumulation group starts here: hand the finished chain to the accumulator
                         // warps; the next partial buffer must have been drained by them
                         if (gopen) {
-                            if (lead) tc_commit(bar_afull + 8 * gpb);
+                            if (lead) tc_commit_t<PAIR>(bar_afull + 8 * gpb);
                             ++gg;
                         }
-                        gpb = gg & 1u;
+                        gpb = gg & nabm;
                         { const long long c0 = dbg_on ? clock64() : 0;
-                          mbar_wait(bar_aempty + 8 * gpb, ((gg >> 1) & 1u) ^ 1u);
+                          mbar_wait(bar_aempty + 8 * gpb, ((gg >> nabs) & 1u) ^ 1u);
                           if (dbg_on) w_aempty += clock64() - c0; }
                         tc_fence_after();
                         gdcol = tmem_u + gpb * CT;
@@ -643,35 +745,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         }
                         if (lead) {
                             // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
-                            if (j == 1 && short2) issue_stage<2>(gdcol, N, alo, ahi, blo, bhi, idesc, gacc0, S, s_first, sstep);
-                            else issue_stage<4>(gdcol, N, alo, ahi, blo, bhi, idesc, gacc0, S, s_first, sstep);
+                            if (j == 1 && short2) issue_stage<2, PAIR>(gdcol, N, alo, ahi, blo, bhi, idesc, gacc0, S, s_first, sstep);
+                            else issue_stage<4, PAIR>(gdcol, N, alo, ahi, blo, bhi, idesc, gacc0, S, s_first, sstep);
                         }
                         gacc0 = 1u;
                         blo += btile16;
                         if (++slot == T || (t == ntaps - 1 && (j == 1 || !two))) {
-                            if (lead) tc_commit(bar_bempty + 8 * st);   // frees the stage when these MMAs retire
+                            if (lead) tc_commit_t<PAIR>(bar_bempty + 8 * st);   // frees the stage when these MMAs retire
                             if (++st == nst) { st = 0; stph ^= 1u; }
                             slot = 0;
                         }
                     }
                 }
                 if (ps.gend && gopen) {
-                    if (lead) tc_commit(bar_afull + 8 * gpb);      // chain complete -> accumulator warps
+                    if (lead) tc_commit_t<PAIR>(bar_afull + 8 * gpb);      // chain complete -> accumulator warps
                     ++gg;
                     gopen = false;
                 }
-                if (lead) tc_commit(bar_pempty + 8 * set);    // patch buffer reusable
+                if (lead) tc_commit_t<PAIR>(bar_pempty + 8 * set);    // patch buffer reusable
                 __syncwarp();
                 if (++set == npb) { set = 0; pph ^= 1u; }
-                cur.next(P, gridDim.x);
+                cur.next(P, tstride);
             }
             if (dbg_on && lead) {
                 P.dbg[0] = (unsigned long long)(clock64() - t_begin);
                 P.dbg[1] = (unsigned long long)w_pfull;
                 P.dbg[2] = (unsigned long long)w_aempty;
                 P.dbg[3] = (unsigned long long)w_bfull;
-                P.dbg[4] = (unsigned long long)w_issue;
-                P.dbg[5] = (unsigned long long)n_issue;
             }
         }
     } else if (warp >= 3) {
@@ -682,16 +782,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const int th = row >> 3, tw = row & 7;
         const uint32_t colbase = (uint32_t)part * (uint32_t)(NCH * 8);
         constexpr bool PARK = NCH >= 6;
+        const uint32_t nabs = (uint32_t)P.nab_log2, nabm = (1u << nabs) - 1u;
+        const uint32_t aempty_l = PAIR ? mapa_u32(bar_aempty, 0) : bar_aempty;   // the leader's issuers wait on it
         uint32_t gg = 0;
         float run[NCH * 8];
         const int tiles_xy = P.tiles_x * P.tiles_y;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#ifdef FVC_TC_ACCDBG
+        const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == 3;
+        long long a_wait = 0, a_drain = 0, a_epi = 0;
+#endif
+        for (int tile = tile0; tile < ntiles; tile += tstride) {
             const int ng = P.sub[(tile / tiles_xy) % P.nsub].ngroups;
             if (RES) {
                 // pull this thread's skip-connection records into L2 while the tile's MMAs run (the epilogue's
                 // loads then hit L2 instead of paying DRAM latency in the middle of the store stream)
                 int t = tile;
-                const int tx = t % P.tiles_x; t /= P.tiles_x;
+                const int tx = (t % P.tiles_x) * xmul + xadd; t /= P.tiles_x;
                 const int ty = t % P.tiles_y; t /= P.tiles_y;
                 const int sub = t % P.nsub;
                 const int b = t / P.nsub;
@@ -712,9 +818,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 }
             }
             for (int g = 0; g < ng; ++g, ++gg) {
-                const uint32_t pb = gg & 1u;
-                mbar_wait_sleep(bar_afull + 8 * pb, (gg >> 1) & 1u, P.acc_sleep_ns);
+                const uint32_t pb = gg & nabm;
+#ifdef FVC_TC_ACCDBG
+                const long long c0 = adbg ? clock64() : 0;
+#endif
+                mbar_wait_sleep(bar_afull + 8 * pb, (gg >> nabs) & 1u, P.acc_sleep_ns);
                 tc_fence_after();
+#ifdef FVC_TC_ACCDBG
+                const long long c1 = adbg ? clock64() : 0;
+                a_wait += c1 - c0;
+#endif
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pb * P.CT + colbase;
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
@@ -737,14 +850,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 if (!PARK || g + 1 < ng) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(aempty_l + 8 * pb);
+                        else mbar_arrive(bar_aempty + 8 * pb);
+                    }
                 }
+#ifdef FVC_TC_ACCDBG
+                if (adbg) a_drain += clock64() - c1;
+#endif
             }
+#ifdef FVC_TC_ACCDBG
+            const long long e0 = adbg ? clock64() : 0;
+#endif
             // tile coordinates are decoded only now (laundered through an empty asm) so that the epilogue's
             // address arithmetic cannot be hoisted above the drain loop, where it would spill `run`
             int t = tile;
             asm volatile("" : "+r"(t));
-            const int tx = t % P.tiles_x; t /= P.tiles_x;
+            const int tx = (t % P.tiles_x) * xmul + xadd; t /= P.tiles_x;
             const int ty = t % P.tiles_y; t /= P.tiles_y;
             const int sub = t % P.nsub;
             const int b = t / P.nsub;
@@ -769,7 +891,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 // the sums in the partial buffer that was just drained (it stays ours until we arrive on
                 // its "empty" barrier), finish the lower half from registers, then fetch the rest back.
                 constexpr int NH = ((NCH / 2) + 1) & ~1;
-                const uint32_t pb = (gg - 1u) & 1u;
+                const uint32_t pb = (gg - 1u) & nabm;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pb * P.CT + colbase;
 #pragma unroll
                 for (int i = NH; i < NCH; ++i) tc_st8(taddr + i * 8, reinterpret_cast<const uint32_t*>(run + i * 8));
@@ -782,18 +904,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_aempty + 8 * pb);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(aempty_l + 8 * pb);
+                    else mbar_arrive(bar_aempty + 8 * pb);
+                }
                 tile_epilogue<NCH - NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase + NH * 8);
             }
+#ifdef FVC_TC_ACCDBG
+            if (adbg) a_epi += clock64() - e0;
+#endif
         }
+#ifdef FVC_TC_ACCDBG
+        if (adbg && lane == 0) { P.dbg[4] = (unsigned long long)a_wait; P.dbg[5] = (unsigned long long)a_drain; P.dbg[6] = (unsigned long long)a_epi; }
+#endif
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // neither CTA may retire while the other still reads its shared memory / signals it
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols)
-                     : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols)
+                         : "memory");
     }
 }
 
@@ -996,7 +1132,21 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     const int smem_cap = 232448 - 1024 /*alignment*/ - 1024 /*barriers + bias*/;
     const int pitch = Cp == 8 ? 32 : 128;
     P.pitch = pitch;
-    const int tile_bytes = N * pitch;
+    // CTA pairs (cta_group::2): two x-neighbouring tiles are one M = 256 MMA; each CTA stages half of every weight
+    // tile, which halves the weight traffic through shared memory and the B-operand reads (the tensor pipe is
+    // bound by shared-memory bandwidth for N < 128 and by the weight re-staging for N = 128, S = 1)
+    int taps_total = 0;
+    for (auto& g : groups) taps_total += (int)g.taps.size();
+    // MMAs per sub-tile and tile: large = bound by the tensor pipe, small = bound by the accumulator warps
+    const int mma_sub = taps_total / std::max(1, L.nsub) * (merged ? (Cp == 8 ? 1 : Cp / 8) : (Cp == 8 ? 2 : Cp * 3 / 16));
+    const bool acc_bound = ep.res_act.p != nullptr || mma_sub < env_int("FVC_TC_ACCBOUND", 100);
+    // Measured at 1080p (tools/layer_ab.py): pairs win everywhere except the accumulator-bound N = 128 layers
+    // (stride-2 transposed 3x3, 54 MMAs per tile), where the single issuer of an S = 1 tile is the limit;
+    // the tensor-bound N = 128 layers run as pairs with S = 2 so that both issuer warps work.
+    const int pair_mode = env_int("FVC_TC_PAIR", 1);   // 0: never, 1: per-layer rule, 2: always
+    const bool pair = N % 16 == 0 && (pair_mode == 2 || (pair_mode == 1 && !(N > 96 && acc_bound && Cp != 8)));
+    P.pair = pair ? 1 : 0;
+    const int tile_bytes = N * pitch / (pair ? 2 : 1);   // per CTA
     int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y, npb = 2, T = 1;
     // S*N accumulator columns per partial buffer, CT/32 in {1,2,3,4,6,8} (template instantiations),
     // CT <= 256 (two partial buffers in 512 TMEM columns, <= 64 running-sum registers per thread).
@@ -1007,11 +1157,15 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // measured per layer class at 1080p (chain 48): N = 128 runs best with S = 1 (32 running sums, no spills:
     // the 64-sum variant stalls on spill reloads queued behind its own global stores), N = 64 3x3/5x5 layers
     // with S = 3, the 7x7 N = 64 layer (SpyNet conv2) with S = 4
-    const int ct_cap = N > 96 ? env_int("FVC_TC_CTMAX128", 128)
-                              : env_int("FVC_TC_CTMAX", (N > 32 && L.k < 7) ? 192 : 256);
+    // Layers with few MMAs per output (transposed / 1x1 convolutions) and residual epilogues are bound by the
+    // accumulator warps, not by the MMAs: they run best with CT = 128 and FOUR partial buffers, so that the MMA
+    // issuers can be a whole tile ahead of an epilogue (measured at 1080p: -0.4 ms per frame).
+    const int ct_cap = N > 96 ? env_int("FVC_TC_CTMAX128", (pair && !acc_bound) ? 256 : 128)
+                              : ((N > 32 && L.k < 7) ? env_int("FVC_TC_CTMAX64", acc_bound ? 128 : 192)
+                                                     : env_int("FVC_TC_CTMAX", 256));
     const int sx_max = std::min(env_int("FVC_TC_SX", 4),
-                                std::max(1, std::min(merged ? 128 : ct_cap, ep.res_act.p ? 192 : 256) / N));
-    const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), 256 / N));
+                                std::max(1, std::min(merged ? 128 : ct_cap, ep.res_act.p ? env_int("FVC_TC_CTRES", 128) : 256) / N));
+    const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), (pair ? env_int("FVC_TC_TPAIR", 512) : 256) / N));   // <= 32 KB per stage and CTA
     // S trades weight re-reads / per-tile overhead (cost ~ one sub-tile's worth per tile, calibrated on
     // SpyNet level 0/1) against filling the 148 SMs: score = wave efficiency * S / (S + 1).
     int sms = 148;
@@ -1029,8 +1183,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * pitch;
         patch = (patch + 1023) & ~(size_t)1023;
-        const long nt = (long)in.B * L.nsub * cdiv(P.Hq, 16) * cdiv(P.Wq, 8 * sx);
-        const double eff = (double)nt / (double)(cdiv64(nt, sms) * sms) * (double)sx / (double)(sx + 1);
+        const long nt = (long)in.B * L.nsub * cdiv(P.Hq, 16) * (pair ? cdiv(cdiv(P.Wq, 8 * sx), 2) : cdiv(P.Wq, 8 * sx));
+        const int units = pair ? sms / 2 : sms;
+        const double eff = (double)nt / (double)(cdiv64(nt, units) * units) * (double)sx / (double)(sx + 1);
         if (eff <= best_eff + 0.02) continue;   // a smaller S must buy a real gain
         bool fits = false;
         for (int nb = 2; nb >= 1 && !fits; --nb) {
@@ -1056,16 +1211,20 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     P.CT = SX * N;
     P.patch_bytes = (uint32_t)((((size_t)PH * PW * pitch) + 1023) & ~(size_t)1023);
     P.patch_tx = (uint32_t)((size_t)PH * PW * pitch);
-    P.btile_bytes = (uint32_t)(N * pitch);
+    P.btile_bytes = (uint32_t)tile_bytes;             // per CTA (half of the tile's rows in pair mode)
     P.stage_bytes = (uint32_t)T * P.btile_bytes;
+    // partial-accumulator buffers: 4 when they fit the 512 TMEM columns (the MMA issuers then run up to a whole
+    // tile ahead of an epilogue), else 2
+    P.nab_log2 = (4 * P.CT <= 512 && env_int("FVC_TC_NAB", 4) >= 4) ? 2 : 1;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * P.CT)) cols <<= 1;
+    while (cols < (uint32_t)((1 << P.nab_log2) * P.CT)) cols <<= 1;
     P.tmem_cols = cols;
-    P.tiles_x = cdiv(P.Wq, 8 * SX);
+    P.tiles_x = pair ? cdiv(cdiv(P.Wq, 8 * SX), 2) : cdiv(P.Wq, 8 * SX);
     P.tiles_y = cdiv(P.Hq, 16);
     // instruction descriptor: D=f32, A=B=f16 (0) or bf16 (1), K-major both, N, M=128
     const uint32_t fmt = FVC_SPLIT_FP16 ? 0u : 1u;
-    P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+              ((uint32_t)((pair ? 256 : 128) >> 4) << 24);
 
     for (auto& g : groups) {
         g.tap_first = ntapent;
@@ -1228,7 +1387,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         }
         cuuint64_t bdims[2] = {(cuuint64_t)rowlen, (cuuint64_t)(nbt_total + T) * N};
         cuuint64_t bstr[1] = {(cuuint64_t)pitch};
-        cuuint32_t bbox[2] = {(cuuint32_t)rowlen, (cuuint32_t)(T * N)};
+        cuuint32_t bbox[2] = {(cuuint32_t)rowlen, (cuuint32_t)(pair ? N / 2 : T * N)};
         cuuint32_t bes[2] = {1, 1};
         r = encode(&P.mapB, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, (void*)plan->wstream, bdims, bstr, bbox, bes,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1247,30 +1406,50 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     }
     plan->smem = 1024 + (size_t)npb * P.patch_bytes + (size_t)nst * P.stage_bytes + 1024;
     int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;
-    plan->grid = std::max(1, std::min(ntiles, sms));
+    plan->grid = pair ? 2 * std::max(1, std::min(ntiles, sms / 2)) : std::max(1, std::min(ntiles, sms));
     *out = plan;
+    return 0;
+}
+
+template <int NCH, bool RES, bool PAIR>
+static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set = true;
+    }
+    if (PAIR) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)plan->grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = plan->smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;   // CTA pair = one cluster (same TPC)
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        FVC_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<NCH, RES, PAIR>, plan->P));
+    } else {
+        k_conv_tc<NCH, RES, PAIR><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->P);
+    }
+    g_launch_count++;
+    FVC_CHECK_LAUNCH();
+    if (plan->dbg) {   // debugging aid: where block 0's MMA issuer spent its cycles
+        unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        FVC_CUDA(cudaStreamSynchronize(s));
+        FVC_CUDA(cudaMemcpy(h, plan->dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        const TcParams& Q = plan->P;
+        fprintf(stderr, "tcdbg pair=%d N=%d S=%d T=%d nst=%d npb=%d PW=%d PH=%d Cout=%d Hout=%d total=%llu pfull=%llu aempty=%llu bfull=%llu | acc wait=%llu drain=%llu epi=%llu res=%d ntiles=%d\n",
+                Q.pair, Q.N, Q.S, Q.T, Q.nst, Q.npb, Q.PW, Q.PH, Q.Cout, Q.Hout, h[0], h[1], h[2], h[3], h[4], h[5], h[6],
+                Q.ep.res_act.p ? 1 : 0, Q.B * Q.nsub * Q.tiles_y * Q.tiles_x);
+    }
     return 0;
 }
 
 template <int NCH, bool RES>
 static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_set = true;
-    }
-    k_conv_tc<NCH, RES><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->P);
-    g_launch_count++;
-    FVC_CHECK_LAUNCH();
-    if (plan->dbg) {   // debugging aid: where block 0's MMA issuer spent its cycles
-        unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
-        FVC_CUDA(cudaStreamSynchronize(s));
-        FVC_CUDA(cudaMemcpy(h, plan->dbg, sizeof(h), cudaMemcpyDeviceToHost));
-        const TcParams& Q = plan->P;
-        fprintf(stderr, "tcdbg N=%d S=%d T=%d nst=%d npb=%d PW=%d PH=%d Cout=%d Hout=%d total=%llu pfull=%llu aempty=%llu bfull=%llu issue=%llu nstage=%llu\n",
-                Q.N, Q.S, Q.T, Q.nst, Q.npb, Q.PW, Q.PH, Q.Cout, Q.Hout, h[0], h[1], h[2], h[3], h[4], h[5]);
-    }
-    return 0;
+    return plan->P.pair ? tc_launch_t3<NCH, RES, true>(plan, s) : tc_launch_t3<NCH, RES, false>(plan, s);
 }
 
 template <int NCH>
