@@ -40,7 +40,11 @@ namespace fvc {
 // ----------------------------------------------------------------------------------------------
 #define TC_MAX_PASS 16
 #define TC_MAX_TAPS 64
-#define TC_THREADS 608   // 19 warps; 96 registers per thread (allocation granularity is 4 warps)
+#define TC_THREADS 640   // 20 warps = 5 warpgroups: warps 0-3 {producer, issuer, issuer, idle} shrink to 40 registers
+                         // (setmaxnreg), the 16 accumulator warps 4-19 grow to 112
+#define TC_ACC_WARP0 4
+#define TC_REGS_CTRL 64
+#define TC_REGS_ACC 104
 
 struct TcPass {
     int8_t seg, plane;     // record segment (128 B unit) and parity plane (0 for stride-1 inputs)
@@ -550,8 +554,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
-    if (threadIdx.x >= 96 && (int)threadIdx.x - 96 < P.N) {
-        const int c = (int)threadIdx.x - 96;
+    if (threadIdx.x >= 128 && (int)threadIdx.x - 128 < P.N) {
+        const int c = (int)threadIdx.x - 128;
         bias_s[c] = c < P.Cout ? P.ep.bias[c] : 0.f;
     }
     tc_fence_before();
@@ -561,6 +565,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    // register re-allocation per warpgroup: the control warps need few registers, the accumulator warps many
+    if (warp < TC_ACC_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
     if (warp == 0) {
         // ================= TMA producer: weight-stream ring + patch ring, polled by one thread ==========
         // Two independent iterators; whichever ring has a free slot is served (a blocking wait on one
@@ -774,10 +781,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 P.dbg[3] = (unsigned long long)w_bfull;
             }
         }
-    } else if (warp >= 3) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_ACC));
         // ======================= accumulator / epilogue warps (16: warps 3..18) ====================
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
-        const int part = (warp - 3) >> 2;                 // which quarter of the CT columns
+        const int part = (warp - TC_ACC_WARP0) >> 2;                 // which quarter of the CT columns
         const int row = quarter * 32 + lane;              // accumulator row = pixel inside the sub-tile
         const int th = row >> 3, tw = row & 7;
         const uint32_t colbase = (uint32_t)part * (uint32_t)(NCH * 8);
@@ -788,7 +797,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         float run[NCH * 8];
         const int tiles_xy = P.tiles_x * P.tiles_y;
 #ifdef FVC_TC_ACCDBG
-        const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == 3;
+        const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == TC_ACC_WARP0;
         long long a_wait = 0, a_drain = 0, a_epi = 0;
 #endif
         for (int tile = tile0; tile < ntiles; tile += tstride) {
