@@ -18,13 +18,16 @@
 //   * Accumulation: tcgen05 adds into its fp32 TMEM accumulator with TRUNCATION (measured: relative bias
 //     -4.9e-8 per MMA in the chain, -2.9e-5 after the 588 MMAs of a 7x7x64 filter; tools/tc_bias.py).  So
 //     TMEM only ever holds SHORT chains (<= 48 MMAs, a "group" of taps, possibly spanning the segment passes
-//     of a tile): two partial-accumulator buffers ping-pong, and 16 accumulator warps drain each finished
+//     of a tile): two or four partial-accumulator buffers rotate, and 16 accumulator warps drain each finished
 //     partial with tcgen05.ld and add it to a running sum in registers in fp32 round-to-nearest, overlapped
 //     with the MMAs of the next group.
-//   * Warp roles (19 warps): warp 0 = TMA producer (polls the weight ring and the patch ring), warps 1-2 =
-//     MMA issuers (even / odd sub-tiles; warp 1 owns the TMEM allocation), warps 3..18 = accumulator /
-//     epilogue warps (drain -> running sum -> bias/activation/skip/GDN -> hi/lo split -> global).
-//     Persistent over tiles.
+//   * Warp roles (20 warps): warp 0 = TMA producer (polls the weight ring and the patch ring), warps 1-2 =
+//     MMA issuers (even / odd sub-tiles; warp 1 owns the TMEM allocation), warp 3 idle, warps 4..19 = accumulator /
+//     epilogue warps (drain -> running sum -> bias/activation/skip/GDN -> hi/lo split -> global).  setmaxnreg
+//     gives the control warpgroup 64 and the accumulator warpgroups 104 registers.  Persistent over tiles.
+//   * CTA pairs (cta_group::2): two x-neighbouring tiles form one M = 256 MMA issued by the leader CTA; each CTA
+//     stages its own patch and half of every weight tile; commits are multicast to both CTAs.
+//   * Up to four partial-accumulator buffers (CT <= 128) let the issuers run a whole tile ahead of an epilogue.
 #include <cuda.h>
 #include <vector>
 #include <cstring>
@@ -40,8 +43,9 @@ namespace fvc {
 // ----------------------------------------------------------------------------------------------
 #define TC_MAX_PASS 16
 #define TC_MAX_TAPS 64
-#define TC_THREADS 640   // 20 warps = 5 warpgroups: warps 0-3 {producer, issuer, issuer, idle} shrink to 40 registers
-                         // (setmaxnreg), the 16 accumulator warps 4-19 grow to 112
+#define TC_THREADS 640   // 20 warps = 5 warpgroups: warps 0-3 {producer, issuer, issuer, idle} shrink to 64 registers
+                         // (setmaxnreg), the 16 accumulator warps 4-19 grow to 104: 128*64 + 512*104 = the CTA's launch
+                         // allocation 640*96 (a larger request blocks forever: the pool is what the launch allocated)
 #define TC_ACC_WARP0 4
 #define TC_REGS_CTRL 64
 #define TC_REGS_ACC 104
@@ -1149,11 +1153,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // MMAs per sub-tile and tile: large = bound by the tensor pipe, small = bound by the accumulator warps
     const int mma_sub = taps_total / std::max(1, L.nsub) * (merged ? (Cp == 8 ? 1 : Cp / 8) : (Cp == 8 ? 2 : Cp * 3 / 16));
     const bool acc_bound = ep.res_act.p != nullptr || mma_sub < env_int("FVC_TC_ACCBOUND", 100);
-    // Measured at 1080p (tools/layer_ab.py): pairs win everywhere except the accumulator-bound N = 128 layers
-    // (stride-2 transposed 3x3, 54 MMAs per tile), where the single issuer of an S = 1 tile is the limit;
-    // the tensor-bound N = 128 layers run as pairs with S = 2 so that both issuer warps work.
-    const int pair_mode = env_int("FVC_TC_PAIR", 1);   // 0: never, 1: per-layer rule, 2: always
-    const bool pair = N % 16 == 0 && (pair_mode == 2 || (pair_mode == 1 && !(N > 96 && acc_bound && Cp != 8)));
+    // Measured at 1080p (tools/layer_ab.py): pairs win or tie on every layer; the tensor-bound N = 128 layers run
+    // with S = 2 so that both issuer warps of the leader work (a single issuer reaches ~115 clk per pair MMA).
+    const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0;
     P.pair = pair ? 1 : 0;
     const int tile_bytes = N * pitch / (pair ? 2 : 1);   // per CTA
     int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y, npb = 2, T = 1;

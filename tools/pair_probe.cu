@@ -75,10 +75,10 @@ __device__ __forceinline__ void tma2_2d(uint32_t dst, const CUtensorMap* map, ui
 // out: [2 CTAs][128 rows][N] fp32; status[0..7]
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 k_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int N, int iters, float* out,
-       long long* status, int commit_every) {
+       long long* status, int commit_every, int rotate) {
     extern __shared__ uint8_t raw[];
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
-    const uint32_t a0 = base, b0 = base + 16 * 1024, bars = b0 + 32 * 1024, slot = bars + 64;
+    const uint32_t a0 = base, b0 = base + 64 * 1024, bars = b0 + 64 * 1024, slot = bars + 64;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cta_rank();
     const uint32_t bar_full = bars, bar_done = bars + 8, bar_ack = bars + 16, bar_rate = bars + 24;
@@ -155,7 +155,11 @@ k_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
         for (int it = 0; it < iters; ++it) {
             if (lead) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma2(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+                // rotate: rate loop variant 1 walks A over 4 x 16 KB and B over 8 x 8 KB regions (no operand re-use
+                // at short distance, as in the conv engine's weight stream); variant 0 re-uses one tile
+                const uint64_t ao = rotate ? (uint64_t)(((it & 3) * 16384) >> 4) : 0ull;
+                const uint64_t bo = rotate ? (uint64_t)(((it & 7) * 8192) >> 4) : 0ull;
+                for (int k = 0; k < 4; ++k) mma2(tmem, ad + ao + (uint64_t)(2 * k), bd + bo + (uint64_t)(2 * k), idesc, 1u);
             }
             // a multicast commit every `commit_every` groups of 4 MMAs (the engine commits once per weight stage)
             if (lead && commit_every && (it & (commit_every - 1)) == commit_every - 1) commit2(bars + 32);   // power of two
@@ -183,10 +187,11 @@ int main() {
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return 2;
     PFN_encodeTiled encode = (PFN_encodeTiled)p;
-    const int Ns[] = {32, 64, 128, 256, 64, 64, 128, 128, 128};
-    const int CEs[] = {0, 0, 0, 0, 1, 2, 1, 2, 4};
+    const int Ns[] = {32, 64, 128, 256, 64, 128, 32, 64, 128};
+    const int CEs[] = {0, 0, 0, 0, 2, 2, 2, 2, 2};
+    const int ROT[] = {0, 0, 0, 0, 0, 0, 1, 1, 1};
     for (int ci = 0; ci < 9; ++ci) {
-        const int N = Ns[ci], ce = CEs[ci];
+        const int N = Ns[ci], ce = CEs[ci], rot = ROT[ci];
         std::vector<__half> hA(256 * 64), hB((size_t)N * 64);
         for (int i = 0; i < 256 * 64; ++i) hA[i] = __float2half((float)((i * 7 + (i >> 6)) % 13 - 6));
         for (int i = 0; i < N * 64; ++i) hB[i] = __float2half((float)((i * 5 + (i >> 6) * 3) % 11 - 5));
@@ -206,10 +211,10 @@ int main() {
         CUresult r2 = encode(&mB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dB, dimsB, strA, boxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r1 || r2) { printf("encode failed %d %d\n", (int)r1, (int)r2); return 3; }
-        const int smem = 64 * 1024;
+        const int smem = 132 * 1024;
         cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         const int iters = 4000;
-        k_pair<<<2, 256, smem>>>(mA, mB, N, iters, dOut, dSt, ce);
+        k_pair<<<2, 256, smem>>>(mA, mB, N, iters, dOut, dSt, ce, rot);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("{\"N\": %d, \"error\": \"%s\"}\n", N, cudaGetErrorString(e)); return 1; }
         std::vector<float> hO(256 * (size_t)N);
@@ -226,9 +231,9 @@ int main() {
                 if (d > maxerr) maxerr = d;
                 if (d > 1e-3 && bad++ < 4) printf("  mismatch m=%d n=%d ref=%g got=%g\n", m, n, ref, hO[(size_t)m * N + n]);
             }
-        printf("{\"N\": %d, \"commit_every_4mma_groups\": %d, \"max_abs_err\": %g, \"mismatches\": %d, \"clk_per_pair_mma\": %.1f, \"status\": [%lld, %lld, %lld], "
+        printf("{\"N\": %d, \"rotate\": %d, \"commit_every_4mma_groups\": %d, \"max_abs_err\": %g, \"mismatches\": %d, \"clk_per_pair_mma\": %.1f, \"status\": [%lld, %lld, %lld], "
                "\"tmem_base\": [%lld, %lld]}\n",
-               N, ce, maxerr, bad, (double)st[0] / (4.0 * iters), st[1], st[2], st[3], st[4], st[5]);
+               N, rot, ce, maxerr, bad, (double)st[0] / (4.0 * iters), st[1], st[2], st[3], st[4], st[5]);
         cudaFree(dA); cudaFree(dB); cudaFree(dOut); cudaFree(dSt);
     }
     return 0;
