@@ -590,3 +590,23 @@ def test_lsvc_tree_equals_dvc_building_blocks(dev, state_dict):
     assert abs(float(lo[5]) - float(vo[3])) <= 1e-6 * float(vo[3]) and abs(float(lo[4]) - float(vo[2])) <= 1e-6 * float(vo[2])
     l.release()
     v.release()
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_compressai_gdn_layer(dev, inverse):
+    """layers.GDN (CompressAI names) against the published formula in torch fp32 (tolerance 2e-5 relative)."""
+    from fastvideocodec_b200.layers import GDN
+    torch.manual_seed(5)
+    g = GDN(64, inverse=inverse)
+    with torch.no_grad():
+        g.beta.add_(0.3 * torch.rand(64))
+        g.gamma.add_(0.05 * torch.rand(64, 64))
+    x = torch.randn(2, 64, 24, 40)
+    ped = 2.0 ** -36
+    beta = torch.clamp(g.beta.detach(), min=(1e-6 + ped) ** 0.5) ** 2 - ped
+    gamma = torch.clamp(g.gamma.detach(), min=ped ** 0.5) ** 2 - ped
+    norm = torch.nn.functional.conv2d(x * x, gamma.view(64, 64, 1, 1), beta)
+    want = x * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+    with torch.no_grad():
+        got = g.to(dev)(x.to(dev)).cpu()
+    assert ((got - want).abs() / (want.abs() + 1e-3)).max().item() <= 2e-5

@@ -153,6 +153,23 @@ def test_parallel_compression_matches_reference_aggregation():
     assert all(abs(a - b) < 1e-4 for a, b in zip(psnr_list, psnrs))
 
 
+def test_compressai_gdn_surface():
+    """layers.GDN keeps CompressAI's parameter / buffer names and initial values (models.py:23, 529-538)."""
+    from fastvideocodec_b200.layers import GDN
+    g = GDN(64, inverse=True)
+    assert set(g.state_dict()) == {"beta", "gamma", "beta_reparam.pedestal", "beta_reparam.lower_bound.bound",
+                                   "gamma_reparam.pedestal", "gamma_reparam.lower_bound.bound"}
+    ped = 2.0 ** -36
+    assert abs(float(g.beta[0]) - (1 + ped) ** 0.5) < 1e-7 and abs(float(g.gamma[3, 3]) - (0.1 + ped) ** 0.5) < 1e-7
+    assert abs(float(g.gamma[0, 1]) - 2.0 ** -18) < 1e-12
+    assert abs(float(g.beta_reparam.lower_bound.bound) - (1e-6 + ped) ** 0.5) < 1e-9
+    with pytest.raises(ValueError):
+        GDN(60)
+    with pytest.raises(TypeError):
+        with torch.no_grad():
+            g(torch.zeros(1, 64, 8, 8))          # CPU tensor: no CPU fallback
+
+
 class _FakeLSVC(torch.nn.Module):
     """Stands in for LSVC (one forward per GOP, models.py:384-398)."""
     r, name = 2048, 'LSVC-128'
