@@ -594,7 +594,8 @@ def test_lsvc_tree_equals_dvc_building_blocks(dev, state_dict):
 
 @pytest.mark.parametrize("inverse", [False, True])
 def test_compressai_gdn_layer(dev, inverse):
-    """layers.GDN (CompressAI names) against the published formula in torch fp32 (tolerance 2e-5 relative)."""
+    """layers.GDN (CompressAI names) against the published formula in torch fp32 (tolerance: 2e-6 absolute + 2e-6 relative,
+    i.e. fp32 rounding of the 22-bit hi/lo activation records and of the 64-term norm)."""
     from fastvideocodec_b200.layers import GDN
     torch.manual_seed(5)
     g = GDN(64, inverse=inverse)
@@ -609,4 +610,4 @@ def test_compressai_gdn_layer(dev, inverse):
     want = x * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
     with torch.no_grad():
         got = g.to(dev)(x.to(dev)).cpu()
-    assert ((got - want).abs() / (want.abs() + 1e-3)).max().item() <= 2e-5
+    assert ((got - want).abs() - 2e-6 * want.abs()).max().item() <= 2e-6
