@@ -611,3 +611,22 @@ def test_compressai_gdn_layer(dev, inverse):
     with torch.no_grad():
         got = g.to(dev)(x.to(dev)).cpu()
     assert ((got - want).abs() - 2e-6 * want.abs()).max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("case", [(64, 64, 3, 1, 0, 1, 33, 45), (128, 128, 3, 2, 1, 2, 9, 15), (8, 32, 7, 1, 0, 1, 24, 40),
+                                  (64, 32, 7, 1, 0, 1, 16, 24)])
+def test_conv2d_pair_mode_bit_identical_to_single_cta(dev, case, monkeypatch):
+    """The CTA-pair engine (tcgen05 cta_group::2, M = 256) must give bit-identical results to the single-CTA
+    engine: same accumulation groups and order, only the tile-to-SM mapping differs."""
+    from fastvideocodec_b200 import ops
+    cin, cout, k, stride, transposed, act, H, W = case
+    torch.manual_seed(11)
+    x = torch.randn(2, cin, H, W)
+    w = torch.randn((cin, cout, k, k) if transposed else (cout, cin, k, k)) / (cin * k * k) ** 0.5
+    b = torch.randn(cout)
+    f = ops.conv_transpose2d if transposed else ops.conv2d
+    monkeypatch.setenv("FVC_TC_PAIR", "1")
+    y_pair = f(x.to(dev), w.to(dev), b.to(dev), stride, act).cpu()
+    monkeypatch.setenv("FVC_TC_PAIR", "0")
+    y_single = f(x.to(dev), w.to(dev), b.to(dev), stride, act).cpu()
+    assert torch.equal(y_pair, y_single)
