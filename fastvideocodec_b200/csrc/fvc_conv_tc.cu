@@ -47,6 +47,8 @@ namespace fvc {
                          // (setmaxnreg), the 16 accumulator warps 4-19 grow to 104: 128*64 + 512*104 = the CTA's launch
                          // allocation 640*96 (a larger request blocks forever: the pool is what the launch allocated)
 #define TC_ACC_WARP0 4
+#define TC_ISSUERS 3     // warps 1..3: the issue loop costs ~100 clk per MMA and thread (register -> uniform-register
+                         // moves of the descriptors), so the sub-tiles of a tile are spread over three issuing threads
 #define TC_REGS_CTRL 64
 #define TC_REGS_ACC 104
 
@@ -293,7 +295,7 @@ __device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint32_t 
                                             uint32_t sstep) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        if (s < S && (s & 1) == s_first) {   // two issuer warps: even / odd sub-tiles
+        if (s < S && (s % TC_ISSUERS) == s_first) {   // issuer warp i owns the sub-tiles s = i (mod TC_ISSUERS)
 #pragma unroll
             for (int k = 0; k < KS; ++k) {
                 if (PAIR)
@@ -533,15 +535,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_pfull + 8 * i, 1);
-            mbar_init(bar_pempty + 8 * i, 2);   // one commit per MMA issuer warp
+            mbar_init(bar_pempty + 8 * i, TC_ISSUERS);   // one commit per MMA issuer warp
         }
         for (int i = 0; i < 4; ++i) {
-            mbar_init(bar_afull + 8 * i, 2);
+            mbar_init(bar_afull + 8 * i, TC_ISSUERS);
             mbar_init(bar_aempty + 8 * i, PAIR ? 32 : 16);  // one arrive per accumulator warp (of both CTAs)
         }
         for (int i = 0; i < P.nst; ++i) {
             mbar_init(bar_bfull + 8 * i, 1);
-            mbar_init(bar_bempty + 8 * i, 2);
+            mbar_init(bar_bempty + 8 * i, TC_ISSUERS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 else if (++spins > (1u << 25)) __trap();
             }
         }
-    } else if ((warp == 1 || warp == 2) && rank == 0) {
+    } else if (warp >= 1 && warp <= TC_ISSUERS && rank == 0) {
         // ================================ MMA issuers ============================================
         // Two warps run the same loop nest and issue the MMAs of the even / odd sub-tiles (disjoint
         // accumulator columns, so no ordering hazard): the tensor-pipe queue is shallow and one warp's
@@ -1173,7 +1175,8 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // issuers can be a whole tile ahead of an epilogue (measured at 1080p: -0.4 ms per frame).
     const int ct_cap = N > 96 ? env_int("FVC_TC_CTMAX128", (pair && !acc_bound) ? 256 : 128)
                               : ((N > 32 && L.k < 7) ? env_int("FVC_TC_CTMAX64", acc_bound ? 128 : 192)
-                                                     : env_int("FVC_TC_CTMAX", 256));
+                                                     : env_int("FVC_TC_CTMAX", N > 32 ? 192 : 256));   // 7x7 N=64: S = 3,
+                                                                                                        // one sub-tile per issuer
     const int sx_max = std::min(env_int("FVC_TC_SX", 4),
                                 std::max(1, std::min(merged ? 128 : ct_cap, ep.res_act.p ? env_int("FVC_TC_CTRES", 128) : 256) / N));
     const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), (pair ? env_int("FVC_TC_TPAIR", 512) : 256) / N));   // <= 32 KB per stage and CTA

@@ -75,7 +75,7 @@ __device__ __forceinline__ void tma2_2d(uint32_t dst, const CUtensorMap* map, ui
 // out: [2 CTAs][128 rows][N] fp32; status[0..7]
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 k_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int N, int iters, float* out,
-       long long* status, int commit_every, int rotate) {
+       long long* status, int commit_every, int rotate, int fill) {
     extern __shared__ uint8_t raw[];
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
     const uint32_t a0 = base, b0 = base + 64 * 1024, bars = b0 + 64 * 1024, slot = bars + 64;
@@ -144,6 +144,29 @@ k_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
         if (lane == 0)
             asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ack_leader) : "memory");
     }
+    // ---- optional background TMA fills (both CTAs): weight-like boxes streamed into a 4-slot ring while the
+    // rate loop runs, as the conv engine's producer does ------------------------------------------------
+    if (fill && warp == 0 && elect_one()) {
+        const uint32_t f0 = base + 129 * 1024, fb = bars + 128;
+        const uint32_t box_bytes = (uint32_t)(N / 2) * 128;
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fb + 8 * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const long long t0 = clock64();
+        long long nfill = 0;
+        uint32_t ph = 0;
+        while (clock64() - t0 < (long long)fill * 1000) {
+            for (int i = 0; i < 4; ++i) {
+                if (nfill >= 4) mbar_wait(fb + 8 * i, ph ^ 1u);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb + 8 * i), "r"(box_bytes) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                             ::"r"(f0 + (uint32_t)i * 16384u), "l"(&mapB), "r"(fb + 8 * i), "r"(0), "r"(0) : "memory");
+                ++nfill;
+            }
+            ph ^= 1u;
+        }
+        for (int i = 0; i < 4; ++i) mbar_wait(fb + 8 * i, ph ^ 1u);
+        if (rank == 0) { status[6] = nfill * box_bytes; status[7] = clock64() - t0; }
+    }
     // ---- leader: wait for both acknowledgements, then the rate loop ---------------------------------
     if (warp == 1 && rank == 0) {
         const bool ok = mbar_wait(bar_ack, 0);
@@ -187,11 +210,12 @@ int main() {
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return 2;
     PFN_encodeTiled encode = (PFN_encodeTiled)p;
-    const int Ns[] = {32, 64, 128, 256, 64, 128, 32, 64, 128};
-    const int CEs[] = {0, 0, 0, 0, 2, 2, 2, 2, 2};
-    const int ROT[] = {0, 0, 0, 0, 0, 0, 1, 1, 1};
-    for (int ci = 0; ci < 9; ++ci) {
-        const int N = Ns[ci], ce = CEs[ci], rot = ROT[ci];
+    const int Ns[] = {32, 64, 128, 256, 64, 128, 32, 64, 128, 64, 128};
+    const int CEs[] = {0, 0, 0, 0, 2, 2, 2, 2, 2, 2, 2};
+    const int ROT[] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1};
+    const int FILL[] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 3000, 3000};   // background TMA fills for ~3 M clk
+    for (int ci = 0; ci < 11; ++ci) {
+        const int N = Ns[ci], ce = CEs[ci], rot = ROT[ci], fill = FILL[ci];
         std::vector<__half> hA(256 * 64), hB((size_t)N * 64);
         for (int i = 0; i < 256 * 64; ++i) hA[i] = __float2half((float)((i * 7 + (i >> 6)) % 13 - 6));
         for (int i = 0; i < N * 64; ++i) hB[i] = __float2half((float)((i * 5 + (i >> 6) * 3) % 11 - 5));
@@ -211,10 +235,10 @@ int main() {
         CUresult r2 = encode(&mB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dB, dimsB, strA, boxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r1 || r2) { printf("encode failed %d %d\n", (int)r1, (int)r2); return 3; }
-        const int smem = 132 * 1024;
+        const int smem = 200 * 1024;
         cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         const int iters = 4000;
-        k_pair<<<2, 256, smem>>>(mA, mB, N, iters, dOut, dSt, ce, rot);
+        k_pair<<<2, 256, smem>>>(mA, mB, N, iters, dOut, dSt, ce, rot, fill);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("{\"N\": %d, \"error\": \"%s\"}\n", N, cudaGetErrorString(e)); return 1; }
         std::vector<float> hO(256 * (size_t)N);
@@ -232,8 +256,8 @@ int main() {
                 if (d > 1e-3 && bad++ < 4) printf("  mismatch m=%d n=%d ref=%g got=%g\n", m, n, ref, hO[(size_t)m * N + n]);
             }
         printf("{\"N\": %d, \"rotate\": %d, \"commit_every_4mma_groups\": %d, \"max_abs_err\": %g, \"mismatches\": %d, \"clk_per_pair_mma\": %.1f, \"status\": [%lld, %lld, %lld], "
-               "\"tmem_base\": [%lld, %lld]}\n",
-               N, rot, ce, maxerr, bad, (double)st[0] / (4.0 * iters), st[1], st[2], st[3], st[4], st[5]);
+               "\"tmem_base\": [%lld, %lld], \"fill_bytes_per_clk_per_cta\": %.1f}\n",
+               N, rot, ce, maxerr, bad, (double)st[0] / (4.0 * iters), st[1], st[2], st[3], st[4], st[5], st[7] ? (double)st[6] / (double)st[7] : 0.0);
         cudaFree(dA); cudaFree(dB); cudaFree(dOut); cudaFree(dSt);
     }
     return 0;
