@@ -21,8 +21,8 @@
 //     of a tile): two or four partial-accumulator buffers rotate, and 16 accumulator warps drain each finished
 //     partial with tcgen05.ld and add it to a running sum in registers in fp32 round-to-nearest, overlapped
 //     with the MMAs of the next group.
-//   * Warp roles (20 warps): warp 0 = TMA producer (polls the weight ring and the patch ring), warps 1-2 =
-//     MMA issuers (even / odd sub-tiles; warp 1 owns the TMEM allocation), warp 3 idle, warps 4..19 = accumulator /
+//   * Warp roles (20 warps): warp 0 = TMA producer (polls the weight ring and the patch ring), warps 1-3 =
+//     MMA issuers (sub-tile s belongs to issuer s mod 3; warp 1 owns the TMEM allocation), warps 4..19 = accumulator /
 //     epilogue warps (drain -> running sum -> bias/activation/skip/GDN -> hi/lo split -> global).  setmaxnreg
 //     gives the control warpgroup 64 and the accumulator warpgroups 104 registers.  Persistent over tiles.
 //   * CTA pairs (cta_group::2): two x-neighbouring tiles form one M = 256 MMA issued by the leader CTA; each CTA
