@@ -75,7 +75,8 @@ struct alignas(64) TcParams {
     CUtensorMap mapB;
     TcSub sub[4];
     TcPass pass[TC_MAX_PASS];
-    int32_t tap_off[TC_MAX_TAPS];  // byte offset of the tap's window inside the patch
+    int32_t tap_off[TC_MAX_TAPS + 1];  // byte offset of the tap's window inside the patch (+1: the issuers prefetch
+                                       // entry t + 1 without a bound check, see the issue loops)
     int nsub, S, SX, N, PW, PH, nst, CT;   // CT = S*N accumulator columns per partial buffer
     int Hq, Wq, tiles_x, tiles_y, B, os, Hout, Wout, Cout, nchunks;
     uint32_t patch_bytes, patch_tx, btile_bytes, stage_bytes, tmem_cols, idesc;
@@ -290,23 +291,24 @@ __device__ __forceinline__ void tc_mma2_pair(uint32_t tmem_d, uint32_t alo, uint
 // bottleneck otherwise: the MMA queue is shallow, every scalar instruction between MMAs shows up as
 // tensor-pipe idle time).
 template <int KS, bool PAIR>
-__device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t N, uint32_t alo, uint32_t ahi, uint32_t blo,
-                                            uint32_t bhi, uint32_t idesc, uint32_t acc0, int S, int s_first,
-                                            uint32_t sstep) {
+__device__ __forceinline__ void issue_subtile(uint32_t dcol, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                              uint32_t idesc, uint32_t acc0) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (s < S && (s % TC_ISSUERS) == s_first) {   // issuer warp i owns the sub-tiles s = i (mod TC_ISSUERS)
-#pragma unroll
-            for (int k = 0; k < KS; ++k) {
-                if (PAIR)
-                    tc_mma2_pair(dcol + (uint32_t)s * N, alo + (uint32_t)s * sstep + (uint32_t)(2 * k), ahi,
-                                 blo + (uint32_t)(2 * k), bhi, idesc, k == 0 ? acc0 : 1u);
-                else
-                    tc_mma2(dcol + (uint32_t)s * N, alo + (uint32_t)s * sstep + (uint32_t)(2 * k), ahi, blo + (uint32_t)(2 * k), bhi,
-                            idesc, k == 0 ? acc0 : 1u);
-            }
-        }
+    for (int k = 0; k < KS; ++k) {
+        if (PAIR) tc_mma2_pair(dcol, alo + (uint32_t)(2 * k), ahi, blo + (uint32_t)(2 * k), bhi, idesc, k == 0 ? acc0 : 1u);
+        else tc_mma2(dcol, alo + (uint32_t)(2 * k), ahi, blo + (uint32_t)(2 * k), bhi, idesc, k == 0 ? acc0 : 1u);
     }
+}
+// An issuer warp owns the sub-tiles s = issuer, issuer + TC_ISSUERS (< S): at most two.  Their accumulator-column
+// and A-address offsets (do*, so*) are computed once per kernel; `ns` (0..2) is warp-uniform, so the two `if`s are
+// uniform branches.  (Written as a loop over all S sub-tiles with an ownership test, every issuer executed the
+// descriptor arithmetic of ALL sub-tiles with predicated-off MMAs: ~340 clk per filter tap in the narrow loop.)
+template <int KS, bool PAIR>
+__device__ __forceinline__ void issue_stage(uint32_t dcol, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                            uint32_t idesc, uint32_t acc0, int ns, uint32_t so0, uint32_t do0,
+                                            uint32_t so1, uint32_t do1) {
+    if (ns > 0) issue_subtile<KS, PAIR>(dcol + do0, alo + so0, ahi, blo, bhi, idesc, acc0);
+    if (ns > 1) issue_subtile<KS, PAIR>(dcol + do1, alo + so1, ahi, blo, bhi, idesc, acc0);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -668,6 +670,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const uint32_t N = (uint32_t)P.N, nst = (uint32_t)P.nst, CT = (uint32_t)P.CT, npb = (uint32_t)P.npb;
             const uint32_t idesc = P.idesc, btile16 = P.btile_bytes >> 4, stage16 = P.stage_bytes >> 4;
             const uint32_t bst16 = lo0 + (bst0 >> 4);
+            // sub-tiles owned by this issuer: s_first and s_first + TC_ISSUERS
+            const int ns = S > s_first ? (S - 1 - s_first) / TC_ISSUERS + 1 : 0;
+            const uint32_t so0 = (uint32_t)s_first * sstep, do0 = (uint32_t)s_first * N;
+            const uint32_t so1 = (uint32_t)(s_first + TC_ISSUERS) * sstep, do1 = (uint32_t)(s_first + TC_ISSUERS) * N;
             const uint32_t nabs = (uint32_t)P.nab_log2, nabm = (1u << nabs) - 1u;
             while (cur.valid(ntiles)) {
                 const TcSub& sb = P.sub[cur.sub];
@@ -702,15 +708,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                                 blo = bst16 + st * stage16;
                             }
                             const int tpt = two ? 2 : 1;       // tiles per tap (1 with merged hi/lo rows)
-                            const int nt = min((T - slot) / tpt, t1 - t);
+                            const int nt = min((T - slot) >> (tpt - 1), t1 - t);   // tpt is 1 or 2: no division
                             if (lead) {
                                 uint32_t toff = (uint32_t)toffp[t] >> 4;
                                 for (int u = 0; u < nt; ++u) {
                                     const uint32_t alo = pa16 + toff;
-                                    toff = (uint32_t)toffp[min(t + u + 1, ntaps - 1)] >> 4;
+                                    toff = (uint32_t)toffp[t + u + 1] >> 4;   // (no min(): it would leave the uniform datapath)
                                     const uint32_t b0 = blo + (uint32_t)(tpt * u) * btile16;
-                                    issue_stage<1, PAIR>(dcol, N, alo, ahi, b0, bhi, idesc, (t + u == t0) ? 0u : 1u, S, s_first, sstep);
-                                    if (two) issue_stage<1, PAIR>(dcol, N, alo, ahi, b0 + btile16, bhi, idesc, 1u, S, s_first, sstep);
+                                    issue_stage<1, PAIR>(dcol, alo, ahi, b0, bhi, idesc, (t + u == t0) ? 0u : 1u, ns, so0, do0, so1, do1);
+                                    if (two) issue_stage<1, PAIR>(dcol, alo, ahi, b0 + btile16, bhi, idesc, 1u, ns, so0, do0, so1, do1);
                                 }
                             }
                             t += nt;
@@ -746,7 +752,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         gopen = true;
                     }
                     const uint32_t alo = pa16 + toff;
-                    toff = (uint32_t)toffp[min(t + 1, ntaps - 1)] >> 4;   // prefetched for the next tap
+                    toff = (uint32_t)toffp[t + 1] >> 4;   // prefetched for the next tap (table has one spare entry)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         if (j == 1 && !two) break;
@@ -758,8 +764,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         }
                         if (lead) {
                             // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
-                            if (j == 1 && short2) issue_stage<2, PAIR>(gdcol, N, alo, ahi, blo, bhi, idesc, gacc0, S, s_first, sstep);
-                            else issue_stage<4, PAIR>(gdcol, N, alo, ahi, blo, bhi, idesc, gacc0, S, s_first, sstep);
+                            if (j == 1 && short2) issue_stage<2, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
+                            else issue_stage<4, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
                         }
                         gacc0 = 1u;
                         blo += btile16;
