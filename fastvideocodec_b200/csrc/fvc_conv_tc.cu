@@ -1160,7 +1160,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     for (auto& g : groups) taps_total += (int)g.taps.size();
     // MMAs per sub-tile and tile: large = bound by the tensor pipe, small = bound by the accumulator warps
     const int mma_sub = taps_total / std::max(1, L.nsub) * (merged ? (Cp == 8 ? 1 : Cp / 8) : (Cp == 8 ? 2 : Cp * 3 / 16));
-    const bool acc_bound = ep.res_act.p != nullptr || mma_sub < env_int("FVC_TC_ACCBOUND", 100);
+    (void)mma_sub;
     // Measured at 1080p (tools/layer_ab.py): pairs win or tie on every layer; the tensor-bound N = 128 layers run
     // with S = 2 so that both issuer warps of the leader work (a single issuer reaches ~115 clk per pair MMA).
     const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0;
@@ -1179,8 +1179,10 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // Layers with few MMAs per output (transposed / 1x1 convolutions) and residual epilogues are bound by the
     // accumulator warps, not by the MMAs: they run best with CT = 128 and FOUR partial buffers, so that the MMA
     // issuers can be a whole tile ahead of an epilogue (measured at 1080p: -0.4 ms per frame).
-    const int ct_cap = N > 96 ? env_int("FVC_TC_CTMAX128", (pair && !acc_bound) ? 256 : 128)
-                              : ((N > 32 && L.k < 7) ? env_int("FVC_TC_CTMAX64", acc_bound ? 128 : 192)
+    // (with one issuer thread per sub-tile and the lean issue loop, CT = 128 + four partial buffers also wins for the
+    // tensor-bound N = 128 and N = 64 3x3 layers: 11.45 -> 11.3 ms per frame)
+    const int ct_cap = N > 96 ? env_int("FVC_TC_CTMAX128", 128)
+                              : ((N > 32 && L.k < 7) ? env_int("FVC_TC_CTMAX64", 128)
                                                      : env_int("FVC_TC_CTMAX", N > 32 ? 192 : 256));   // 7x7 N=64: S = 3,
                                                                                                         // one sub-tile per issuer
     const int sx_max = std::min(env_int("FVC_TC_SX", 4),
