@@ -1154,33 +1154,20 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     const int pitch = Cp == 8 ? 32 : 128;
     P.pitch = pitch;
     // CTA pairs (cta_group::2): two x-neighbouring tiles are one M = 256 MMA; each CTA stages half of every weight
-    // tile, which halves the weight traffic through shared memory and the B-operand reads (the tensor pipe is
-    // bound by shared-memory bandwidth for N < 128 and by the weight re-staging for N = 128, S = 1)
-    int taps_total = 0;
-    for (auto& g : groups) taps_total += (int)g.taps.size();
-    // MMAs per sub-tile and tile: large = bound by the tensor pipe, small = bound by the accumulator warps
-    const int mma_sub = taps_total / std::max(1, L.nsub) * (merged ? (Cp == 8 ? 1 : Cp / 8) : (Cp == 8 ? 2 : Cp * 3 / 16));
-    (void)mma_sub;
-    // Measured at 1080p (tools/layer_ab.py): pairs win or tie on every layer; the tensor-bound N = 128 layers run
-    // with S = 2 so that both issuer warps of the leader work (a single issuer reaches ~115 clk per pair MMA).
+    // tile, which halves the weight bytes staged through shared memory and the B-operand reads per SM.
+    // Measured at 1080p (tools/layer_ab.py): pairs win or tie on every layer.
     const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0;
     P.pair = pair ? 1 : 0;
     const int tile_bytes = N * pitch / (pair ? 2 : 1);   // per CTA
     int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y, npb = 2, T = 1;
-    // S*N accumulator columns per partial buffer, CT/32 in {1,2,3,4,6,8} (template instantiations),
-    // CT <= 256 (two partial buffers in 512 TMEM columns, <= 64 running-sum registers per thread).
-    // Prefer the largest S (weights are re-read once per tile).  Two patch buffers when that still
-    // leaves room for a deep weight ring; otherwise one (big-halo 7x7 layers: the exposed patch load is
-    // a few % of a pass, a starved weight ring costs far more).
-    // (residual epilogues keep CT <= 192: 48 running sums leave registers for the prefetched skip data)
-    // measured per layer class at 1080p (chain 48): N = 128 runs best with S = 1 (32 running sums, no spills:
-    // the 64-sum variant stalls on spill reloads queued behind its own global stores), N = 64 3x3/5x5 layers
-    // with S = 3, the 7x7 N = 64 layer (SpyNet conv2) with S = 4
-    // Layers with few MMAs per output (transposed / 1x1 convolutions) and residual epilogues are bound by the
-    // accumulator warps, not by the MMAs: they run best with CT = 128 and FOUR partial buffers, so that the MMA
-    // issuers can be a whole tile ahead of an epilogue (measured at 1080p: -0.4 ms per frame).
-    // (with one issuer thread per sub-tile and the lean issue loop, CT = 128 + four partial buffers also wins for the
-    // tensor-bound N = 128 and N = 64 3x3 layers: 11.45 -> 11.3 ms per frame)
+    // S sub-tiles of 128 pixels share every weight stage; CT = S*N accumulator columns per partial buffer,
+    // CT/32 in {1,2,3,4,6,8} (template instantiations), CT <= 256.  Two patch buffers when that still leaves room
+    // for a deep weight ring; otherwise one (big-halo 7x7 layers: the exposed patch load is a few % of a pass, a
+    // starved weight ring costs far more).
+    // Measured per layer class at 1080p (chain 48, tools/layer_ab.py): CT = 128 with FOUR partial buffers wins for
+    // every N >= 64 class (N = 128: S = 1, N = 64: S = 2): the MMA issuers can then be a whole tile ahead of an
+    // epilogue, and each issuer warp owns exactly one sub-tile.  The 7x7 N = 64 layer (SpyNet conv2) keeps S = 3
+    // (one sub-tile per issuer, two partial buffers), the N <= 32 layers S = 4.
     const int ct_cap = N > 96 ? env_int("FVC_TC_CTMAX128", 128)
                               : ((N > 32 && L.k < 7) ? env_int("FVC_TC_CTMAX64", 128)
                                                      : env_int("FVC_TC_CTMAX", N > 32 ? 192 : 256));   // 7x7 N=64: S = 3,
