@@ -23,7 +23,7 @@ def main():
     out = {}
     x = synthetic_gop(64, 64, gop=5, gop_id=4)[:, 0]          # I-frame + 4 P-frames
     out["x"] = x.numpy()
-    for tag, name in (("tree", "LSVC-128"), ("chain", "LSVC-L-128")):
+    for tag, name in (("tree", "LSVC-128"), ("chain", "LSVC-L-128"), ("onehop", "LSVC-O-128")):
         with ref_shim._cwd(ref_shim.REF_ROOT):
             m = refmodels.LSVC(name, use_split=False)
         m.load_state_dict(sd, strict=True)

@@ -538,7 +538,7 @@ def test_entropy_models_meanscale_forward(dev):
         assert abs(bits - want_bits) <= 0.005 * want_bits
 
 
-@pytest.mark.parametrize("tag,name", [("tree", "LSVC-128"), ("chain", "LSVC-L-128")])
+@pytest.mark.parametrize("tag,name", [("tree", "LSVC-128"), ("chain", "LSVC-L-128"), ("onehop", "LSVC-O-128")])
 def test_lsvc_forward_matches_reference_golden(dev, state_dict, tag, name):
     """SURVEY 8f N1 — LSVC batched / tree GOP forward (models.py:1344-1411) through fvc_lsvc_mv_forward /
     fvc_lsvc_mc_res_forward against the unmodified reference's outputs (tests/golden/lsvc_64.npz)."""

@@ -103,8 +103,8 @@ def test_oracle_lsvc_matches_reference(state_dict):
     from fastvideocodec_b200.lsvc import graph_from_batch, refidx_from_graph
     gold = load_golden("lsvc_64.npz")
     x = gold["x"]
-    for tag, linear in (("tree", False), ("chain", True)):
-        g, layers, parents = graph_from_batch(4, isLinear=linear)
+    for tag, linear, onehop in (("tree", False, False), ("chain", True, False), ("onehop", False, True)):
+        g, layers, parents = graph_from_batch(4, isLinear=linear, isOnehop=onehop)
         out = O.lsvc_forward(state_dict, x, layers, parents, refidx_from_graph(g, 4))
         for i, n in enumerate(["com", "mc", "warped"]):
             assert (out[i] - gold["%s_%s" % (tag, n)]).abs().max().item() <= 2e-5, (tag, n)
