@@ -75,7 +75,7 @@ __device__ __forceinline__ void tma2_2d(uint32_t dst, const CUtensorMap* map, ui
 // out: [2 CTAs][128 rows][N] fp32; status[0..7]
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 k_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int N, int iters, float* out,
-       long long* status, int commit_every, int rotate, int fill) {
+       long long* status, int commit_every, int rotate, int fill, int drain) {
     extern __shared__ uint8_t raw[];
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
     const uint32_t a0 = base, b0 = base + 64 * 1024, bars = b0 + 64 * 1024, slot = bars + 64;
@@ -143,6 +143,28 @@ k_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
         __syncwarp();
         if (lane == 0)
             asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ack_leader) : "memory");
+        // optional background TMEM drains (both CTAs, 4 warps each): tcgen05.ld of 64 columns the MMAs do not write,
+        // for ~drain * 1000 clk, as the conv engine's accumulator warps do while the next group is issued.
+        // (measured: ~179 B/clk per CTA of drains, with or without TMA fills, leave the pair MMA at 43 / 64 clk)
+        if (drain && N <= 128) {
+            const long long t0 = clock64();
+            long long nld = 0;
+            float sink = 0.f;
+            while (clock64() - t0 < (long long)drain * 1000) {
+                for (int c = 0; c < 64; c += 8) {
+                    uint32_t v[8];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                                 : "r"(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c)
+                                 : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    sink += __uint_as_float(v[0]);
+                }
+                nld += 8;
+            }
+            if (sink == 123.456f) status[3] = 2;
+            if (warp == 4 && lane == 0 && rank == 0) { status[8] = nld * 4 /*warps*/ * 32 * 8 * 4; status[9] = clock64() - t0; }
+        }
     }
     // ---- optional background TMA fills (both CTAs): weight-like boxes streamed into a 4-slot ring while the
     // rate loop runs, as the conv engine's producer does ------------------------------------------------
@@ -210,12 +232,13 @@ int main() {
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return 2;
     PFN_encodeTiled encode = (PFN_encodeTiled)p;
-    const int Ns[] = {32, 64, 128, 256, 64, 128, 32, 64, 128, 64, 128};
-    const int CEs[] = {0, 0, 0, 0, 2, 2, 2, 2, 2, 2, 2};
-    const int ROT[] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1};
-    const int FILL[] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 3000, 3000};   // background TMA fills for ~3 M clk
-    for (int ci = 0; ci < 11; ++ci) {
-        const int N = Ns[ci], ce = CEs[ci], rot = ROT[ci], fill = FILL[ci];
+    const int Ns[] = {32, 64, 128, 256, 64, 128, 32, 64, 128, 64, 128, 64, 128, 64, 128};
+    const int CEs[] = {0, 0, 0, 0, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2};
+    const int ROT[] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+    const int FILL[] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 3000, 3000, 0, 0, 3000, 3000};   // background TMA fills for ~3 M clk
+    const int DRAIN[] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3000, 3000, 3000, 3000};  // background tcgen05.ld drains
+    for (int ci = 0; ci < 15; ++ci) {
+        const int N = Ns[ci], ce = CEs[ci], rot = ROT[ci], fill = FILL[ci], drain = DRAIN[ci];
         std::vector<__half> hA(256 * 64), hB((size_t)N * 64);
         for (int i = 0; i < 256 * 64; ++i) hA[i] = __float2half((float)((i * 7 + (i >> 6)) % 13 - 6));
         for (int i = 0; i < N * 64; ++i) hB[i] = __float2half((float)((i * 5 + (i >> 6) * 3) % 11 - 5));
@@ -223,10 +246,10 @@ int main() {
         float* dOut;
         long long* dSt;
         cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2);
-        cudaMalloc(&dOut, 256 * (size_t)N * 4); cudaMalloc(&dSt, 64);
+        cudaMalloc(&dOut, 256 * (size_t)N * 4); cudaMalloc(&dSt, 128);
         cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
         cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
-        cudaMemset(dOut, 0, 256 * (size_t)N * 4); cudaMemset(dSt, 0, 64);
+        cudaMemset(dOut, 0, 256 * (size_t)N * 4); cudaMemset(dSt, 0, 128);
         CUtensorMap mA, mB;
         cuuint64_t dimsA[2] = {64, 256}, strA[1] = {128}, dimsB[2] = {64, (cuuint64_t)N};
         cuuint32_t boxA[2] = {64, 128}, boxB[2] = {64, (cuuint32_t)(N / 2)}, es[2] = {1, 1};
@@ -238,13 +261,13 @@ int main() {
         const int smem = 200 * 1024;
         cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         const int iters = 4000;
-        k_pair<<<2, 256, smem>>>(mA, mB, N, iters, dOut, dSt, ce, rot, fill);
+        k_pair<<<2, 256, smem>>>(mA, mB, N, iters, dOut, dSt, ce, rot, fill, drain);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("{\"N\": %d, \"error\": \"%s\"}\n", N, cudaGetErrorString(e)); return 1; }
         std::vector<float> hO(256 * (size_t)N);
-        long long st[8];
+        long long st[16];
         cudaMemcpy(hO.data(), dOut, hO.size() * 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(st, dSt, 64, cudaMemcpyDeviceToHost);
+        cudaMemcpy(st, dSt, 128, cudaMemcpyDeviceToHost);
         double maxerr = 0;
         int bad = 0;
         for (int m = 0; m < 256; ++m)
@@ -256,8 +279,8 @@ int main() {
                 if (d > 1e-3 && bad++ < 4) printf("  mismatch m=%d n=%d ref=%g got=%g\n", m, n, ref, hO[(size_t)m * N + n]);
             }
         printf("{\"N\": %d, \"rotate\": %d, \"commit_every_4mma_groups\": %d, \"max_abs_err\": %g, \"mismatches\": %d, \"clk_per_pair_mma\": %.1f, \"status\": [%lld, %lld, %lld], "
-               "\"tmem_base\": [%lld, %lld], \"fill_bytes_per_clk_per_cta\": %.1f}\n",
-               N, rot, ce, maxerr, bad, (double)st[0] / (4.0 * iters), st[1], st[2], st[3], st[4], st[5], st[7] ? (double)st[6] / (double)st[7] : 0.0);
+               "\"tmem_base\": [%lld, %lld], \"fill_bytes_per_clk_per_cta\": %.1f, \"drain_bytes_per_clk_per_cta\": %.1f}\n",
+               N, rot, ce, maxerr, bad, (double)st[0] / (4.0 * iters), st[1], st[2], st[3], st[4], st[5], st[7] ? (double)st[6] / (double)st[7] : 0.0, st[9] ? (double)st[8] / (double)st[9] : 0.0);
         cudaFree(dA); cudaFree(dB); cudaFree(dOut); cudaFree(dSt);
     }
     return 0;
