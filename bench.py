@@ -26,9 +26,42 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-H, W, GOP = 1088, 1920, 10
+H, W, GOP, BATCH = 1088, 1920, 10, 1
 FLOP_PER_PX = 1397809 + 5376          # conv 2*MAC + GDN 1x1, per pixel per P-frame
 METRIC = "1080p P-frames/sec (whole box)"
+# --config: the headline workload (configs[1]/[2]) or one of the other BASELINE.json configs (lines for profiles/)
+CONFIGS = {"hd": (1088, 1920, 1, "DVC P-frame forward 1088x1920, GOP=10 (9 P-frames/step/rank), B=1, configs[1]; "
+                                 "GOPs sharded by rank (configs[2])"),
+           "4k": (2176, 3840, 1, "DVC P-frame forward 3840x2160 padded to 2176 rows, GOP=10, B=1, configs[3]"),
+           "multiview": (768, 1280, 8, "DVC P-frame forward, 8 camera views of 1280x720 padded to 768 rows folded "
+                                       "into the batch (B=8), GOP=10, configs[4]")}
+
+
+def hbm_kernel_bytes(tag, h, w, b):
+    """Algorithmic HBM bytes of one launch of a memory-bound kernel, fp32 tensors as the reference
+    holds them + the engine's 4 B/channel hi|lo records; `tag` is the profile name '@kernel[:variant]'."""
+    px = float(h * w * b)
+    name, _, var = tag[1:].partition(":")
+    if name == "k_mc_prep":                       # ref gather 12 + mv 8 in; warpframe 12 + [warp,ref] record 32 out
+        return 64 * px
+    if name == "k_mc_finish":                     # warpnet res 12 + warpframe 12 + cur 12 in; prediction 12 + record 32 out
+        return 80 * px
+    if name == "k_spynet_prep":                   # im1 12 + im2 gather 12 + coarse flow 2 in; record 32 + flow_up 8 out
+        lvl = int(var[1:])
+        return 66 * px / 4 ** (3 - lvl)
+    if name == "k_recon_losses":                  # cur, pred, warp 36 + res 12 in; clipped 12 out
+        return 60 * px
+    if name == "k_upadd_act":                     # 64-ch records (256 B): low/4 + skip in; x and relu(x) out
+        return (256 / 4 + 256 + 512) * px / (1 if var == "full" else 4)
+    if name == "k_pool_act":                      # 4 records in, x and relu(x) out, per output pixel
+        return (4 * 256 + 512) * px / (4 if var == "full" else 16)
+    if name == "k_quant_bits_factorized":         # 8 B/element (SURVEY 8d)
+        return 8 * (128 * px / 256 if var == "mv" else 64 * px / 4096)
+    if name == "k_quant_bits_laplace":            # 12 B/element
+        return 12 * 96 * px / 256
+    if name == "k_avg_pool2_planar":
+        return None
+    return None
 
 
 def _peaks():
@@ -102,7 +135,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "P-frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DVC P-frame forward %dx%d, GOP=%d, B=1 (configs[1])" % (H, W, GOP)},
+            "config": {"workload": CONFIGS[args.config][3]},
             "cpu_baseline": {"value": v, "unit": "P-frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "P-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -130,6 +163,65 @@ def cpu_baseline_sample():
             "sample": "%d P-frame(s) at %dx%d, fp32, oracle port of the reference on torch CPU" % (n, H, W)}
 
 
+def gpu_baseline_sample(dev, n_frames=3):
+    """Like-for-like GPU baseline (SURVEY 8d last row): the reference's PyTorch algorithm (the oracle port: F.conv2d
+    -> cuDNN, grid_sample-equivalent gathers, ...) on the SAME B200 in fp32, once with TF32 disabled (the
+    parity-equivalent baseline) and once with PyTorch's default cuDNN TF32 (what a user of the reference gets).
+    Outside every timed region of our arm; a reported baseline like cpu_baseline, never on the product path."""
+    import torch
+    from fastvideocodec_b200.synthetic import init_state_dict, synthetic_gop
+    from oracle import dvc_oracle
+    sd = {k: v.to(dev) for k, v in init_state_dict(0).items()}
+    frames = synthetic_gop(H, W, gop=2, gop_id=0, batch=BATCH).to(dev)
+    out = {"kind": "port", "what": "oracle port of DVC/net.py:70-220 on torch CUDA (cuDNN) fp32, %d P-frames at "
+                                   "%dx%d B=%d after 1 warm-up" % (n_frames, H, W, BATCH), "unit": "P-frames/s"}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        with torch.no_grad(), torch.device(dev):
+            for key, tf32 in (("fp32_tf32_off", False), ("fp32_tf32_on", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                dvc_oracle.pframe_forward(sd, frames[1], frames[0])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n_frames):
+                    dvc_oracle.pframe_forward(sd, frames[1], frames[0])
+                e1.record()
+                torch.cuda.synchronize()
+                out[key] = BATCH * n_frames / (e0.elapsed_time(e1) * 1e-3)
+    except Exception as ex:  # the baseline must never take the bench down
+        out["error"] = "%s: %s" % (type(ex).__name__, str(ex)[:200])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+    return out
+
+
+def parity_against_reference_golden(rows_first_gop):
+    """First timed GOP (rank 0: gop_id 0) against the UNMODIFIED reference's own closed-loop rows for the same GOP
+    (tests/golden/hd_gop10.npz, oracle/gen_golden_r2.py): north-star gates bpp 0.5 %, PSNR 0.02 dB on the GOP means."""
+    import math
+    import numpy as np
+    p = os.path.join(ROOT, "tests", "golden", "hd_gop10.npz")
+    if not os.path.exists(p):
+        return {"ok": None, "why": "tests/golden/hd_gop10.npz missing"}
+    with np.load(p) as z:
+        ref = z["rows"]                         # [9, 8]: mse warploss interloss bpp_f bpp_z bpp_mv bpp psnr
+    got = rows_first_gop.double().numpy()       # [9, 7]
+    bpp, bpp_ref = got[:, 6].mean(), ref[:, 6].mean()
+    psnr = float(np.mean([10.0 * math.log10(1.0 / m) for m in got[:, 0]]))
+    psnr_ref = float(ref[:, 7].mean())
+    frame_bpp_rel = float(np.max(np.abs(got[:, 6] - ref[:, 6]) / ref[:, 6]))
+    frame_psnr = float(np.max(np.abs(np.array([10.0 * math.log10(1.0 / m) for m in got[:, 0]]) - ref[:, 7])))
+    bpp_rel = float(abs(bpp - bpp_ref) / bpp_ref)
+    psnr_db = abs(psnr - psnr_ref)
+    return {"against": "unmodified reference, closed-loop GOP-10 rows (tests/golden/hd_gop10.npz)",
+            "bpp": float(bpp), "bpp_ref": float(bpp_ref), "bpp_rel": bpp_rel, "psnr": psnr, "psnr_ref": psnr_ref,
+            "psnr_db": psnr_db, "max_frame_bpp_rel": frame_bpp_rel, "max_frame_psnr_db": frame_psnr,
+            "gates": {"bpp_rel": 0.005, "psnr_db": 0.02}, "ok": bool(bpp_rel <= 0.005 and psnr_db <= 0.02)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -146,11 +238,11 @@ def run_ours(args, rank, world, local_rank):
 
     # each rank codes its own GOPs (GOP g seeded 1234+g; rank r owns g = r mod world): weak scaling
     n_local = 2
-    host_gops = [synthetic_gop(H, W, gop=GOP, gop_id=rank + i * world).contiguous().pin_memory()
-                 for i in range(n_local)]                      # [G,1,3,H,W] each
+    host_gops = [synthetic_gop(H, W, gop=GOP, gop_id=rank + i * world, batch=BATCH).contiguous().pin_memory()
+                 for i in range(n_local)]                      # [G,B,3,H,W] each
     dev_gops = [g.to(dev) for g in host_gops]
-    ctx = model._context(1, H, W, dev)
-    rec = torch.empty((2, 1, 3, H, W), device=dev)
+    ctx = model._context(BATCH, H, W, dev)
+    rec = torch.empty((2, BATCH, 3, H, W), device=dev)
     scal = torch.empty((args.steps + args.warmup, GOP - 1, 7), device=dev)
 
     def gop_resident(step):
@@ -185,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t)
-    frames_total = world * args.steps * (GOP - 1)
+    frames_total = world * args.steps * (GOP - 1) * BATCH
     value = frames_total / (ms_max * 1e-3)
 
     # ---- end to end: host frames -> metrics on host -----------------------------------------
@@ -204,14 +296,14 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = frames_total / (float(t2) * 1e-3)
-    h2d = GOP * 3 * H * W * 4
+    h2d = GOP * BATCH * 3 * H * W * 4
     d2h = (GOP - 1) * 7 * 4
 
     # ---- statistics: the one collective of the path ---------------------------------------------
     stats = summarize(reduce_stats(stats_vector(torch.cat(rows, 0))))
 
     # ---- roofline of the dominant kernels (convolution engine), rank 0 only ---------------------
-    roof, cpu = None, None
+    roof, cpu, gpu_base, parity = None, None, None, None
     if rank == 0:
         tf_peak, hbm_peak, how = _peaks()
         os.environ["FVC_PROFILE"] = "1"
@@ -219,26 +311,56 @@ def run_ours(args, rank, world, local_rank):
         pm.load_state_dict(init_state_dict(0))
         pm = pm.to(dev).eval()
         fr = dev_gops[0]
-        conv_s = []
+        conv_s, texts = [], []
         with torch.no_grad():
-            for i in range(1, 5):
+            for i in range(1, 6):
                 pm(fr[i], fr[i - 1])
                 conv_s.append(lib().fvc_ctx_last_conv_seconds(pm._last_ctx.handle))
+                texts.append(lib().fvc_ctx_profile_text(pm._last_ctx.handle).decode())
         os.environ["FVC_PROFILE"] = "0"
         conv_t = sorted(conv_s[1:])[len(conv_s[1:]) // 2]
-        flops = FLOP_PER_PX * H * W
+        flops = FLOP_PER_PX * H * W * BATCH
         ach = flops / conv_t / 1e12
-        traffic = None   # DRAM bytes of the convolution launches of one frame, from the committed ncu pass
+        # memory-bound kernels: achieved HBM GB/s per launch from the same CUDA-event pass (median of 4 frames)
+        per = {}
+        for t in texts[1:]:
+            seen = {}
+            for ln in t.splitlines():
+                name, ms = ln.rsplit(" ", 1)
+                if name.startswith("@"):
+                    seen.setdefault(name, []).append(float(ms))
+            for name, v in seen.items():
+                per.setdefault(name, []).append(sum(v) / len(v))
+        other_ms = sum(float(ln.rsplit(" ", 1)[1]) for ln in texts[-1].splitlines() if ln.startswith("@"))
+        hbm_kernels = {}
+        for name, v in sorted(per.items()):
+            ms = sorted(v)[len(v) // 2]
+            nbytes = hbm_kernel_bytes(name, H, W, BATCH)
+            if nbytes:
+                gbs = nbytes / (ms * 1e-3) / 1e9
+                hbm_kernels[name[1:]] = {"ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)}
+        traffic, traffic_src = None, None   # DRAM bytes of the convolution launches of one frame
         tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and (H, W, BATCH) == (1088, 1920, 1):
             with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_frame")
+                tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_frame")
+            traffic_src = "profiles/conv_traffic.json (ncu dram__bytes_read+write over the conv launches of one frame; " \
+                          "%s); not measured in this run" % tj.get("source", "committed ncu pass")
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": traffic, "kernel": "convolution engine (%s), all conv launches of one P-frame" % impl_name,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "convolution engine (%s), all conv launches of one P-frame" % impl_name,
                 "algorithmic_flop_per_frame": flops, "conv_seconds_per_frame": conv_t,
-                "conv_share_of_frame": conv_t / (ms_max * 1e-3 / (args.steps * (GOP - 1))), "peak_source": how}
+                "conv_share_of_frame": conv_t / (ms_max * 1e-3 / (args.steps * (GOP - 1))), "peak_source": how,
+                "hbm_kernels": hbm_kernels, "hbm_peak_gbs": hbm_peak,
+                "non_conv_ms_per_frame_serialised": round(other_ms, 4)}
         pm.release()
+        if (H, W, BATCH) == (1088, 1920, 1):
+            parity = parity_against_reference_golden(rows[0])
         if world == 1:
+            model.release()
+            torch.cuda.empty_cache()
+            gpu_base = gpu_baseline_sample(dev)
             cpu = cpu_baseline_sample()
 
     if rank == 0:
@@ -246,15 +368,16 @@ def run_ours(args, rank, world, local_rank):
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16 hi/lo pairs x3 MMAs (fp32 accumulate)" if impl_name == "tc" else "f32",
                 "data": "synthetic",
-                "config": {"workload": "DVC P-frame forward %dx%d, GOP=%d (9 P-frames/step/rank), B=1, configs[1]; "
-                                       "GOPs sharded by rank (configs[2])" % (H, W, GOP),
+                "config": {"workload": CONFIGS[args.config][3],
                            "engine": impl_name, "l2": "per-frame working set (GBs of activations) exceeds the 126 MB L2",
                            "parallelism": "gop-sharded x%d, no data-path collective" % world},
                 "clocks": clk.summary(),
-                "e2e": {"value": e2e_value, "unit": "P-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": "P-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "d2h_what": "the 7 scalars per P-frame only (eval.py reads metrics, not frames; "
+                                    "models.py:376-383)"},
                 "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu,
-                "parity_stats": stats}
+                "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_base,
+                "parity": parity, "parity_stats": stats}
         print(json.dumps(line), flush=True)
     model.release()
 
@@ -265,7 +388,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="hd", choices=sorted(CONFIGS))
     args = ap.parse_args()
+    global H, W, BATCH
+    H, W, BATCH = CONFIGS[args.config][:3]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

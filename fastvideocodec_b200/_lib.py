@@ -45,6 +45,9 @@ _SIGNATURES = {
     "fvc_gop_forward_host": (_i, [C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, _s]),
     "fvc_lsvc_mv_forward": (_i, [C.c_void_p, _f, _f, _f, _f, _s]),
     "fvc_lsvc_mc_res_forward": (_i, [C.c_void_p, _f, _f, _f, _f, _f, _f, _f, _s]),
+    "fvc_decode_from_latents": (_i, [C.c_void_p, _f, _f, _f, _f, _s]),
+    "fvc_ctx_force_latents": (_i, [C.c_void_p, _f, _f, _f]),
+    "fvc_ctx_saturation_count": (_l, [C.c_void_p, _i, _s]),
     "fvc_ctx_launch_count": (_l, [C.c_void_p]),
     "fvc_ctx_last_conv_seconds": (C.c_double, [C.c_void_p]),
     "fvc_ctx_profile_text": (C.c_char_p, [C.c_void_p]),

@@ -178,6 +178,8 @@ struct Epilogue {
     ActT out_act_sq;          // optional ACT output holding sq_scale * y^2 (input of the GDN 1x1 convolution)
     float sq_scale;
     int res_mode;             // how res_act enters: 0: y += r;  1: y = r / sqrt(y) (GDN);  2: y = r * sqrt(y) (IGDN)
+    unsigned int* sat_count;  // optional: incremented once per epilogue tile that stored an ACT value with |hi| >= 65504
+                              // (the fp16 pair range; such values are clamped by cvt.satfinite and the result is wrong)
 };
 
 }  // namespace fvc

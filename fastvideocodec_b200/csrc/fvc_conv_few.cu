@@ -7,6 +7,8 @@
 // Block = 128 threads = 32 (x) by 4; output tile 32 x 16; a thread owns 4 vertically adjacent pixels of one
 // column, so neighbouring threads read neighbouring float4s (conflict-free) and each input value loaded from
 // shared memory is used for up to 4 x CO x 4 FMAs.  Input channels are processed in chunks of 16.
+#include <atomic>
+
 #include "fvc_kernels.cuh"
 #include "fvc_epilogue.cuh"
 
@@ -165,10 +167,13 @@ template <int K, int CO>
 static int few_launch(const FewParams& P, cudaStream_t s) {
     constexpr int PW = 32 + K - 1, PH = 16 + K - 1;
     const size_t smem = ((size_t)PH * 4 * PW + (size_t)K * K * 4 * CO) * sizeof(float4);
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<unsigned long long> attr{0};   // per-device attribute: one bit per device ordinal
+    int dev = 0;
+    FVC_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr.load(std::memory_order_acquire) & bit)) {
         FVC_CUDA(cudaFuncSetAttribute(k_conv_few<K, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        attr.fetch_or(bit, std::memory_order_release);
     }
     dim3 grid(cdiv(P.W, 32), cdiv(P.H, 16), P.B);
     k_conv_few<K, CO><<<grid, 128, smem, s>>>(P);

@@ -29,6 +29,7 @@
 //     stages its own patch and half of every weight tile; commits are multicast to both CTAs.
 //   * Up to four partial-accumulator buffers (CT <= 128) let the issuers run a whole tile ahead of an epilogue.
 #include <cuda.h>
+#include <atomic>
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -356,6 +357,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
     e16 *rec_out = nullptr, *rec_relu = nullptr, *rec_sq = nullptr;
     const e16* rec_res = nullptr;
     size_t pixC = 0;   // pixel index * Cout (fp32 NHWC tensors)
+    uint32_t satm = 0; // running max |hi| of the ACT values this thread stores (range check, see ep_sat_track)
     auto enter_pixel = [&](int s) {
         cur_s = s;
         const int qx = (tx * P.SX + s) * 8 + tw;
@@ -491,20 +493,21 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
             }
             const int c0 = cc[j0];
             if (PAIR == 2) {
-                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store16_packed(rec_out, ep.out_act.Cp, c0, v, false);
-                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store16_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true);
+                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store16_packed(rec_out, ep.out_act.Cp, c0, v, false, satm);
+                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store16_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm);
             } else {
-                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false);
-                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true);
+                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false, satm);
+                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm);
             }
             if (ep.out_act_sq.p && c0 < ep.out_act_sq.Cp) {   // squares for the following (I)GDN
 #pragma unroll
                 for (int q = 0; q < PAIR * 8; ++q) v[q] = v[q] * v[q] * ep.sq_scale;
-                if (PAIR == 2) ep_store16_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false);
-                else ep_store8_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false);
+                if (PAIR == 2) ep_store16_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false, satm);
+                else ep_store8_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false, satm);
             }
         }
     }
+    if (ep.sat_count && ep_sat_hit(satm)) atomicAdd(ep.sat_count, 1u);
 }
 
 // Warp roles: 0 = TMA producer (weight stream + patches), 1, 2 = MMA issuers (warp 1 owns the TMEM
@@ -1422,10 +1425,14 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
 
 template <int NCH, bool RES, bool PAIR>
 static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device (and this function may run on several host threads): one bit per device ordinal
+    static std::atomic<unsigned long long> attr_set{0};
+    int dev = 0;
+    FVC_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
         FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_set = true;
+        attr_set.fetch_or(bit, std::memory_order_release);
     }
     if (PAIR) {
         cudaLaunchConfig_t cfg = {};

@@ -48,7 +48,20 @@ __device__ __forceinline__ uint32_t ep_pack2(float a, float b) {
 #endif
     return r;
 }
-__device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const float* v, bool relu) {
+// Range tracking of the stored hi halves: satm holds the running max |hi| of both 16-bit lanes (one HMNMX2 per two
+// elements).  A lane that reaches 0x7BFF (65504) was clamped by cvt.satfinite: the caller reports it (sat_count).
+__device__ __forceinline__ uint32_t ep_sat_track(uint32_t satm, uint32_t hi) {
+#if FVC_SPLIT_FP16
+    __half2 m = __hmax2(*reinterpret_cast<__half2*>(&satm), __habs2(*reinterpret_cast<__half2*>(&hi)));
+    return *reinterpret_cast<uint32_t*>(&m);
+#else
+    return satm;
+#endif
+}
+__device__ __forceinline__ bool ep_sat_hit(uint32_t satm) {
+    return (satm & 0xffffu) >= 0x7bffu || (satm >> 16) >= 0x7bffu;
+}
+__device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const float* v, bool relu, uint32_t& satm) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -58,6 +71,7 @@ __device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const
             b = fmaxf(b, 0.f);
         }
         hi[j] = ep_pack2(a, b);
+        satm = ep_sat_track(satm, hi[j]);
         float ha, hb;
         e2f2(hi[j], ha, hb);
         lo[j] = ep_pack2(a - ha, b - hb);
@@ -69,7 +83,7 @@ __device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const
 // 16 channels at once: one 32-byte (full L2 sector) store for the hi halves and one for the lo halves.
 // (16-byte stores write half sectors: ncu showed DRAM reads ~= output size, i.e. read-for-ownership
 // fills on every output sector.)  rec + c0 must be 32-byte aligned: c0 % 16 == 0.
-__device__ __forceinline__ void ep_pack8(const float* v, bool relu, uint32_t* hi, uint32_t* lo) {
+__device__ __forceinline__ void ep_pack8(const float* v, bool relu, uint32_t* hi, uint32_t* lo, uint32_t& satm) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float a = v[2 * j], b = v[2 * j + 1];
@@ -78,6 +92,7 @@ __device__ __forceinline__ void ep_pack8(const float* v, bool relu, uint32_t* hi
             b = fmaxf(b, 0.f);
         }
         hi[j] = ep_pack2(a, b);
+        satm = ep_sat_track(satm, hi[j]);
         float ha, hb;
         e2f2(hi[j], ha, hb);
         lo[j] = ep_pack2(a - ha, b - hb);
@@ -93,10 +108,10 @@ __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
-__device__ __forceinline__ void ep_store16_packed(e16* rec, int Cp, int c0, const float* v16, bool relu) {
+__device__ __forceinline__ void ep_store16_packed(e16* rec, int Cp, int c0, const float* v16, bool relu, uint32_t& satm) {
     uint32_t hi[8], lo[8];
-    ep_pack8(v16, relu, hi, lo);
-    ep_pack8(v16 + 8, relu, hi + 4, lo + 4);
+    ep_pack8(v16, relu, hi, lo, satm);
+    ep_pack8(v16 + 8, relu, hi + 4, lo + 4, satm);
     st_global_v8(rec + c0, hi);
     st_global_v8(rec + Cp + c0, lo);
 }

@@ -571,8 +571,14 @@ int launch_reduce_partials(const float* partials, int n, int groups, double scal
 
 // sums6 = mse, warploss, interloss, bits_feature, bits_z, bits_mv ->
 // scalars7 = mse, warploss, interloss, bpp_feature, bpp_z, bpp_mv, bpp   (net.py:212-220)
-__global__ void k_finalize_scalars(const float* __restrict__ sums6, float n_pix, float* __restrict__ out) {
+__global__ void k_finalize_scalars(const float* __restrict__ sums6, float n_pix, float* __restrict__ out,
+                                   const unsigned int* __restrict__ sat_count) {
     if (threadIdx.x == 0) {
+        if (sat_count && *sat_count) {
+            // an activation left the fp16 operand-pair range and was clamped somewhere upstream: fail loudly
+            for (int i = 0; i < 7; ++i) out[i] = __int_as_float(0x7fc00000);
+            return;
+        }
         out[0] = sums6[0];
         out[1] = sums6[1];
         out[2] = sums6[2];
@@ -583,8 +589,9 @@ __global__ void k_finalize_scalars(const float* __restrict__ sums6, float n_pix,
         out[6] = (bf + bz) + bm;
     }
 }
-int launch_finalize_scalars(const float* sums6, float n_pix, float* scalars7, cudaStream_t s) {
-    k_finalize_scalars<<<1, 32, 0, s>>>(sums6, n_pix, scalars7);
+int launch_finalize_scalars(const float* sums6, float n_pix, float* scalars7, const unsigned int* sat_count,
+                            cudaStream_t s) {
+    k_finalize_scalars<<<1, 32, 0, s>>>(sums6, n_pix, scalars7, sat_count);
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;

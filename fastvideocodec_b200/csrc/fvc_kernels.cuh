@@ -29,7 +29,8 @@ int launch_gdn_reparam(const float* beta, const float* gamma, float* beta_eff, f
 int launch_recon_losses(const float* cur, const float* pred, const float* warp, const float* res, int res_nhwc3,
                         int B, int HW, float* clipped, float* partials, int* nblocks_out, cudaStream_t s,
                         int clip_mse = 0);
-int launch_finalize_scalars(const float* sums6, float n_pix, float* scalars7, cudaStream_t s);
+int launch_finalize_scalars(const float* sums6, float n_pix, float* scalars7, const unsigned int* sat_count,
+                            cudaStream_t s);
 int launch_reduce_partials(const float* partials, int n, int groups, double scale, float* out, cudaStream_t s);
 // layout conversion
 int launch_nchw_to_act(const float* x, ActT out, int C, int do_abs, cudaStream_t s);

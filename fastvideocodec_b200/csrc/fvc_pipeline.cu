@@ -118,6 +118,12 @@ struct fvc_ctx {
     int stage_G = 0;
     float* stage_frames = nullptr;
     float* stage_scalars = nullptr;
+    // teacher forcing (tests / inspection): device fp32 NCHW tensors that replace the quantised latents
+    // quant_mv, z_hat, feat_hat right after the quantisers (nullptr = free running)
+    const float* force_q[3] = {nullptr, nullptr, nullptr};
+    // number of epilogue tiles that produced an activation at or beyond the fp16 pair range (|v| >= 65504):
+    // those values were clamped, the results are wrong; scalars turn NaN and the host entry points fail
+    unsigned int* sat_count = nullptr;
 
     template <typename T>
     int alloc(T** p, size_t bytes) {
@@ -313,11 +319,39 @@ static int build_buffers(fvc_ctx* c) {
     A(c->alloc(&c->bits_partials, (size_t)bits_max_blocks() * 3 * 4));
     A(c->alloc(&c->bits_counts, 3 * sizeof(int)));
     A(c->alloc(&c->scalars, 8 * 4));
+    A(c->alloc(&c->sat_count, 4));
 #undef A
     return 0;
 }
 
 // ----------------------------------------------------------------------------------------------
+// FVC_PROFILE=1: every launch of the frame is bracketed by CUDA events on the launching stream.  Convolutions are
+// listed under their layer name, the memory-bound kernels under "@<kernel>[:<tag>]".
+struct ProfScope {
+    fvc_ctx* c;
+    cudaStream_t s;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(fvc_ctx* ctx, const std::string& name, cudaStream_t st) : c(ctx), s(st) {
+        if (!c->profile) return;
+        if (c->conv_event_used == c->conv_events.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            c->conv_events.push_back({a, b});
+        }
+        cudaEvent_t e0 = c->conv_events[c->conv_event_used].first;
+        e1 = c->conv_events[c->conv_event_used].second;
+        if (c->conv_event_names.size() <= c->conv_event_used) c->conv_event_names.resize(c->conv_event_used + 1);
+        c->conv_event_names[c->conv_event_used] = name;
+        c->conv_event_used++;
+        cudaEventRecord(e0, s);
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, s);
+    }
+};
+// memory-bound kernel launch with profiling scope (uses the enclosing function's `rc`, `c`, `s`)
+#define PK(tag, expr) do { ProfScope _ps(c, tag, s); rc = (expr); if (rc) return rc; } while (0)
+
 static ActT no_act() {
     ActT t;
     t.p = nullptr; t.B = t.H = t.W = t.Cp = t.parity = 0;
@@ -352,21 +386,8 @@ static int run_conv(fvc_ctx* c, const std::string& name, ActT in, int Hout, int 
     }
     ep.bias = r.bias;
     ep.act = r.act;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (c->profile) {
-        if (c->conv_event_used == c->conv_events.size()) {
-            cudaEvent_t a, b;
-            FVC_CUDA(cudaEventCreate(&a));
-            FVC_CUDA(cudaEventCreate(&b));
-            c->conv_events.push_back({a, b});
-        }
-        e0 = c->conv_events[c->conv_event_used].first;
-        e1 = c->conv_events[c->conv_event_used].second;
-        if (c->conv_event_names.size() <= c->conv_event_used) c->conv_event_names.resize(c->conv_event_used + 1);
-        c->conv_event_names[c->conv_event_used] = name;
-        c->conv_event_used++;
-        FVC_CUDA(cudaEventRecord(e0, s));
-    }
+    ep.sat_count = c->sat_count;
+    ProfScope prof(c, name, s);
     int rc;
     if (c->impl == FVC_IMPL_TC && c->use_few && r.few_w && !in.parity && ep.act == FVC_ACT_NONE && !ep.res_act.p &&
         !ep.out_act_relu.p && !ep.out_act_sq.p && ep.out_f32) {
@@ -384,9 +405,7 @@ static int run_conv(fvc_ctx* c, const std::string& name, ActT in, int Hout, int 
         }
         rc = launch_conv_simt(r.L, r.simt, in, Hout, Wout, ep, s);
     }
-    if (rc) return rc;
-    if (c->profile) FVC_CUDA(cudaEventRecord(e1, s));
-    return 0;
+    return rc;
 }
 
 // conv followed by (I)GDN: conv kernel writes the raw activations, a second kernel normalises
@@ -438,6 +457,24 @@ static int res_block(fvc_ctx* c, int idx, ActT x_relu, ActT x_skip, ActT tmp, Ac
     return run_conv(c, n2, tmp, out.H, out.W, ep, s);
 }
 
+// mvDecoder (synthesis_mv.py:71-79): c->quant_mv (ACT) -> c->mv_hat (fp32 NHWC2)
+static int run_mv_decoder(fvc_ctx* c, cudaStream_t s) {
+    const int H = c->H, W = c->W;
+    char nm[96];
+    ActT in = c->quant_mv;
+    for (int i = 1; i <= 8; ++i) {
+        snprintf(nm, sizeof(nm), "mvDecoder.deconv%d", i);
+        Epilogue ep = make_ep(c->conv[nm]);
+        int sh = 4 - (i + 1) / 2;
+        if (i < 8) ep.out_act = c->d[i];
+        else ep.out_f32 = c->mv_hat;
+        int rc = run_conv(c, nm, in, H >> sh, W >> sh, ep, s);
+        if (rc) return rc;
+        if (i < 8) in = c->d[i];
+    }
+    return 0;
+}
+
 // Phase A of the path: opticFlow + mvEncoder + quantiser/bits + mvDecoder (net.py:71-77; LSVC: models.py:1350-1351,
 // 1333-1342).  Leaves mv_hat in c->mv_hat (fp32 NHWC2) and the mv bit partials in c->bits_partials[2].
 static int forward_mv(fvc_ctx* c, const float* cur, const float* ref, int* nb_mv_out, cudaStream_t s) {
@@ -451,8 +488,8 @@ static int forward_mv(fvc_ctx* c, const float* cur, const float* ref, int* nb_mv
     std::vector<const float*> im1(L), im2(L);
     im1[0] = cur; im2[0] = ref;
     for (int sc = 1; sc < L; ++sc) {
-        R(launch_avg_pool2_planar(im1[sc - 1], c->pyr1[sc], B * 3, H >> (sc - 1), W >> (sc - 1), s));
-        R(launch_avg_pool2_planar(im2[sc - 1], c->pyr2[sc], B * 3, H >> (sc - 1), W >> (sc - 1), s));
+        PK("@k_avg_pool2_planar", launch_avg_pool2_planar(im1[sc - 1], c->pyr1[sc], B * 3, H >> (sc - 1), W >> (sc - 1), s));
+        PK("@k_avg_pool2_planar", launch_avg_pool2_planar(im2[sc - 1], c->pyr2[sc], B * 3, H >> (sc - 1), W >> (sc - 1), s));
         im1[sc] = c->pyr1[sc];
         im2[sc] = c->pyr2[sc];
     }
@@ -460,7 +497,7 @@ static int forward_mv(fvc_ctx* c, const float* cur, const float* ref, int* nb_mv
     for (int i = 0; i < L; ++i) {
         int sc = L - 1 - i;
         int h = H >> sc, w = W >> sc;
-        R(launch_spynet_prep(im1[sc], im2[sc], i == 0 ? nullptr : c->sflow[i - 1], c->sx[i], c->sflow_up[i], s));
+        PK("@k_spynet_prep:L" + std::to_string(i), launch_spynet_prep(im1[sc], im2[sc], i == 0 ? nullptr : c->sflow[i - 1], c->sx[i], c->sflow_up[i], s));
         ActT chain_in[5] = {c->sx[i], c->sa1[i], c->sa2[i], c->sa3[i], c->sa4[i]};
         for (int k = 0; k < 5; ++k) {
             snprintf(nm, sizeof(nm), "opticFlow.moduleBasic.%d.conv%d", i, k + 1);
@@ -493,23 +530,58 @@ static int forward_mv(fvc_ctx* c, const float* cur, const float* ref, int* nb_mv
     {
         FactorizedParams prm;
         for (int i = 0; i < 11; ++i) prm.p[i] = c->be_mv.p[i];
-        R(launch_quant_bits_factorized(c->mvfeature, 1, B, 128, (H / 16) * (W / 16), prm, nullptr, c->quant_mv,
+        PK("@k_quant_bits_factorized:mv", launch_quant_bits_factorized(c->mvfeature, 1, B, 128, (H / 16) * (W / 16), prm, nullptr, c->quant_mv,
                                        c->bits_partials + 2 * maxb, &nb_mv, s));
     }
-    // ---- mvDecoder (synthesis_mv.py:71-79) ---------------------------------------------------
-    {
-        ActT in = c->quant_mv;
-        for (int i = 1; i <= 8; ++i) {
-            snprintf(nm, sizeof(nm), "mvDecoder.deconv%d", i);
-            Epilogue ep = make_ep(c->conv[nm]);
-            int sh = 4 - (i + 1) / 2;
-            if (i < 8) ep.out_act = c->d[i];
-            else ep.out_f32 = c->mv_hat;
-            R(run_conv(c, nm, in, H >> sh, W >> sh, ep, s));
-            if (i < 8) in = c->d[i];
-        }
-    }
+    if (c->force_q[0]) R(launch_nchw_to_act(c->force_q[0], c->quant_mv, 128, 0, s));   // teacher forcing
     *nb_mv_out = nb_mv;
+    R(run_mv_decoder(c, s));
+#undef R
+    return 0;
+}
+
+// motion compensation (net.py:64-68, endecoder.py:282-296): c->mv_hat, ref -> c->warpframe, c->prediction;
+// with `cur` also the residual record (net.py:81); cur == nullptr (decoder): the residual is not formed
+static int run_motion_comp(fvc_ctx* c, const float* cur, const float* ref, cudaStream_t s) {
+    const int H = c->H, W = c->W;
+    int rc;
+#define R(expr) do { rc = (expr); if (rc) return rc; } while (0)
+    PK("@k_mc_prep", launch_mc_prep(ref, c->mv_hat, c->warpframe, c->xmc, s));
+    {
+        Epilogue ep = make_ep(c->conv["warpnet.feature_ext"]);
+        ep.out_act = c->wf;
+        R(run_conv(c, "warpnet.feature_ext", c->xmc, H, W, ep, s));
+    }
+    R(res_block(c, 0, c->wf, c->wf, c->wt0, c->wc0, no_act(), s));          // f >= 0: relu(f) == f
+    PK("@k_pool_act:full", launch_pool_act(c->wc0, c->wc0p, c->wc0p_r, s));
+    R(res_block(c, 1, c->wc0p_r, c->wc0p, c->wt1, c->wc1, no_act(), s));
+    PK("@k_pool_act:half", launch_pool_act(c->wc1, c->wc1p, c->wc1p_r, s));
+    R(res_block(c, 2, c->wc1p_r, c->wc1p, c->wt2, c->wc2, c->wc2_r, s));
+    R(res_block(c, 3, c->wc2_r, c->wc2, c->wt3, c->wc3, no_act(), s));
+    PK("@k_upadd_act:half", launch_upadd_act(c->wc3, c->wc1, c->wc3u, c->wc3u_r, s));
+    R(res_block(c, 4, c->wc3u_r, c->wc3u, c->wt4, c->wc4, no_act(), s));
+    PK("@k_upadd_act:full", launch_upadd_act(c->wc4, c->wc0, c->wc4u, c->wc4u_r, s));
+    R(res_block(c, 5, c->wc4u_r, c->wc4u, c->wt5, c->wc5, no_act(), s));
+    {
+        Epilogue ep = make_ep(c->conv["warpnet.conv6"]);
+        ep.out_f32 = c->wres;
+        R(run_conv(c, "warpnet.conv6", c->wc5, H, W, ep, s));
+    }
+    PK("@k_mc_finish", launch_mc_finish(c->wres, c->warpframe, cur ? cur : ref, c->prediction, c->residual, s));
+#undef R
+    return 0;
+}
+
+// residual decoder (synthesis.py:54-58): c->feat_hat (ACT) -> c->recon_res (fp32 NHWC3)
+static int run_res_decoder(fvc_ctx* c, cudaStream_t s) {
+    int rc;
+#define R(expr) do { rc = (expr); if (rc) return rc; } while (0)
+    R(run_conv_gdn(c, "resDecoder.deconv1", "resDecoder.igdn1", c->feat_hat, c->g_raw[0], c->g_sq[0], c->g[0], s));
+    R(run_conv_gdn(c, "resDecoder.deconv2", "resDecoder.igdn2", c->g[0], c->g_raw[1], c->g_sq[1], c->g[1], s));
+    R(run_conv_gdn(c, "resDecoder.deconv3", "resDecoder.igdn3", c->g[1], c->g_raw[2], c->g_sq[2], c->g[2], s));
+    Epilogue ep = make_ep(c->conv["resDecoder.deconv4"]);
+    ep.out_f32 = c->recon_res;
+    R(run_conv(c, "resDecoder.deconv4", c->g[2], c->H, c->W, ep, s));
 #undef R
     return 0;
 }
@@ -524,29 +596,7 @@ static int forward_mc_res(fvc_ctx* c, const float* cur, const float* ref, float*
     int nb_z = 0, nb_f = 0;
     const int maxb = bits_max_blocks();
 #define R(expr) do { rc = (expr); if (rc) return rc; } while (0)
-    // ---- motion compensation (net.py:64-68, endecoder.py:282-296) ------------------------------
-    R(launch_mc_prep(ref, c->mv_hat, c->warpframe, c->xmc, s));
-    {
-        Epilogue ep = make_ep(c->conv["warpnet.feature_ext"]);
-        ep.out_act = c->wf;
-        R(run_conv(c, "warpnet.feature_ext", c->xmc, H, W, ep, s));
-    }
-    R(res_block(c, 0, c->wf, c->wf, c->wt0, c->wc0, no_act(), s));          // f >= 0: relu(f) == f
-    R(launch_pool_act(c->wc0, c->wc0p, c->wc0p_r, s));
-    R(res_block(c, 1, c->wc0p_r, c->wc0p, c->wt1, c->wc1, no_act(), s));
-    R(launch_pool_act(c->wc1, c->wc1p, c->wc1p_r, s));
-    R(res_block(c, 2, c->wc1p_r, c->wc1p, c->wt2, c->wc2, c->wc2_r, s));
-    R(res_block(c, 3, c->wc2_r, c->wc2, c->wt3, c->wc3, no_act(), s));
-    R(launch_upadd_act(c->wc3, c->wc1, c->wc3u, c->wc3u_r, s));
-    R(res_block(c, 4, c->wc3u_r, c->wc3u, c->wt4, c->wc4, no_act(), s));
-    R(launch_upadd_act(c->wc4, c->wc0, c->wc4u, c->wc4u_r, s));
-    R(res_block(c, 5, c->wc4u_r, c->wc4u, c->wt5, c->wc5, no_act(), s));
-    {
-        Epilogue ep = make_ep(c->conv["warpnet.conv6"]);
-        ep.out_f32 = c->wres;
-        R(run_conv(c, "warpnet.conv6", c->wc5, H, W, ep, s));
-    }
-    R(launch_mc_finish(c->wres, c->warpframe, cur, c->prediction, c->residual, s));
+    R(run_motion_comp(c, cur, ref, s));
     // ---- residual encoder (analysis.py:44-48) ---------------------------------------------------
     R(run_conv_gdn(c, "resEncoder.conv1", "resEncoder.gdn1", c->residual, c->r_raw[0], c->r_sq[0], c->r[0], s));
     R(run_conv_gdn(c, "resEncoder.conv2", "resEncoder.gdn2", c->r[0], c->r_raw[1], c->r_sq[1], c->r[1], s));
@@ -557,7 +607,7 @@ static int forward_mc_res(fvc_ctx* c, const float* cur, const float* ref, float*
         R(run_conv(c, "resEncoder.conv4", c->r[2], H / 16, W / 16, ep, s));
     }
     // ---- hyper-prior (analysis_prior.py:40-56, synthesis_prior.py:42-58) ------------------------
-    R(launch_nhwc_to_act(c->feature, c->featabs, 96, 1, s));
+    PK("@k_nhwc_to_act", launch_nhwc_to_act(c->feature, c->featabs, 96, 1, s));
     {
         Epilogue ep = make_ep(c->conv["respriorEncoder.conv1"]);
         ep.out_act = c->p1;
@@ -572,9 +622,10 @@ static int forward_mc_res(fvc_ctx* c, const float* cur, const float* ref, float*
     {
         FactorizedParams prm;
         for (int i = 0; i < 11; ++i) prm.p[i] = c->be_z.p[i];
-        R(launch_quant_bits_factorized(c->z, 1, B, 64, (H / 64) * (W / 64), prm, nullptr, c->z_hat,
+        PK("@k_quant_bits_factorized:z", launch_quant_bits_factorized(c->z, 1, B, 64, (H / 64) * (W / 64), prm, nullptr, c->z_hat,
                                        c->bits_partials + 1 * maxb, &nb_z, s));
     }
+    if (c->force_q[1]) R(launch_nchw_to_act(c->force_q[1], c->z_hat, 64, 0, s));   // teacher forcing
     {
         Epilogue ep = make_ep(c->conv["respriorDecoder.deconv1"]);
         ep.out_act = c->s1;
@@ -586,20 +637,13 @@ static int forward_mc_res(fvc_ctx* c, const float* cur, const float* ref, float*
         ep.out_f32 = c->sigma;
         R(run_conv(c, "respriorDecoder.deconv3", c->s2, H / 16, W / 16, ep, s));
     }
-    R(launch_quant_bits_laplace(c->feature, c->sigma, (int64_t)B * (H / 16) * (W / 16) * 96, 96, nullptr,
+    PK("@k_quant_bits_laplace", launch_quant_bits_laplace(c->feature, c->sigma, (int64_t)B * (H / 16) * (W / 16) * 96, 96, nullptr,
                                 c->feat_hat, c->bits_partials + 0 * maxb, &nb_f, s));
-    // ---- residual decoder (synthesis.py:54-58) --------------------------------------------------
-    R(run_conv_gdn(c, "resDecoder.deconv1", "resDecoder.igdn1", c->feat_hat, c->g_raw[0], c->g_sq[0], c->g[0], s));
-    R(run_conv_gdn(c, "resDecoder.deconv2", "resDecoder.igdn2", c->g[0], c->g_raw[1], c->g_sq[1], c->g[1], s));
-    R(run_conv_gdn(c, "resDecoder.deconv3", "resDecoder.igdn3", c->g[1], c->g_raw[2], c->g_sq[2], c->g[2], s));
-    {
-        Epilogue ep = make_ep(c->conv["resDecoder.deconv4"]);
-        ep.out_f32 = c->recon_res;
-        R(run_conv(c, "resDecoder.deconv4", c->g[2], H, W, ep, s));
-    }
+    if (c->force_q[2]) R(launch_nchw_to_act(c->force_q[2], c->feat_hat, 96, 0, s));   // teacher forcing
+    R(run_res_decoder(c, s));
     // ---- reconstruction, distortion, rate (net.py:103-116, 207-217) -------------------------------
     int nloss = 0;
-    R(launch_recon_losses(cur, c->prediction, c->warpframe, c->recon_res, 1, B, H * W, recon_out, c->loss_partials,
+    PK("@k_recon_losses", launch_recon_losses(cur, c->prediction, c->warpframe, c->recon_res, 1, B, H * W, recon_out, c->loss_partials,
                           &nloss, s, clip_mse));
     R(launch_reduce_partials(c->loss_partials, nloss, 3, loss_scale, c->scalars, s));
     R(launch_reduce_partials(c->bits_partials + 0 * maxb, nb_f, 1, 1.0, c->scalars + 3, s));
@@ -620,7 +664,7 @@ static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_
     if (rc) return rc;
     rc = launch_reduce_partials(c->bits_partials + 2 * bits_max_blocks(), nb_mv, 1, 1.0, c->scalars + 5, s);
     if (rc) return rc;
-    return launch_finalize_scalars(c->scalars, (float)((double)B * H * W), scalars_out, s);
+    return launch_finalize_scalars(c->scalars, (float)((double)B * H * W), scalars_out, c->sat_count, s);
 }
 
 }  // namespace fvc
@@ -789,7 +833,7 @@ int fvc_pframe_forward(fvc_ctx* c, const float* cur, const float* ref, float* re
         for (size_t i = 0; i < c->conv_event_used; ++i) {
             float ms = 0;
             cudaEventElapsedTime(&ms, c->conv_events[i].first, c->conv_events[i].second);
-            tot += ms * 1e-3;
+            if (c->conv_event_names[i][0] != '@') tot += ms * 1e-3;   // convolution launches only
             snprintf(line, sizeof(line), "%s %.4f\n", c->conv_event_names[i].c_str(), ms);
             c->profile_text += line;
         }
@@ -838,6 +882,49 @@ int fvc_lsvc_mc_res_forward(fvc_ctx* c, const float* cur, const float* ref, cons
     }
     c->launches += g_launch_count - before;
     return rc;
+}
+
+/* Decoder half of the path (net.py:77-80 mvDecoder + motioncompensation, 101-105 resDecoder, reconstruction and
+ * clamp): what a receiver runs on the entropy-decoded latents. */
+int fvc_decode_from_latents(fvc_ctx* c, const float* ref, const float* quant_mv, const float* feat_hat,
+                            float* recon_out, void* stream) {
+    FVC_ARG(c && ref && quant_mv && feat_hat && recon_out);
+    if (fvc_ctx_missing_params(c) != 0) {
+        set_error("fvc_decode_from_latents: %d parameters not set", fvc_ctx_missing_params(c));
+        return FVC_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t before = g_launch_count;
+    c->conv_event_used = 0;
+    int nloss = 0;
+    int rc = launch_nchw_to_act(quant_mv, c->quant_mv, 128, 0, s);
+    if (!rc) rc = run_mv_decoder(c, s);
+    if (!rc) rc = run_motion_comp(c, nullptr, ref, s);
+    if (!rc) rc = launch_nchw_to_act(feat_hat, c->feat_hat, 96, 0, s);
+    if (!rc) rc = run_res_decoder(c, s);
+    // clamp(prediction + recon_res, 0, 1); the distortion sums are formed against `ref` and discarded
+    if (!rc) rc = launch_recon_losses(ref, c->prediction, c->warpframe, c->recon_res, 1, c->B, c->H * c->W, recon_out,
+                                      c->loss_partials, &nloss, s, 0);
+    c->launches += g_launch_count - before;
+    return rc;
+}
+
+int fvc_ctx_force_latents(fvc_ctx* c, const float* quant_mv, const float* z_hat, const float* feat_hat) {
+    FVC_ARG(c != nullptr);
+    c->force_q[0] = quant_mv;
+    c->force_q[1] = z_hat;
+    c->force_q[2] = feat_hat;
+    return 0;
+}
+
+int64_t fvc_ctx_saturation_count(fvc_ctx* c, int reset, void* stream) {
+    if (!c) { set_error("fvc_ctx_saturation_count: null context"); return FVC_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned int h = 0;
+    FVC_CUDA(cudaMemcpyAsync(&h, c->sat_count, 4, cudaMemcpyDeviceToHost, s));
+    FVC_CUDA(cudaStreamSynchronize(s));
+    if (reset) FVC_CUDA(cudaMemsetAsync(c->sat_count, 0, 4, s));
+    return (int64_t)h;
 }
 
 int64_t fvc_ctx_launch_count(fvc_ctx* c) { return c ? c->launches : -1; }
@@ -939,7 +1026,14 @@ int fvc_gop_forward_host(fvc_ctx* c, const float* frames_host, int G, float* rec
     if (recon_host)
         FVC_CUDA(cudaMemcpyAsync(recon_host, c->stage_rec, fsz * (G - 1) * 4, cudaMemcpyDeviceToHost, s));
     FVC_CUDA(cudaMemcpyAsync(scalars_host, c->stage_scalars, (size_t)(G - 1) * 7 * 4, cudaMemcpyDeviceToHost, s));
+    unsigned int sat = 0;
+    FVC_CUDA(cudaMemcpyAsync(&sat, c->sat_count, 4, cudaMemcpyDeviceToHost, s));
     FVC_CUDA(cudaStreamSynchronize(s));
+    if (sat) {
+        set_error("fvc_gop_forward_host: activations reached the fp16 operand-pair range (|v| >= 65504) in %u epilogue "
+                  "tiles and were clamped; results are invalid for these weights (see fvc_ctx_saturation_count)", sat);
+        return FVC_ERR_STATE;
+    }
     return 0;
 }
 

@@ -60,15 +60,14 @@ class _Context:
         if not self.handle:
             raise _lib.FvcError("fvc_ctx_create failed: %s" % lib().fvc_last_error().decode())
         self.versions = None
-        self.scalars = torch.empty(7, device=device, dtype=torch.float32)
 
     def sync_params(self, model):
-        params = dict(model.state_dict(keep_vars=True))
-        versions = tuple((k, p.data_ptr(), p._version) for k, p in params.items())
+        params = model._param_items()
+        versions = tuple((p.data_ptr(), p._version) for _, p in params)
         if versions == self.versions:
             return
         s = stream_ptr()
-        for k, p in params.items():
+        for k, p in params:
             t = p.detach()
             if not t.is_cuda:
                 raise RuntimeError("VideoCompressor parameters must live on the CUDA device (call .cuda())")
@@ -110,19 +109,33 @@ class VideoCompressor(nn.Module):
         self.calrealbits = False
         self.decoding_time = 0.0
         self.impl = _default_impl()
+        self.max_contexts = int(os.environ.get("FVC_MAX_CONTEXTS", "6"))
         self._ctxs = {}
+        self._pitems = None
         # reference initialisers (xavier / constants; SpyNet: scaled default init because the
         # pretrained .npy files are not redistributable with this package)
         seed = int(torch.initial_seed() % (2 ** 31))
         self.load_state_dict(init_state_dict(seed, spynet_levels), strict=True)
 
     # -- context management -----------------------------------------------------------------
+    def _param_items(self):
+        """(key, tensor) list of the state_dict, cached: the module tree is fixed after construction (``.to()`` and
+        ``load_state_dict`` keep the Parameter objects and change data_ptr / _version, which sync_params checks)."""
+        if self._pitems is None:
+            self._pitems = list(self.state_dict(keep_vars=True).items())
+        return self._pitems
+
     def _context(self, B, H, W, device):
+        """Least-recently-used cache of at most ``max_contexts`` library contexts (each owns ~9 GB of
+        intermediates per 1080p frame of batch; LSVC uses one per distinct tree-layer width)."""
         key = (B, H, W, device, self.impl)
-        ctx = self._ctxs.get(key)
+        ctx = self._ctxs.pop(key, None)
         if ctx is None:
+            while len(self._ctxs) >= max(1, int(self.max_contexts)):
+                old_key = next(iter(self._ctxs))
+                self._ctxs.pop(old_key).close()
             ctx = _Context(self, B, H, W, device, self.impl)
-            self._ctxs[key] = ctx
+        self._ctxs[key] = ctx          # most recently used last
         ctx.sync_params(self)
         return ctx
 
@@ -188,8 +201,18 @@ class VideoCompressor(nn.Module):
 
         Returns (recon_host [G-1,B,3,H,W] or None, scalars_host [G-1,7]).  H2D/D2H copies inside.
         """
+        if not (torch.is_tensor(frames_host) and frames_host.device.type == "cpu" and frames_host.dtype == torch.float32
+                and frames_host.dim() == 5 and frames_host.shape[2] == 3 and frames_host.is_contiguous()):
+            raise TypeError("frames_host must be a contiguous CPU float32 [G,B,3,H,W] tensor (pinned memory "
+                            "recommended: pageable memory makes the upload synchronous)")
         G, B, _, H, W = frames_host.shape
+        if G < 2:
+            raise ValueError("a GOP needs the I-frame and at least one P-frame (G >= 2)")
+        if H % 64 or W % 64:
+            raise ValueError("H and W must be multiples of 64 (got %dx%d)" % (H, W))
         dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("VideoCompressor parameters must live on the CUDA device (call .cuda())")
         with torch.cuda.device(dev):
             ctx = self._context(B, H, W, dev)
             rec = torch.empty((G - 1, B, 3, H, W), dtype=torch.float32, pin_memory=True) if want_recon else None
@@ -199,6 +222,43 @@ class VideoCompressor(nn.Module):
                                              C.c_void_p(sc.data_ptr()), stream_ptr()), "fvc_gop_forward_host")
         self._last_ctx = ctx
         return rec, sc
+
+    def decode_from_latents(self, referframe, quant_mv, feat_hat):
+        """Decoder half of ``forward`` (net.py:77-80 and 101-105): entropy-decoded latents + reference frame ->
+        clamped reconstruction.  One call into fvc_decode_from_latents."""
+        B, _, H, W = referframe.shape
+        for t, shp in ((referframe, (B, 3, H, W)), (quant_mv, (B, out_channel_mv, H // 16, W // 16)),
+                       (feat_hat, (B, 96, H // 16, W // 16))):
+            if not (t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == shp):
+                raise TypeError("expected CUDA float32 tensors of shapes [B,3,H,W], [B,128,H/16,W/16], [B,96,H/16,W/16]")
+        if H % 64 or W % 64:
+            raise ValueError("H and W must be multiples of 64 (got %dx%d)" % (H, W))
+        ref, qmv, fh = referframe.contiguous(), quant_mv.contiguous(), feat_hat.contiguous()
+        with torch.cuda.device(ref.device):
+            ctx = self._context(B, H, W, ref.device)
+            recon = torch.empty_like(ref)
+            check(lib().fvc_decode_from_latents(ctx.handle, ptr(ref), ptr(qmv), ptr(fh), ptr(recon), stream_ptr()),
+                  "fvc_decode_from_latents")
+        self._last_ctx = ctx
+        return recon
+
+    def force_latents(self, B, H, W, device, quant_mv=None, z_hat=None, feat_hat=None):
+        """Teacher forcing for tests: the next forwards on the (B,H,W) context use these quantised latents (CUDA fp32
+        NCHW; the caller keeps them alive) instead of their own quantiser outputs; all None = free running."""
+        ctx = self._context(B, H, W, device)
+        ctx.forced = tuple(None if t is None else t.contiguous() for t in (quant_mv, z_hat, feat_hat))
+        p = [C.c_void_p(0) if t is None else ptr(t) for t in ctx.forced]
+        check(lib().fvc_ctx_force_latents(ctx.handle, *p), "fvc_ctx_force_latents")
+
+    def saturation_count(self, reset=False):
+        """Epilogue tiles that hit the fp16 operand-pair range (|v| >= 65504) since creation / last reset, summed
+        over this model's contexts; non-zero means clamped activations, i.e. invalid results (scalars are NaN)."""
+        n = 0
+        for c in self._ctxs.values():
+            with torch.cuda.device(c.key[3]):
+                n += check(lib().fvc_ctx_saturation_count(c.handle, int(bool(reset)), stream_ptr()),
+                           "fvc_ctx_saturation_count")
+        return n
 
     def launch_count(self):
         return sum(lib().fvc_ctx_launch_count(c.handle) for c in self._ctxs.values())

@@ -158,6 +158,25 @@ FVC_API int fvc_lsvc_mv_forward(fvc_ctx* ctx, const float* cur, const float* ref
 FVC_API int fvc_lsvc_mc_res_forward(fvc_ctx* ctx, const float* cur, const float* ref, const float* mv_hat,
                                     float* com_out, float* mc_out, float* warp_out, float* sums_out, void* stream);
 
+/* Decoder half of VideoCompressor.forward — net.py:77-80 (mvDecoder, motioncompensation) and net.py:101-105
+ * (resDecoder, recon = prediction + recon_res, clamp): what a receiver computes from the entropy-decoded latents.
+ * ref: [B,3,H,W]; quant_mv: [B,128,H/16,W/16]; feat_hat: [B,96,H/16,W/16] (integer-valued fp32, NCHW)
+ * -> recon_out: [B,3,H,W] (clamped).  Stream-ordered. */
+FVC_API int fvc_decode_from_latents(fvc_ctx* ctx, const float* ref, const float* quant_mv, const float* feat_hat,
+                                    float* recon_out, void* stream);
+
+/* Teacher forcing for tests / inspection: until cleared (NULL), every following forward replaces the output of the
+ * three quantisers (net.py:76 quant_mv [B,128,H/16,W/16], net.py:91 z_hat [B,64,H/64,W/64], net.py:100 feat_hat
+ * [B,96,H/16,W/16]; fp32 NCHW device tensors owned by the caller) by the given tensors; the bit estimates are
+ * still those of the free-running quantisers. */
+FVC_API int fvc_ctx_force_latents(fvc_ctx* ctx, const float* quant_mv, const float* z_hat, const float* feat_hat);
+
+/* Range check of the tcgen05 engine's fp16 operand pairs: number of epilogue tiles (since creation / last reset)
+ * that stored an activation with |v| >= 65504 (clamped: the reference is fp32, so the result is then wrong).
+ * While it is non-zero, fvc_pframe_forward writes NaN into scalars_out and fvc_gop_forward_host fails with
+ * FVC_ERR_STATE.  Synchronises the stream. */
+FVC_API int64_t fvc_ctx_saturation_count(fvc_ctx* ctx, int reset, void* stream);
+
 /* Launch statistics since creation: kernels launched by this library through ctx. */
 FVC_API int64_t fvc_ctx_launch_count(fvc_ctx* ctx);
 /* Dominant-kernel timing hook for bench.py: seconds spent in convolution kernels during the last

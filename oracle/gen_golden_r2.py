@@ -1,0 +1,147 @@
+"""Round-2 golden vectors, produced by running the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):
+
+    python -m oracle.gen_golden_r2 [real] [hd] [l6]
+
+Writes
+  tests/golden/spynet_real.npz      : the reference's own pretrained SpyNet weights, levels 1-4
+                                      (DVC/flow_pretrain_np/modelL{1..4}_F-{1..5}-{weight,bias}.npy, |w|max ~ 5),
+                                      under the reference's state_dict keys
+  tests/golden/pframe_real_128.npz  : one P-frame, 128x128, all intermediates + outputs, of the reference running
+                                      WITH those weights (every other parameter: init_state_dict(0))
+  tests/golden/hd_gop10.npz         : the reference's closed-loop GOP rows (7 scalars + PSNR x 9 P-frames) for
+                                      synthetic_gop(1088, 1920, gop=10, gop_id=0) with init_state_dict(0) — the GOP
+                                      bench.py times — plus, for the first (open-loop) P-frame, the three quantised
+                                      latents (int8) and the reference's pre-quantisation values at every element
+                                      within 2e-3 of a rounding tie (sparse), so that flips can be judged at HD
+  tests/golden/pframe_L6_256.npz    : one P-frame at 256x256 of the reference class with ``self.L`` patched to 6
+                                      (endecoder.py:318-319; moduleBasic extended with MEBasic(modelL5), (modelL6)),
+                                      weights init_state_dict(0, spynet_levels=6)
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from fastvideocodec_b200.synthetic import init_state_dict, synthetic_gop  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+from oracle.gen_golden import _np  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SCALARS = ["mse", "warploss", "interloss", "bpp_feature", "bpp_z", "bpp_mv", "bpp"]
+PREQUANT = {"quant_mv": "mvfeature", "z_hat": "z", "feat_hat": "feature"}
+
+
+def real_spynet_state_dict():
+    """init_state_dict(0) with the opticFlow.* entries replaced by the reference's pretrained .npy weights."""
+    model = ref_shim.build_reference_model(None)       # the reference ctor loads flow_pretrain_np itself
+    sd = init_state_dict(0)
+    real = {k: v.detach().clone() for k, v in model.state_dict().items() if k.startswith("opticFlow.")}
+    assert set(real) == {k for k in sd if k.startswith("opticFlow.")}
+    sd.update(real)
+    return sd, real
+
+
+def gen_real():
+    sd, real = real_spynet_state_dict()
+    np.savez_compressed(os.path.join(GOLD, "spynet_real.npz"), **_np(real))
+    model = ref_shim.build_reference_model(sd)
+    frames = synthetic_gop(128, 128, gop=2, gop_id=21)[:, 0]
+    ref, cur = frames[0:1], frames[1:2]
+    out, cap = ref_shim.run_reference_with_capture(model, cur, ref)
+    d = dict(cur=cur, ref=ref, clipped=out[0])
+    for n, v in zip(SCALARS, out[1:]):
+        d[n] = v
+    d.update(cap)
+    np.savez_compressed(os.path.join(GOLD, "pframe_real_128.npz"), **_np(d))
+
+
+def gen_hd():
+    sd = init_state_dict(0)
+    model = ref_shim.build_reference_model(sd)
+    frames = synthetic_gop(1088, 1920, gop=10, gop_id=0)[:, 0]
+    x_prev = frames[0:1]
+    rows = []
+    d = {}
+    for i in range(1, frames.shape[0]):
+        t0 = time.time()
+        if i == 1:
+            out, cap = ref_shim.run_reference_with_capture(model, frames[i:i + 1], x_prev)
+            for q, pre in PREQUANT.items():
+                d["f1_" + q] = cap[q].to(torch.int8)
+                assert torch.equal(d["f1_" + q].float(), cap[q])
+                frac = cap[pre] - torch.floor(cap[pre])
+                idx = ((frac - 0.5).abs() <= 2e-3).flatten().nonzero().flatten()
+                d["f1_%s_tie_idx" % pre] = idx.to(torch.int32)
+                d["f1_%s_tie_val" % pre] = cap[pre].flatten()[idx]
+                d["f1_%s_rms" % pre] = cap[pre].pow(2).mean().sqrt()
+            d["f1_clipped_u16"] = (out[0] * 65535.0).round().to(torch.int32).numpy().astype(np.uint16)   # 1.5e-5 steps
+        else:
+            with torch.no_grad():
+                out = model(frames[i:i + 1], x_prev)
+        x_prev = out[0].detach()
+        psnr = 10.0 * torch.log(1 / out[1]) / math.log(10.0)
+        rows.append([float(v) for v in out[1:]] + [float(psnr)])
+        print("hd frame %d: %.1f s  bpp %.5f psnr %.4f" % (i, time.time() - t0, rows[-1][6], rows[-1][7]), flush=True)
+    d["rows"] = np.asarray(rows, dtype=np.float64)
+    d["gop_id"] = np.asarray(0)
+    d = {k: (v if isinstance(v, np.ndarray) else _np({"x": v})["x"]) for k, v in d.items()}
+    np.savez_compressed(os.path.join(GOLD, "hd_gop10.npz"), **d)
+
+
+def build_reference_model_levels(sd, levels):
+    """Reference VideoCompressor with ME_Spynet.L patched (endecoder.py:318-319): the class hard-codes 4 levels but the
+    checkout ships modelL5 / modelL6 weights; SURVEY 7.2-6 defines parity for L > 4 against this patched class."""
+    refnet = ref_shim.load_reference()
+    import DVC.subnet.endecoder as endec
+    with ref_shim._cwd(ref_shim.REF_ROOT):
+        model = refnet.VideoCompressor()
+        model.opticFlow.L = levels
+        model.opticFlow.moduleBasic = torch.nn.ModuleList(
+            [endec.MEBasic("motion_estimation" + "modelL" + str(i + 1)) for i in range(levels)])
+    model.load_state_dict(sd, strict=True)
+    return model.eval()
+
+
+def gen_l6():
+    sd = init_state_dict(0, spynet_levels=6)
+    model = build_reference_model_levels(sd, 6)
+    frames = synthetic_gop(256, 256, gop=2, gop_id=31)[:, 0]
+    ref, cur = frames[0:1], frames[1:2]
+    out, cap = ref_shim.run_reference_with_capture(model, cur, ref)
+    d = dict(cur=cur, ref=ref, clipped=out[0], estmv=cap["estmv"], mv_hat=cap["mv_hat"], mvfeature=cap["mvfeature"],
+             feature=cap["feature"], z=cap["z"], quant_mv=cap["quant_mv"], z_hat=cap["z_hat"], feat_hat=cap["feat_hat"],
+             sigma=cap["sigma"])
+    for n, v in zip(SCALARS, out[1:]):
+        d[n] = v
+    np.savez_compressed(os.path.join(GOLD, "pframe_L6_256.npz"), **_np(d))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    what = sys.argv[1:] or ["real", "l6", "hd"]
+    if "real" in what:
+        gen_real()
+    if "l6" in what:
+        gen_l6()
+    if "hd" in what:
+        gen_hd()
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    main()

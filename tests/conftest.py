@@ -54,3 +54,29 @@ def golden_gop_64():
 @pytest.fixture(scope="session")
 def golden_ops():
     return load_golden("ops.npz")
+
+
+@pytest.fixture(scope="session")
+def real_state_dict(state_dict):
+    """init_state_dict(0) with opticFlow.* replaced by the reference's own pretrained SpyNet weights
+    (tests/golden/spynet_real.npz, written by oracle/gen_golden_r2.py from DVC/flow_pretrain_np; |w|max ~ 5)."""
+    sd = dict(state_dict)
+    real = load_golden("spynet_real.npz")
+    assert set(real) == {k for k in sd if k.startswith("opticFlow.")}
+    sd.update(real)
+    return sd
+
+
+@pytest.fixture(scope="session")
+def golden_pframe_real_128():
+    return load_golden("pframe_real_128.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_pframe_L6_256():
+    return load_golden("pframe_L6_256.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_hd_gop10():
+    return load_golden("hd_gop10.npz")

@@ -126,3 +126,46 @@ def test_lsvc_graph_helpers():
     assert len(layers) == 3 and parents[14] == 12 and refidx_from_graph(g, 14)[7] == 0
     g, layers, parents = graph_from_batch(5, isOnehop=True)
     assert refidx_from_graph(g, 5) == [0] * 5
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2 goldens (oracle/gen_golden_r2.py)
+# ------------------------------------------------------------------------------------------------
+def test_oracle_matches_reference_with_real_spynet_weights(real_state_dict, golden_pframe_real_128):
+    """The reference run with its own pretrained SpyNet weights (committed as tests/golden/spynet_real.npz)."""
+    assert max(v.abs().max().item() for k, v in real_state_dict.items() if k.startswith("opticFlow.")) > 3.0
+    _check_pframe(real_state_dict, golden_pframe_real_128)
+
+
+def test_oracle_matches_reference_deeper_pyramid_L6(golden_pframe_L6_256):
+    """levels=6 (configs[3] "deeper flow pyramid") against the reference class with ME_Spynet.L patched to 6."""
+    from fastvideocodec_b200.synthetic import init_state_dict
+    g = golden_pframe_L6_256
+    sd = init_state_dict(0, spynet_levels=6)
+    out, cap = O.pframe_forward(sd, g["cur"], g["ref"], levels=6, capture=True)
+    for name in ("estmv", "mv_hat", "mvfeature", "feature", "z", "sigma"):
+        err = (cap[name] - g[name]).abs().max().item()
+        assert err <= 2e-4 * max(1.0, g[name].abs().max().item()), (name, err)
+    for name in ("quant_mv", "z_hat", "feat_hat"):
+        assert (cap[name] != g[name]).float().mean().item() <= 1e-4, name
+    assert (out[0] - g["clipped"]).abs().max().item() <= 1e-4
+    for i, name in enumerate(SCALARS, start=1):
+        assert abs(float(out[i]) - float(g[name])) <= 1e-4 * max(abs(float(g[name])), 1e-3), name
+    # and it differs from the 4-level pyramid (the extra levels are really used)
+    out4 = O.pframe_forward({k: v for k, v in sd.items()}, g["cur"], g["ref"], levels=4)
+    assert abs(float(out4[7]) - float(out[7])) > 1e-6
+
+
+def test_oracle_matches_reference_hd_gop_first_frame(state_dict, golden_hd_gop10):
+    """First (open-loop) P-frame of the 1088x1920 GOP bench.py times: the oracle against the unmodified reference's
+    scalars, quantised latents and clipped frame (tests/golden/hd_gop10.npz).  ~15 s of host time."""
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    g = golden_hd_gop10
+    frames = synthetic_gop(1088, 1920, gop=2, gop_id=int(g["gop_id"]))[:, 0]
+    out, cap = O.pframe_forward(state_dict, frames[1:2], frames[0:1], capture=True)
+    for name in ("quant_mv", "z_hat", "feat_hat"):
+        assert (cap[name] != g["f1_" + name].float()).float().mean().item() <= 1e-4, name
+    want = torch.from_numpy(g["f1_clipped_u16"].numpy().astype("float32")) / 65535.0
+    assert ((out[0] - want).abs() > 2e-5).float().mean().item() <= 1e-3     # u16 steps; tie flips perturb locally
+    for i in range(7):
+        assert abs(float(out[1 + i]) - g["rows"][0, i].item()) <= 1e-4 * abs(g["rows"][0, i].item()), i
