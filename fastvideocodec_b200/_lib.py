@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfvc_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fvc_b200.h")
 
 ACT_NONE, ACT_RELU, ACT_LRELU01, ACT_EXP, ACT_LRELU001 = 0, 1, 2, 3, 4
-IMPL_SIMT, IMPL_TC = 0, 1
+IMPL_SIMT, IMPL_TC, IMPL_TC_FAST = 0, 1, 2
 
 _lib = None
 
@@ -48,6 +48,16 @@ _SIGNATURES = {
     "fvc_decode_from_latents": (_i, [C.c_void_p, _f, _f, _f, _f, _s]),
     "fvc_ctx_force_latents": (_i, [C.c_void_p, _f, _f, _f]),
     "fvc_ctx_saturation_count": (_l, [C.c_void_p, _i, _s]),
+    "fvc_ctx_set_realbits": (_i, [C.c_void_p, _i, _i]),
+    "fvc_ctx_get_bitstream": (_l, [C.c_void_p, _i, C.c_void_p, _l, _s]),
+    "fvc_decode_bitstreams": (_i, [C.c_void_p, _f, C.c_void_p, _l, C.c_void_p, _l, C.c_void_p, _l, _f, _s]),
+    "fvc_cdf_table_factorized": (_i, [C.POINTER(C.c_void_p), _i, _i, C.c_void_p, _s]),
+    "fvc_cdf_table_laplace": (_i, [_f, _l, _i, C.c_void_p, _s]),
+    "fvc_entropy_encode_factorized": (_i, [_f, _l, _i, C.c_void_p, _i, _i, C.c_void_p, _l, C.c_void_p, C.c_void_p, _s]),
+    "fvc_entropy_encode_laplace": (_i, [_f, _f, _l, _i, _i, C.c_void_p, _l, C.c_void_p, C.c_void_p, _s]),
+    "fvc_entropy_decode_factorized": (_i, [C.c_void_p, _l, _l, _i, C.c_void_p, _i, _i, _f, C.c_void_p, _s]),
+    "fvc_entropy_decode_laplace": (_i, [C.c_void_p, _l, _l, _f, _i, _i, _f, C.c_void_p, _s]),
+    "fvc_entropy_stream_capacity": (_l, [_l, _i]),
     "fvc_ctx_launch_count": (_l, [C.c_void_p]),
     "fvc_ctx_last_conv_seconds": (C.c_double, [C.c_void_p]),
     "fvc_ctx_profile_text": (C.c_char_p, [C.c_void_p]),

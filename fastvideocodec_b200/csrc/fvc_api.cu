@@ -68,6 +68,7 @@ int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int 
     FVC_ARG(x && w && bias && y);
     FVC_ARG(B >= 1 && Cin >= 1 && Cin <= 128 && Cout >= 1 && Cout <= 128 && (k == 1 || k == 3 || k == 5 || k == 7));
     FVC_ARG(stride == 1 || stride == 2);
+    FVC_ARG(impl == FVC_IMPL_SIMT || impl == FVC_IMPL_TC || impl == FVC_IMPL_TC_FAST);
     FVC_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0) || transposed);
     cudaStream_t s = (cudaStream_t)stream;
     ConvLayer L;
@@ -75,7 +76,7 @@ int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int 
     int Ho = transposed ? H * stride : H / stride, Wo = transposed ? W * stride : W / stride;
     TmpPool tmp(s);
     ActT in;
-    in.B = B; in.H = H; in.W = W; in.Cp = (impl == FVC_IMPL_TC && Cin <= 8) ? 8 : pad_c(Cin);   // narrow records for the input layers
+    in.B = B; in.H = H; in.W = W; in.Cp = (impl != FVC_IMPL_SIMT && Cin <= 8) ? 8 : pad_c(Cin);   // narrow records for the input layers
     in.parity = (!transposed && stride == 2) ? 1 : 0;
     if (tmp.get(&in.p, act_bytes(B, H, W, in.Cp))) return FVC_ERR_CUDA;
     int rc = launch_nchw_to_act(x, in, Cin, 0, s);
@@ -88,13 +89,13 @@ int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int 
     ep.acc_scale = 1.f;
     ep.act = act;
     ep.out_f32 = out_nhwc;
-    if (impl == FVC_IMPL_TC) {
+    if (impl != FVC_IMPL_SIMT) {
         if (!tc_supported(L, in.Cp)) {
             set_error("fvc_conv2d: shape not supported by the tcgen05 engine");
             return FVC_ERR_ARG;
         }
         TcPlan* plan = nullptr;
-        rc = tc_plan_create(L, w, in, Ho, Wo, ep, &plan, s);
+        rc = tc_plan_create(L, w, in, Ho, Wo, ep, &plan, s, impl == FVC_IMPL_TC_FAST);
         if (rc) return rc;
         rc = tc_plan_launch(plan, s);
         if (rc == 0) rc = (cudaStreamSynchronize(s) == cudaSuccess) ? 0 : cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
@@ -231,6 +232,83 @@ int fvc_gaussian_forward(const float* x, const float* scales, const float* means
     int rc = launch_gaussian_forward(x, scales, means, xhat_out, lik_out, partials, &nb, n, s);
     if (rc) return rc;
     return launch_reduce_partials(partials, nb, 1, 1.0, bits_out, s);
+}
+
+/* ---- entropy coding, op level (net.py:123-138, 155-168, 183-195; fvc_entropy.cu) -------------------------------- */
+int fvc_cdf_table_factorized(const float* const* params, int C, int mxrange, uint32_t* table_out, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(params && table_out && C >= 1);
+    FactorizedParams prm;
+    for (int i = 0; i < 11; ++i) {
+        FVC_ARG(params[i] != nullptr);
+        prm.p[i] = params[i];
+    }
+    return launch_cdf_table_factorized(prm, C, mxrange, table_out, (cudaStream_t)stream);
+}
+
+int fvc_cdf_table_laplace(const float* sigma, int64_t n, int mxrange, uint32_t* table_out, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(sigma && table_out && n >= 0);
+    return launch_cdf_table_laplace(sigma, n, mxrange, table_out, (cudaStream_t)stream);
+}
+
+static int entropy_encode_common(bool laplace, const float* x, const float* sigma, const uint32_t* table, int64_t n, int C,
+                                 int R, int L, uint8_t* out, int64_t capacity, uint32_t* nbytes_out, uint32_t* err_out,
+                                 cudaStream_t s) {
+    FVC_ARG(x && out && nbytes_out && err_out && n >= 1 && L >= 1 && L <= 65533);
+    FVC_ARG((int64_t)entropy_stream_capacity(n, L) <= capacity);
+    TmpPool tmp(s);
+    uint32_t *packed = nullptr, *lane_words = nullptr;
+    uint16_t* words = nullptr;
+    if (tmp.get(&packed, (size_t)n * 4) || tmp.get(&words, entropy_words_capacity(n, L) * 2) ||
+        tmp.get(&lane_words, (size_t)cdiv64(n, L) * 4))
+        return FVC_ERR_CUDA;
+    FVC_CUDA(cudaMemsetAsync(err_out, 0, 12, s));
+    int rc = laplace ? launch_sym_laplace(x, sigma, n, R, packed, err_out, s)
+                     : launch_sym_factorized(x, n, C, R, table, packed, err_out, s);
+    if (rc) return rc;
+    return launch_rans_encode(packed, n, L, words, lane_words, out, nbytes_out, s);
+}
+
+int fvc_entropy_encode_factorized(const float* x, int64_t n, int C, const uint32_t* table, int mxrange, int lane_len,
+                                  void* stream_out, int64_t capacity, uint32_t* nbytes_out, uint32_t* err_out,
+                                  void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(table && C >= 1);
+    return entropy_encode_common(false, x, nullptr, table, n, C, mxrange, lane_len, (uint8_t*)stream_out, capacity,
+                                 nbytes_out, err_out, (cudaStream_t)stream);
+}
+
+int fvc_entropy_encode_laplace(const float* x, const float* sigma, int64_t n, int mxrange, int lane_len,
+                               void* stream_out, int64_t capacity, uint32_t* nbytes_out, uint32_t* err_out,
+                               void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(sigma != nullptr);
+    return entropy_encode_common(true, x, sigma, nullptr, n, 1, mxrange, lane_len, (uint8_t*)stream_out, capacity,
+                                 nbytes_out, err_out, (cudaStream_t)stream);
+}
+
+int fvc_entropy_decode_factorized(const void* stream_in, int64_t nbytes, int64_t n, int C, const uint32_t* table,
+                                  int mxrange, int lane_len, float* q_out, uint32_t* err_out, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(stream_in && table && q_out && err_out && n >= 1 && C >= 1);
+    FVC_CUDA(cudaMemsetAsync(err_out, 0, 12, (cudaStream_t)stream));
+    return launch_rans_decode_factorized((const uint8_t*)stream_in, nbytes, n, lane_len, C, mxrange, table, q_out,
+                                         err_out, (cudaStream_t)stream);
+}
+
+int fvc_entropy_decode_laplace(const void* stream_in, int64_t nbytes, int64_t n, const float* sigma, int mxrange,
+                               int lane_len, float* q_out, uint32_t* err_out, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(stream_in && sigma && q_out && err_out && n >= 1);
+    FVC_CUDA(cudaMemsetAsync(err_out, 0, 12, (cudaStream_t)stream));
+    return launch_rans_decode_laplace((const uint8_t*)stream_in, nbytes, n, lane_len, mxrange, sigma, q_out, err_out,
+                                      (cudaStream_t)stream);
+}
+
+int64_t fvc_entropy_stream_capacity(int64_t n, int lane_len) {
+    if (n < 0 || lane_len < 1) return FVC_ERR_ARG;
+    return (int64_t)entropy_stream_capacity(n, lane_len);
 }
 
 }  // extern "C"

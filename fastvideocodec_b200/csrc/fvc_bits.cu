@@ -4,6 +4,7 @@
 // are summed in a fixed order afterwards (deterministic).  Accurate libm-grade intrinsics are used
 // on purpose: p = F(q+.5)-F(q-.5) cancels, and the bpp parity gate is on the sum.
 #include "fvc_kernels.cuh"
+#include "fvc_bits.cuh"
 
 namespace fvc {
 
@@ -11,32 +12,10 @@ static const int kBitsThreads = 256;
 static const int kBitsMaxBlocks = 148 * 8;
 int bits_max_blocks() { return kBitsMaxBlocks; }
 
-__device__ __forceinline__ float softplusf(float x) {  // F.softplus(beta=1, threshold=20)
-    return x > 20.f ? x : log1pf(expf(x));
-}
-__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ float bits_of(float p) {  // clamp(-log(p+1e-5)/log(2), 0, 50)
-    float b = -1.0f * logf(p + 1e-5f) / 0.6931471805599453f;
-    return fminf(fmaxf(b, 0.f), 50.f);
-}
-
-// BitEstimator CDF (bitEstimator.py:20-42) with per-channel constants sp = softplus(h), ta = tanh(a)
-struct ChanParams {
-    float sp1, b1, ta1, sp2, b2, ta2, sp3, b3, ta3, sp4, b4;
-};
-__device__ __forceinline__ float factorized_cdf(float x, const ChanParams& c) {
-    x = x * c.sp1 + c.b1;
-    x = x + tanhf(x) * c.ta1;
-    x = x * c.sp2 + c.b2;
-    x = x + tanhf(x) * c.ta2;
-    x = x * c.sp3 + c.b3;
-    x = x + tanhf(x) * c.ta3;
-    return sigmoidf(x * c.sp4 + c.b4);
-}
-
 __global__ void __launch_bounds__(kBitsThreads)
 k_quant_bits_factorized(const float* __restrict__ x, int nhwc, int B, int C, int HW, FactorizedParams prm,
                         float* __restrict__ q_f32, ActT q_act, float* __restrict__ partials) {
+    pdl_sync();
     extern __shared__ float smf[];  // ChanParams[C]
     ChanParams* cp = reinterpret_cast<ChanParams*>(smf);
     __shared__ float red[32];
@@ -82,6 +61,7 @@ k_quant_bits_factorized(const float* __restrict__ x, int nhwc, int B, int C, int
 
 // zero the padding channels of an ACT record tensor (C..Cp-1), both halves
 __global__ void k_zero_pad_channels(ActT t, int C) {
+    pdl_sync();
     int pad = t.Cp - C;
     int64_t n = (int64_t)t.B * t.H * t.W * pad;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +74,7 @@ __global__ void k_zero_pad_channels(ActT t, int C) {
 static int zero_pad(ActT t, int C, cudaStream_t s) {
     if (!t.p || t.Cp == C) return 0;
     int64_t n = (int64_t)t.B * t.H * t.W * (t.Cp - C);
-    k_zero_pad_channels<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(t, C);
+    FVC_CUDA(launch_pdl(k_zero_pad_channels, (unsigned)cdiv64(n, 256), 256, 0, s, t, C));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -107,23 +87,19 @@ int launch_quant_bits_factorized(const float* x, int nhwc, int B, int C, int HW,
     int64_t n = (int64_t)B * C * HW;
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(cdiv64(n, kBitsThreads * 4), 1), kBitsMaxBlocks);
     size_t smem = (size_t)C * sizeof(ChanParams);
-    k_quant_bits_factorized<<<blocks, kBitsThreads, smem, s>>>(x, nhwc, B, C, HW, prm, q_f32, q_act, partials);
+    FVC_CUDA(launch_pdl(k_quant_bits_factorized, blocks, kBitsThreads, smem, s, x, nhwc, B, C, HW, prm, q_f32, q_act, partials));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     *nblocks = blocks;
     return zero_pad(q_act, C, s);
 }
 
-// Laplace(0, sigma).cdf(v) = 0.5 - 0.5*sign(v)*expm1(-|v|/sigma)   (torch.distributions.Laplace)
-__device__ __forceinline__ float laplace_cdf(float v, float sigma) {
-    float sgn = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
-    return 0.5f - 0.5f * sgn * expm1f(-fabsf(v) / sigma);
-}
 
 // x, sigma: fp32 NHWC [npix, C]; net.py:121-151
 __global__ void __launch_bounds__(kBitsThreads)
 k_quant_bits_laplace(const float* __restrict__ x, const float* __restrict__ sigma, int64_t n, int C,
                      float* __restrict__ q_f32, ActT q_act, float* __restrict__ partials) {
+    pdl_sync();
     __shared__ float red[32];
     float acc = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -148,7 +124,7 @@ int launch_quant_bits_laplace(const float* x, const float* sigma, int64_t n, int
                               float* partials, int* nblocks, cudaStream_t s) {
     FVC_ARG(!q_act.p || (q_act.parity == 0 && q_act.Cp >= C));
     int blocks = (int)std::min<int64_t>(std::max<int64_t>(cdiv64(n, kBitsThreads * 4), 1), kBitsMaxBlocks);
-    k_quant_bits_laplace<<<blocks, kBitsThreads, 0, s>>>(x, sigma, n, C, q_f32, q_act, partials);
+    FVC_CUDA(launch_pdl(k_quant_bits_laplace, blocks, kBitsThreads, 0, s, x, sigma, n, C, q_f32, q_act, partials));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     *nblocks = blocks;

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string>
 #include <algorithm>
+#include <utility>
 
 #include "../../include/fvc_b200.h"
 
@@ -130,6 +131,32 @@ __device__ __forceinline__ float block_sum(float v, float* smem32) {
     v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.f;
     if (w == 0) v = warp_sum(v);
     return v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the frame pipeline starts with pdl_sync() and is launched with
+// the programmatic-stream-serialization attribute, so its CTAs may become resident and run their prologue (barrier
+// init, TMEM allocation, descriptor prefetch, bias staging) while the previous kernel drains; griddepcontrol.wait
+// then blocks until the previous grid has completed and its writes are visible.  FVC_PDL=0 launches normally.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -42,6 +42,7 @@ __global__ void k_few_pack(const float* __restrict__ w, float* __restrict__ out,
 
 template <int K, int CO>
 __global__ void __launch_bounds__(128) k_conv_few(const __grid_constant__ FewParams P) {
+    pdl_sync();
     constexpr int TW = 32, TH = 16, PW = TW + K - 1, PH = TH + K - 1, R = K / 2;
     extern __shared__ float4 smf[];
     float4* patch = smf;                       // [PH][4][PW]
@@ -176,7 +177,7 @@ static int few_launch(const FewParams& P, cudaStream_t s) {
         attr.fetch_or(bit, std::memory_order_release);
     }
     dim3 grid(cdiv(P.W, 32), cdiv(P.H, 16), P.B);
-    k_conv_few<K, CO><<<grid, 128, smem, s>>>(P);
+    FVC_CUDA(launch_pdl(k_conv_few<K, CO>, grid, 128, smem, s, P));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;

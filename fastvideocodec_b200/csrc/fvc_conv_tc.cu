@@ -85,6 +85,7 @@ struct alignas(64) TcParams {
     int pair;         // CTA-pair mode: tcgen05 cta_group::2, M = 256 (two CTAs x 128 pixels), each CTA stages half of
                       // every weight tile; tiles_x then counts PAIRS of tiles along x
     int nab_log2;     // log2 of the number of partial-accumulator buffers in TMEM (2 or 4 buffers of CT columns)
+    int fast;         // precision 'fast': hi halves only (one MMA per product); ACT outputs are written without lo
     int merged;       // Cout <= 16: weight rows interleave 8-row blocks of w_hi and w_lo (MMA N = 32, two
                       // products per A read); the epilogue adds the two column blocks of every channel chunk
     int pitch;        // bytes per pixel of a record segment in shared memory: 128 (SWIZZLE_128B), or 32 for the
@@ -357,6 +358,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
     e16 *rec_out = nullptr, *rec_relu = nullptr, *rec_sq = nullptr;
     const e16* rec_res = nullptr;
     size_t pixC = 0;   // pixel index * Cout (fp32 NHWC tensors)
+    const bool wlo = P.fast == 0;   // precision 'fast': only the hi halves of ACT outputs are written
     uint32_t satm = 0; // running max |hi| of the ACT values this thread stores (range check, see ep_sat_track)
     auto enter_pixel = [&](int s) {
         cur_s = s;
@@ -493,17 +495,17 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
             }
             const int c0 = cc[j0];
             if (PAIR == 2) {
-                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store16_packed(rec_out, ep.out_act.Cp, c0, v, false, satm);
-                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store16_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm);
+                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store16_packed(rec_out, ep.out_act.Cp, c0, v, false, satm, wlo);
+                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store16_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm, wlo);
             } else {
-                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false, satm);
-                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm);
+                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false, satm, wlo);
+                if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm, wlo);
             }
             if (ep.out_act_sq.p && c0 < ep.out_act_sq.Cp) {   // squares for the following (I)GDN
 #pragma unroll
                 for (int q = 0; q < PAIR * 8; ++q) v[q] = v[q] * v[q] * ep.sq_scale;
-                if (PAIR == 2) ep_store16_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false, satm);
-                else ep_store8_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false, satm);
+                if (PAIR == 2) ep_store16_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false, satm, wlo);
+                else ep_store8_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false, satm, wlo);
             }
         }
     }
@@ -575,6 +577,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // everything above (barriers, TMEM allocation, bias staging: parameters only) overlapped the previous kernel's
+    // tail; from here on activations written by earlier kernels are read and buffers they read are overwritten
+    pdl_sync();
 
     // register re-allocation per warpgroup: the control warps need few registers, the accumulator warps many
     if (warp < TC_ACC_WARP0) {
@@ -687,6 +692,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 const uint32_t pa16 = lo0 + ((patch0 + set * P.patch_bytes) >> 4);
                 const int ntaps = ps.ntaps, gtaps = ps.gtaps;
                 const bool two = ps.nbt == 2, short2 = ps.ks1 != 4;   // second tile per tap / with 2 k-steps
+                const bool short1 = ps.ks0 == 2;                      // fast mode, 32-channel records: hi half only
                 const bool narrow = ps.ks0 == 1;                      // 8-channel records: one k-step per tile
                 const int32_t* toffp = P.tap_off + ps.tap_first;
                 int slot = 0;                   // tile index inside the current weight stage
@@ -767,7 +773,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         }
                         if (lead) {
                             // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
-                            if (j == 1 && short2) issue_stage<2, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
+                            if (j == 1 ? short2 : short1) issue_stage<2, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
                             else issue_stage<4, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
                         }
                         gacc0 = 1u;
@@ -1079,7 +1085,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, int Wout, const Epilogue& ep,
-                   TcPlan** out, cudaStream_t s) {
+                   TcPlan** out, cudaStream_t s, bool fast) {
     FVC_ARG(tc_supported(L, in.Cp));
     FVC_ARG(ep.gdn_beta == nullptr);
     FVC_ARG((L.st == 2) == (in.parity != 0));
@@ -1100,11 +1106,12 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // Cout <= 16 ("merged"): padded channels of the output records are never written (the buffers are
     // zero-initialised) and the MMA N = 32 carries w_hi and w_lo row blocks side by side.
     const int merge_max = env_int("FVC_TC_MERGED", 32);
-    const bool merged = (Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 0));
+    const bool merged = !fast && ((Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 0)));
     if (merged) chans = cdiv(L.Cout, 16) * 16;
     const int N = merged ? 2 * chans : std::max(16, cdiv(chans, 16) * 16);   // MMA N
     P.N = N;
     P.merged = merged ? 1 : 0;
+    P.fast = fast ? 1 : 0;
     P.nchunks = 0;
     P.Cout = L.Cout;
     P.nsub = L.nsub;
@@ -1250,7 +1257,14 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // ---- segment passes -----------------------------------------------------------------------------
     struct SegPass { int seg, nbt, ks0, ks1, kind0, kind1, c0; };
     std::vector<SegPass> segp;
-    if (merged) {
+    if (fast) {
+        // hi halves only.  Narrow records: the single K = 16 step [a_hi | a_lo] x [w_hi | w_hi] (a_lo * w_hi rides along
+        // for free); 32-channel records: the first two k-steps of the [hi | hi] tile, i.e. a_hi * w_hi.
+        if (Cp == 8) segp.push_back({0, 1, 1, 0, 4, 0, 0});
+        else if (Cp == 32) segp.push_back({0, 1, 2, 0, 2, 0, 0});
+        else if (Cp == 64) segp.push_back({0, 1, 4, 0, 0, 0, 0});
+        else { segp.push_back({0, 1, 4, 0, 0, 0, 0}); segp.push_back({1, 1, 4, 0, 0, 0, 64}); }
+    } else if (merged) {
         if (Cp == 8) segp.push_back({0, 1, 1, 0, 9, 0, 0});
         else if (Cp == 32) segp.push_back({0, 1, 4, 0, 8, 0, 0});
         else if (Cp == 64) { segp.push_back({0, 1, 4, 0, 6, 0, 0}); segp.push_back({1, 1, 4, 0, 7, 0, 0}); }
@@ -1283,7 +1297,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
                 {
                     // taps per accumulation group: keep every TMEM chain <= chain_max MMAs
                     const int per_tap = sp.ks0 + (sp.nbt == 2 ? sp.ks1 : 0);
-                    const int chain_max = env_int("FVC_TC_CHAIN", 48);
+                    const int chain_max = fast ? env_int("FVC_TC_CHAIN_FAST", 4096) : env_int("FVC_TC_CHAIN", 48);
                     ps.gtaps = (int8_t)std::max(1, std::min(127, chain_max / per_tap));
                 }
                 ps.tap_first = (int16_t)g.tap_first;
@@ -1297,7 +1311,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         sb.npass = npass - sb.pass_first;
         sb.ngroups = 0;
         {
-            const int chain_max = env_int("FVC_TC_CHAIN", 48);
+            const int chain_max = fast ? env_int("FVC_TC_CHAIN_FAST", 4096) : env_int("FVC_TC_CHAIN", 48);
             const bool span = env_int("FVC_TC_SPAN", 1) != 0;
             int chain = 0;
             for (int q = sb.pass_first; q < npass; ++q) {
@@ -1434,20 +1448,27 @@ static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
         FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set.fetch_or(bit, std::memory_order_release);
     }
-    if (PAIR) {
+    {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)plan->grid);
         cfg.blockDim = dim3(TC_THREADS);
         cfg.dynamicSmemBytes = plan->smem;
         cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;   // CTA pair = one cluster (same TPC)
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cudaLaunchAttribute at[2];
+        int na = 0;
+        if (PAIR) {
+            at[na].id = cudaLaunchAttributeClusterDimension;   // CTA pair = one cluster (same TPC)
+            at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        if (pdl_enabled()) {
+            at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_sync()
+            at[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
         cfg.attrs = at;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = na;
         FVC_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<NCH, RES, PAIR>, plan->P));
-    } else {
-        k_conv_tc<NCH, RES, PAIR><<<plan->grid, TC_THREADS, plan->smem, s>>>(plan->P);
     }
     g_launch_count++;
     FVC_CHECK_LAUNCH();

@@ -61,7 +61,8 @@ __device__ __forceinline__ uint32_t ep_sat_track(uint32_t satm, uint32_t hi) {
 __device__ __forceinline__ bool ep_sat_hit(uint32_t satm) {
     return (satm & 0xffffu) >= 0x7bffu || (satm >> 16) >= 0x7bffu;
 }
-__device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const float* v, bool relu, uint32_t& satm) {
+__device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const float* v, bool relu, uint32_t& satm,
+                                                 bool with_lo = true) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -77,7 +78,7 @@ __device__ __forceinline__ void ep_store8_packed(e16* rec, int Cp, int c0, const
         lo[j] = ep_pack2(a - ha, b - hb);
     }
     *reinterpret_cast<uint4*>(rec + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(rec + Cp + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (with_lo) *reinterpret_cast<uint4*>(rec + Cp + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // 16 channels at once: one 32-byte (full L2 sector) store for the hi halves and one for the lo halves.
@@ -108,12 +109,13 @@ __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
-__device__ __forceinline__ void ep_store16_packed(e16* rec, int Cp, int c0, const float* v16, bool relu, uint32_t& satm) {
+__device__ __forceinline__ void ep_store16_packed(e16* rec, int Cp, int c0, const float* v16, bool relu, uint32_t& satm,
+                                                  bool with_lo = true) {
     uint32_t hi[8], lo[8];
     ep_pack8(v16, relu, hi, lo, satm);
     ep_pack8(v16 + 8, relu, hi + 4, lo + 4, satm);
     st_global_v8(rec + c0, hi);
-    st_global_v8(rec + Cp + c0, lo);
+    if (with_lo) st_global_v8(rec + Cp + c0, lo);   // precision 'fast' keeps the (zero-initialised) lo halves untouched
 }
 
 __device__ __forceinline__ float ep_act(float v, int act) {

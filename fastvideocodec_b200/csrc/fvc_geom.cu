@@ -73,6 +73,7 @@ __device__ __forceinline__ float warp_sample(const float* __restrict__ plane, in
 // avg_pool2d(2,2) on planar fp32
 // ----------------------------------------------------------------------------------------------
 __global__ void k_avg_pool2_planar(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W) {
+    pdl_sync();
     int Wo = W >> 1, Ho = H >> 1;
     int64_t n = (int64_t)planes * Ho * Wo;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,7 +89,7 @@ __global__ void k_avg_pool2_planar(const float* __restrict__ x, float* __restric
 int launch_avg_pool2_planar(const float* x, float* y, int planes, int H, int W, cudaStream_t s) {
     int64_t n = (int64_t)planes * (H / 2) * (W / 2);
     if (n == 0) return 0;
-    k_avg_pool2_planar<<<LAUNCH_1D(n, 256), 0, s>>>(x, y, planes, H, W);
+    FVC_CUDA(launch_pdl(k_avg_pool2_planar, LAUNCH_1D(n, 256), 0, s, x, y, planes, H, W));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -199,6 +200,7 @@ __device__ __forceinline__ void store_record(const ActT& t, e16* rec, const floa
 // ----------------------------------------------------------------------------------------------
 __global__ void k_spynet_prep(const float* __restrict__ im1, const float* __restrict__ im2,
                               const float* __restrict__ flow_prev, ActT X, float* __restrict__ flow_up) {
+    pdl_sync();
     int H = X.H, W = X.W;
     int64_t n = (int64_t)X.B * H * W;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,7 +238,7 @@ int launch_spynet_prep(const float* im1, const float* im2, const float* flow_pre
                        cudaStream_t s) {
     FVC_ARG(X.Cp == 32 || X.Cp == 8);
     int64_t n = (int64_t)X.B * X.H * X.W;
-    k_spynet_prep<<<LAUNCH_1D(n, 128), 0, s>>>(im1, im2, flow_prev, X, flow_up);
+    FVC_CUDA(launch_pdl(k_spynet_prep, LAUNCH_1D(n, 128), 0, s, im1, im2, flow_prev, X, flow_up));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -247,6 +249,7 @@ int launch_spynet_prep(const float* im1, const float* im2, const float* flow_pre
 // ----------------------------------------------------------------------------------------------
 __global__ void k_mc_prep(const float* __restrict__ ref, const float* __restrict__ mv, float* __restrict__ warpframe,
                           ActT X) {
+    pdl_sync();
     int H = X.H, W = X.W;
     int64_t n = (int64_t)X.B * H * W;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,7 +274,7 @@ __global__ void k_mc_prep(const float* __restrict__ ref, const float* __restrict
 int launch_mc_prep(const float* ref, const float* mv, float* warpframe, ActT X, cudaStream_t s) {
     FVC_ARG(X.Cp == 32 || X.Cp == 8);
     int64_t n = (int64_t)X.B * X.H * X.W;
-    k_mc_prep<<<LAUNCH_1D(n, 128), 0, s>>>(ref, mv, warpframe, X);
+    FVC_CUDA(launch_pdl(k_mc_prep, LAUNCH_1D(n, 128), 0, s, ref, mv, warpframe, X));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -280,6 +283,7 @@ int launch_mc_prep(const float* ref, const float* mv, float* warpframe, ActT X, 
 // prediction = warpnet(x) + warpframe (net.py:67); residual = input - prediction (net.py:81)
 __global__ void k_mc_finish(const float* __restrict__ res, const float* __restrict__ warpframe,
                             const float* __restrict__ cur, float* __restrict__ pred, ActT R) {
+    pdl_sync();
     int H = R.H, W = R.W;
     int64_t n = (int64_t)R.B * H * W;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,7 +307,7 @@ int launch_mc_finish(const float* res, const float* warpframe, const float* cur,
                      cudaStream_t s) {
     FVC_ARG(R.Cp == 32 || R.Cp == 8);
     int64_t n = (int64_t)R.B * R.H * R.W;
-    k_mc_finish<<<LAUNCH_1D(n, 128), 0, s>>>(res, warpframe, cur, pred, R);
+    FVC_CUDA(launch_pdl(k_mc_finish, LAUNCH_1D(n, 128), 0, s, res, warpframe, cur, pred, R));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -341,6 +345,7 @@ __device__ __forceinline__ void store8(e16* rec, int Cp, int c8, const float* v)
 
 // AvgPool2d(2,2) on ACT (Warp_net c0_p / c1_p, endecoder.py:286-288) + optional relu copy
 __global__ void k_pool_act(ActT in, ActT out, ActT out_relu) {
+    pdl_sync();
     int G = out.Cp >> 3;
     int64_t n = (int64_t)out.B * out.H * out.W * G;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,49 +372,59 @@ __global__ void k_pool_act(ActT in, ActT out, ActT out_relu) {
 int launch_pool_act(ActT in, ActT out, ActT out_relu, cudaStream_t s) {
     FVC_ARG(in.Cp == out.Cp && in.H == 2 * out.H && in.W == 2 * out.W);
     int64_t n = (int64_t)out.B * out.H * out.W * (out.Cp / 8);
-    k_pool_act<<<LAUNCH_1D(n, 256), 0, s>>>(in, out, out_relu);
+    FVC_CUDA(launch_pdl(k_pool_act, LAUNCH_1D(n, 256), 0, s, in, out, out_relu));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
 }
 
-// out = skip + bilinearupsacling2(low) (align_corners=True; endecoder.py:291, 293) + optional relu copy
-__global__ void k_upadd_act(ActT low, ActT skip, ActT out, ActT out_relu) {
-    int G = out.Cp >> 3;
-    int64_t n = (int64_t)out.B * out.H * out.W * G;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int g = (int)(i % G);
-    int64_t pix = i / G;
-    int x = (int)(pix % out.W);
-    int y = (int)((pix / out.W) % out.H);
-    int b = (int)(pix / ((int64_t)out.W * out.H));
+// out = skip + bilinearupsacling2(low) (align_corners=True; endecoder.py:291, 293) + optional relu copy.
+// Block = 32 output pixels of one image row x 8 channel groups (16-byte hi + 16-byte lo vectors): 8 consecutive
+// lanes cover the 128-byte hi (and lo) half of a 64-channel record, so every warp access is four full lines.  Row
+// and batch come from blockIdx (no 64-bit divisions: the first version spent more issue slots on index arithmetic
+// than on the 14 memory instructions and reached 53 % of the HBM rate).
+__global__ void __launch_bounds__(256) k_upadd_act(ActT low, ActT skip, ActT out, ActT out_relu) {
+    pdl_sync();
+    const int G = out.Cp >> 3;                       // 8-channel groups per record (8 for the 64-channel Warp_net)
+    const int ppb = 256 / G;                         // pixels per block
+    const int g = (int)threadIdx.x % G;
+    const int x = (int)blockIdx.x * ppb + (int)threadIdx.x / G;
+    const int y = (int)blockIdx.y % out.H;
+    const int b = (int)blockIdx.y / out.H;
+    if (x >= out.W) return;
     int x0, x1, y0, y1;
     float lx, ly;
     up2_index(x, low.W, 1, x0, x1, lx);
     up2_index(y, low.H, 1, y0, y1, ly);
     float v00[8], v01[8], v10[8], v11[8], sk[8], r[8];
-    load8(low.p + act_pixel_offset(low, b, y0, x0), low.Cp, g, v00);
-    load8(low.p + act_pixel_offset(low, b, y0, x1), low.Cp, g, v01);
-    load8(low.p + act_pixel_offset(low, b, y1, x0), low.Cp, g, v10);
-    load8(low.p + act_pixel_offset(low, b, y1, x1), low.Cp, g, v11);
-    load8(skip.p + act_pixel_offset(skip, b, y, x), skip.Cp, g, sk);
+    const e16* lrow0 = low.p + act_pixel_offset(low, b, y0, 0);
+    const e16* lrow1 = low.p + act_pixel_offset(low, b, y1, 0);
+    const size_t lrec = (size_t)2 * low.Cp;
+    const size_t opix = act_pixel_offset(out, b, y, x);   // skip / out / out_relu share the geometry (checked on the host)
+    load8(lrow0 + x0 * lrec, low.Cp, g, v00);
+    load8(lrow0 + x1 * lrec, low.Cp, g, v01);
+    load8(lrow1 + x0 * lrec, low.Cp, g, v10);
+    load8(lrow1 + x1 * lrec, low.Cp, g, v11);
+    load8(skip.p + opix, skip.Cp, g, sk);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float up = (1.f - ly) * ((1.f - lx) * v00[j] + lx * v01[j]) + ly * ((1.f - lx) * v10[j] + lx * v11[j]);
         r[j] = sk[j] + up;
     }
-    store8(out.p + act_pixel_offset(out, b, y, x), out.Cp, g, r);
+    store8(out.p + opix, out.Cp, g, r);
     if (out_relu.p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = fmaxf(r[j], 0.f);
-        store8(out_relu.p + act_pixel_offset(out_relu, b, y, x), out_relu.Cp, g, r);
+        store8(out_relu.p + opix, out_relu.Cp, g, r);
     }
 }
 int launch_upadd_act(ActT low, ActT skip, ActT out, ActT out_relu, cudaStream_t s) {
     FVC_ARG(low.Cp == out.Cp && skip.Cp == out.Cp && out.H == 2 * low.H && out.W == 2 * low.W);
-    int64_t n = (int64_t)out.B * out.H * out.W * (out.Cp / 8);
-    k_upadd_act<<<LAUNCH_1D(n, 256), 0, s>>>(low, skip, out, out_relu);
+    FVC_ARG(!out.parity && !skip.parity && !low.parity && (!out_relu.p || (!out_relu.parity && out_relu.Cp == out.Cp)));
+    FVC_ARG(skip.H == out.H && skip.W == out.W && (256 % (out.Cp / 8)) == 0 && (int64_t)out.B * out.H <= 65535);
+    const int ppb = 256 / (out.Cp / 8);
+    FVC_CUDA(launch_pdl(k_upadd_act, dim3((unsigned)cdiv(out.W, ppb), (unsigned)(out.B * out.H)), dim3(256), 0, s, low,
+                        skip, out, out_relu));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -503,6 +518,7 @@ int launch_gdn_act(ActT in, int C, const float* beta_eff, const float* gamma_eff
 __global__ void k_recon_losses(const float* __restrict__ cur, const float* __restrict__ pred,
                                const float* __restrict__ warp, const float* __restrict__ res, int res_nhwc3, int B,
                                int HW, float* __restrict__ clipped, float* __restrict__ partials, int clip_mse) {
+    pdl_sync();
     __shared__ float red[32];
     int64_t n = (int64_t)B * 3 * HW;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -540,7 +556,7 @@ int launch_recon_losses(const float* cur, const float* pred, const float* warp, 
     int64_t n = (int64_t)B * 3 * HW;
     int blocks = (int)std::min<int64_t>(cdiv64(n, 256 * 4), 148 * 8);
     if (blocks < 1) blocks = 1;
-    k_recon_losses<<<blocks, 256, 0, s>>>(cur, pred, warp, res, res_nhwc3, B, HW, clipped, partials, clip_mse);
+    FVC_CUDA(launch_pdl(k_recon_losses, blocks, 256, 0, s, cur, pred, warp, res, res_nhwc3, B, HW, clipped, partials, clip_mse));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     *nblocks_out = blocks;
@@ -550,6 +566,7 @@ int launch_recon_losses(const float* cur, const float* pred, const float* warp, 
 // partials: [n][groups] -> out[g] = scale * sum_n (double accumulation, fixed order: deterministic)
 __global__ void k_reduce_partials(const float* __restrict__ partials, int n, int groups, double scale,
                                   float* __restrict__ out) {
+    pdl_sync();
     int g = blockIdx.x;
     __shared__ double sh[256];
     double acc = 0.0;
@@ -563,7 +580,7 @@ __global__ void k_reduce_partials(const float* __restrict__ partials, int n, int
     if (threadIdx.x == 0) out[g] = (float)(sh[0] * scale);
 }
 int launch_reduce_partials(const float* partials, int n, int groups, double scale, float* out, cudaStream_t s) {
-    k_reduce_partials<<<groups, 256, 0, s>>>(partials, n, groups, scale, out);
+    FVC_CUDA(launch_pdl(k_reduce_partials, groups, 256, 0, s, partials, n, groups, scale, out));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -573,6 +590,7 @@ int launch_reduce_partials(const float* partials, int n, int groups, double scal
 // scalars7 = mse, warploss, interloss, bpp_feature, bpp_z, bpp_mv, bpp   (net.py:212-220)
 __global__ void k_finalize_scalars(const float* __restrict__ sums6, float n_pix, float* __restrict__ out,
                                    const unsigned int* __restrict__ sat_count) {
+    pdl_sync();
     if (threadIdx.x == 0) {
         if (sat_count && *sat_count) {
             // an activation left the fp16 operand-pair range and was clamped somewhere upstream: fail loudly
@@ -591,7 +609,7 @@ __global__ void k_finalize_scalars(const float* __restrict__ sums6, float n_pix,
 }
 int launch_finalize_scalars(const float* sums6, float n_pix, float* scalars7, const unsigned int* sat_count,
                             cudaStream_t s) {
-    k_finalize_scalars<<<1, 32, 0, s>>>(sums6, n_pix, scalars7, sat_count);
+    FVC_CUDA(launch_pdl(k_finalize_scalars, 1, 32, 0, s, sums6, n_pix, scalars7, sat_count));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -601,6 +619,7 @@ int launch_finalize_scalars(const float* sums6, float n_pix, float* scalars7, co
 // layout conversion
 // ----------------------------------------------------------------------------------------------
 __global__ void k_nchw_to_act(const float* __restrict__ x, ActT out, int C, int do_abs) {
+    pdl_sync();
     int64_t n = (int64_t)out.B * out.H * out.W * out.Cp;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -616,12 +635,13 @@ __global__ void k_nchw_to_act(const float* __restrict__ x, ActT out, int C, int 
 }
 int launch_nchw_to_act(const float* x, ActT out, int C, int do_abs, cudaStream_t s) {
     int64_t n = (int64_t)out.B * out.H * out.W * out.Cp;
-    k_nchw_to_act<<<LAUNCH_1D(n, 256), 0, s>>>(x, out, C, do_abs);
+    FVC_CUDA(launch_pdl(k_nchw_to_act, LAUNCH_1D(n, 256), 0, s, x, out, C, do_abs));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
 }
 __global__ void k_nhwc_to_act(const float* __restrict__ x, ActT out, int C, int do_abs) {
+    pdl_sync();
     int64_t n = (int64_t)out.B * out.H * out.W * out.Cp;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -637,7 +657,7 @@ __global__ void k_nhwc_to_act(const float* __restrict__ x, ActT out, int C, int 
 }
 int launch_nhwc_to_act(const float* x, ActT out, int C, int do_abs, cudaStream_t s) {
     int64_t n = (int64_t)out.B * out.H * out.W * out.Cp;
-    k_nhwc_to_act<<<LAUNCH_1D(n, 256), 0, s>>>(x, out, C, do_abs);
+    FVC_CUDA(launch_pdl(k_nhwc_to_act, LAUNCH_1D(n, 256), 0, s, x, out, C, do_abs));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;

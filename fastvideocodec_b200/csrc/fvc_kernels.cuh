@@ -55,6 +55,24 @@ int launch_gaussian_forward(const float* x, const float* scales, const float* me
                             float* partials, int* nblocks, int64_t n, cudaStream_t s);
 int bits_max_blocks();
 
+// ---- entropy coding of the quantised latents (fvc_entropy.cu; net.py:123-138, 155-168, 183-195) ------------
+// R = mxrange (150): symbols s = q + R in [0, 2R-2]; tables are uint32 [C][2R] / [n][2R]; L = symbols per rANS lane
+size_t entropy_stream_capacity(int64_t n, int L);   // bytes
+size_t entropy_words_capacity(int64_t n, int L);    // 16-bit words of scratch
+int launch_cdf_table_factorized(FactorizedParams prm, int C, int R, uint32_t* table, cudaStream_t s);
+int launch_cdf_table_laplace(const float* sigma, int64_t n, int R, uint32_t* table, cudaStream_t s);
+int launch_sym_factorized(const float* x, int64_t n, int C, int R, const uint32_t* table, uint32_t* packed,
+                          unsigned int* err, cudaStream_t s);
+int launch_sym_laplace(const float* x, const float* sigma, int64_t n, int R, uint32_t* packed, unsigned int* err,
+                       cudaStream_t s);
+int launch_rans_encode(const uint32_t* packed, int64_t n, int L, uint16_t* words, uint32_t* lane_words, uint8_t* out,
+                       uint32_t* total_bytes, cudaStream_t s);
+int launch_rans_decode_factorized(const uint8_t* stream, int64_t nbytes, int64_t n, int L, int C, int R,
+                                  const uint32_t* table, float* q_out, unsigned int* err, cudaStream_t s);
+int launch_rans_decode_laplace(const uint8_t* stream, int64_t nbytes, int64_t n, int L, int R, const float* sigma,
+                               float* q_out, unsigned int* err, cudaStream_t s);
+int launch_bytes_to_bits(const uint32_t* nbytes, const unsigned int* err, float* bits, cudaStream_t s);
+
 // ---- convolution engines ---------------------------------------------------------------------
 // SIMT: packed fp32 weights [sub][tap][CinP][CoutS]
 struct SimtWeights {
@@ -75,8 +93,9 @@ int launch_conv_few(const ConvLayer& L, const float* w_packed, const float* bias
 
 // TC (tcgen05): packed bf16 hi/lo weight stream + TMA descriptors (fvc_conv_tc.cu)
 struct TcPlan;  // opaque
+// fast = 1: one MMA per product on the hi halves only (fp16 operands, ~11 significant bits), ACT outputs carry hi only
 int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, int Wout, const Epilogue& ep,
-                   TcPlan** plan, cudaStream_t s);
+                   TcPlan** plan, cudaStream_t s, bool fast = false);
 int tc_plan_launch(TcPlan* plan, cudaStream_t s);
 void tc_plan_destroy(TcPlan* plan);
 bool tc_supported(const ConvLayer& L, int CinP);

@@ -14,6 +14,12 @@ namespace fvc {
 thread_local std::string g_err;
 thread_local int64_t g_launch_count = 0;
 
+bool pdl_enabled() {
+    // opt-in: measured neutral to -1 % on the power-capped 1080p frame (profiles/r02_pdl_ab.txt)
+    static const bool on = [] { const char* v = getenv("FVC_PDL"); return v && v[0] == '1'; }();
+    return on;
+}
+
 void set_error(const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -124,6 +130,17 @@ struct fvc_ctx {
     // number of epilogue tiles that produced an activation at or beyond the fp16 pair range (|v| >= 65504):
     // those values were clamped, the results are wrong; scalars turn NaN and the host entry points fail
     unsigned int* sat_count = nullptr;
+    // real entropy coding (calrealbits, net.py:123-138 / 155-168 / 183-195): allocated on first use
+    int realbits = 0, mxrange = 150, rans_L = 8192;
+    uint32_t *cdf_tab_mv = nullptr, *cdf_tab_z = nullptr;   // [C][2R] integer CDFs of the two BitEstimators
+    uint32_t* sym_packed = nullptr;                          // start | freq << 16 per symbol (largest latent)
+    uint16_t* rans_words = nullptr;
+    uint32_t* rans_lane_words = nullptr;
+    uint8_t* stream[3] = {nullptr, nullptr, nullptr};        // 0: feature, 1: z, 2: mv
+    size_t stream_cap[3] = {0, 0, 0};
+    uint32_t* stream_bytes = nullptr;                        // device [3]
+    unsigned int* ent_err = nullptr;                         // device [3]: out-of-range symbols, empty intervals, bad lanes
+    int ent_R = 0, ent_L = 0;
 
     template <typename T>
     int alloc(T** p, size_t bytes) {
@@ -157,7 +174,7 @@ static int build_layers(fvc_ctx* c) {
     char buf[128];
     // records of the network's input layers (<= 8 real channels): narrow [hi 8 | lo 8] records on the
     // tensor-core engine (one 16-element k-step per tap and product pair instead of a 32-channel padded one)
-    const int cin_narrow = c->impl == FVC_IMPL_TC ? 8 : 32;
+    const int cin_narrow = c->impl != FVC_IMPL_SIMT ? 8 : 32;
     c->cp_narrow = cin_narrow;
     const int sp[5][2] = {{8, 32}, {32, 64}, {64, 32}, {32, 16}, {16, 2}};
     for (int l = 0; l < c->levels; ++l)
@@ -389,12 +406,12 @@ static int run_conv(fvc_ctx* c, const std::string& name, ActT in, int Hout, int 
     ep.sat_count = c->sat_count;
     ProfScope prof(c, name, s);
     int rc;
-    if (c->impl == FVC_IMPL_TC && c->use_few && r.few_w && !in.parity && ep.act == FVC_ACT_NONE && !ep.res_act.p &&
+    if (c->impl != FVC_IMPL_SIMT && c->use_few && r.few_w && !in.parity && ep.act == FVC_ACT_NONE && !ep.res_act.p &&
         !ep.out_act_relu.p && !ep.out_act_sq.p && ep.out_f32) {
         rc = launch_conv_few(r.L, r.few_w, r.bias, in, Hout, Wout, ep, s);
-    } else if (c->impl == FVC_IMPL_TC && tc_supported(r.L, r.CinP)) {
+    } else if (c->impl != FVC_IMPL_SIMT && tc_supported(r.L, r.CinP)) {
         if (!r.tc) {
-            rc = tc_plan_create(r.L, r.w_raw, in, Hout, Wout, ep, &r.tc, s);
+            rc = tc_plan_create(r.L, r.w_raw, in, Hout, Wout, ep, &r.tc, s, c->impl == FVC_IMPL_TC_FAST);
             if (rc) return rc;
         }
         rc = tc_plan_launch(r.tc, s);
@@ -420,7 +437,7 @@ static int run_conv_gdn(fvc_ctx* c, const std::string& conv, const std::string& 
     ConvRt& r = c->conv[conv];
     Epilogue ep = make_ep(r);
     ep.out_act = raw;
-    const bool tc = c->impl == FVC_IMPL_TC;
+    const bool tc = c->impl != FVC_IMPL_SIMT;
     // squares are stored scaled by 2^-6 so that |x| up to ~2000 stays inside the fp16 range of the hi half
     const float sq_scale = 1.f / 64.f;
     if (tc) {
@@ -455,6 +472,56 @@ static int res_block(fvc_ctx* c, int idx, ActT x_relu, ActT x_skip, ActT tmp, Ac
     ep.out_act = out;
     ep.out_act_relu = out_relu;
     return run_conv(c, n2, tmp, out.H, out.W, ep, s);
+}
+
+// ---- real entropy coding --------------------------------------------------------------------------------
+static int64_t latent_count(fvc_ctx* c, int which) {   // 0: feature [B,96,H/16,W/16], 1: z [B,64,H/64,W/64], 2: mv [B,128,..]
+    const int64_t p16 = (int64_t)c->B * (c->H / 16) * (c->W / 16), p64 = (int64_t)c->B * (c->H / 64) * (c->W / 64);
+    return which == 0 ? p16 * 96 : (which == 1 ? p64 * 64 : p16 * 128);
+}
+static int ensure_entropy_buffers(fvc_ctx* c) {
+    if (c->sym_packed && c->ent_R == c->mxrange && c->ent_L == c->rans_L) return 0;
+    if (c->sym_packed) {
+        set_error("mxrange / lane length of a context cannot change once entropy coding was used");
+        return FVC_ERR_STATE;
+    }
+    const int R = c->mxrange, L = c->rans_L;
+    const int64_t nmax = latent_count(c, 2);
+    if (c->alloc(&c->cdf_tab_mv, (size_t)128 * 2 * R * 4) || c->alloc(&c->cdf_tab_z, (size_t)64 * 2 * R * 4) ||
+        c->alloc(&c->sym_packed, (size_t)nmax * 4) || c->alloc(&c->rans_words, entropy_words_capacity(nmax, L) * 2) ||
+        c->alloc(&c->rans_lane_words, (size_t)cdiv64(nmax, L) * 4) || c->alloc(&c->stream_bytes, 16) ||
+        c->alloc(&c->ent_err, 16))
+        return FVC_ERR_CUDA;
+    for (int k = 0; k < 3; ++k) {
+        c->stream_cap[k] = entropy_stream_capacity(latent_count(c, k), L);
+        if (c->alloc(&c->stream[k], c->stream_cap[k])) return FVC_ERR_CUDA;
+    }
+    c->ent_R = R; c->ent_L = L;
+    return 0;
+}
+static FactorizedParams be_params(const BitEstRt& be) {
+    FactorizedParams prm;
+    for (int i = 0; i < 11; ++i) prm.p[i] = be.p[i];
+    return prm;
+}
+// which = 1 (z) or 2 (mv): x is the pre-round latent, fp32 NHWC
+static int encode_factorized(fvc_ctx* c, int which, const float* x, cudaStream_t s) {
+    int rc;
+    const BitEstRt& be = which == 1 ? c->be_z : c->be_mv;
+    uint32_t* tab = which == 1 ? c->cdf_tab_z : c->cdf_tab_mv;
+    const int64_t n = latent_count(c, which);
+    PK(which == 1 ? "@entropy_encode:z" : "@entropy_encode:mv", launch_cdf_table_factorized(be_params(be), be.C, c->mxrange, tab, s));
+    rc = launch_sym_factorized(x, n, be.C, c->mxrange, tab, c->sym_packed, c->ent_err, s);
+    if (rc) return rc;
+    return launch_rans_encode(c->sym_packed, n, c->rans_L, c->rans_words, c->rans_lane_words, c->stream[which],
+                              c->stream_bytes + which, s);
+}
+static int encode_laplace(fvc_ctx* c, cudaStream_t s) {
+    int rc;
+    const int64_t n = latent_count(c, 0);
+    PK("@entropy_encode:feature", launch_sym_laplace(c->feature, c->sigma, n, c->mxrange, c->sym_packed, c->ent_err, s));
+    return launch_rans_encode(c->sym_packed, n, c->rans_L, c->rans_words, c->rans_lane_words, c->stream[0],
+                              c->stream_bytes + 0, s);
 }
 
 // mvDecoder (synthesis_mv.py:71-79): c->quant_mv (ACT) -> c->mv_hat (fp32 NHWC2)
@@ -533,6 +600,7 @@ static int forward_mv(fvc_ctx* c, const float* cur, const float* ref, int* nb_mv
         PK("@k_quant_bits_factorized:mv", launch_quant_bits_factorized(c->mvfeature, 1, B, 128, (H / 16) * (W / 16), prm, nullptr, c->quant_mv,
                                        c->bits_partials + 2 * maxb, &nb_mv, s));
     }
+    if (c->realbits) R(encode_factorized(c, 2, c->mvfeature, s));                     // net.py:183-195
     if (c->force_q[0]) R(launch_nchw_to_act(c->force_q[0], c->quant_mv, 128, 0, s));   // teacher forcing
     *nb_mv_out = nb_mv;
     R(run_mv_decoder(c, s));
@@ -570,6 +638,23 @@ static int run_motion_comp(fvc_ctx* c, const float* cur, const float* ref, cudaS
     PK("@k_mc_finish", launch_mc_finish(c->wres, c->warpframe, cur ? cur : ref, c->prediction, c->residual, s));
 #undef R
     return 0;
+}
+
+// hyper-prior decoder (synthesis_prior.py:42-58): c->z_hat (ACT) -> c->sigma (fp32 NHWC96)
+static int run_prior_decoder(fvc_ctx* c, cudaStream_t s) {
+    const int H = c->H, W = c->W;
+    int rc;
+    Epilogue ep = make_ep(c->conv["respriorDecoder.deconv1"]);
+    ep.out_act = c->s1;
+    rc = run_conv(c, "respriorDecoder.deconv1", c->z_hat, H / 32, W / 32, ep, s);
+    if (rc) return rc;
+    ep = make_ep(c->conv["respriorDecoder.deconv2"]);
+    ep.out_act = c->s2;
+    rc = run_conv(c, "respriorDecoder.deconv2", c->s1, H / 16, W / 16, ep, s);
+    if (rc) return rc;
+    ep = make_ep(c->conv["respriorDecoder.deconv3"]);
+    ep.out_f32 = c->sigma;
+    return run_conv(c, "respriorDecoder.deconv3", c->s2, H / 16, W / 16, ep, s);
 }
 
 // residual decoder (synthesis.py:54-58): c->feat_hat (ACT) -> c->recon_res (fp32 NHWC3)
@@ -625,20 +710,12 @@ static int forward_mc_res(fvc_ctx* c, const float* cur, const float* ref, float*
         PK("@k_quant_bits_factorized:z", launch_quant_bits_factorized(c->z, 1, B, 64, (H / 64) * (W / 64), prm, nullptr, c->z_hat,
                                        c->bits_partials + 1 * maxb, &nb_z, s));
     }
+    if (c->realbits) R(encode_factorized(c, 1, c->z, s));                           // net.py:155-168
     if (c->force_q[1]) R(launch_nchw_to_act(c->force_q[1], c->z_hat, 64, 0, s));   // teacher forcing
-    {
-        Epilogue ep = make_ep(c->conv["respriorDecoder.deconv1"]);
-        ep.out_act = c->s1;
-        R(run_conv(c, "respriorDecoder.deconv1", c->z_hat, H / 32, W / 32, ep, s));
-        ep = make_ep(c->conv["respriorDecoder.deconv2"]);
-        ep.out_act = c->s2;
-        R(run_conv(c, "respriorDecoder.deconv2", c->s1, H / 16, W / 16, ep, s));
-        ep = make_ep(c->conv["respriorDecoder.deconv3"]);
-        ep.out_f32 = c->sigma;
-        R(run_conv(c, "respriorDecoder.deconv3", c->s2, H / 16, W / 16, ep, s));
-    }
+    R(run_prior_decoder(c, s));
     PK("@k_quant_bits_laplace", launch_quant_bits_laplace(c->feature, c->sigma, (int64_t)B * (H / 16) * (W / 16) * 96, 96, nullptr,
                                 c->feat_hat, c->bits_partials + 0 * maxb, &nb_f, s));
+    if (c->realbits) R(encode_laplace(c, s));                                         // net.py:123-138
     if (c->force_q[2]) R(launch_nchw_to_act(c->force_q[2], c->feat_hat, 96, 0, s));   // teacher forcing
     R(run_res_decoder(c, s));
     // ---- reconstruction, distortion, rate (net.py:103-116, 207-217) -------------------------------
@@ -664,6 +741,10 @@ static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_
     if (rc) return rc;
     rc = launch_reduce_partials(c->bits_partials + 2 * bits_max_blocks(), nb_mv, 1, 1.0, c->scalars + 5, s);
     if (rc) return rc;
+    if (c->realbits) {   // total_bits = real_bits (net.py:147-149, 172-174, 200-202): 8 x bytes of the three streams
+        for (int k = 0; k < 3 && !rc; ++k) rc = launch_bytes_to_bits(c->stream_bytes + k, c->ent_err, c->scalars + 3 + k, s);
+        if (rc) return rc;
+    }
     return launch_finalize_scalars(c->scalars, (float)((double)B * H * W), scalars_out, c->sat_count, s);
 }
 
@@ -679,7 +760,7 @@ int fvc_version(void) { return 200; }
 
 fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl) {
     if (B < 1 || H < 64 || W < 64 || (H % 64) || (W % 64) || levels < 1 || levels > 6 ||
-        (impl != FVC_IMPL_SIMT && impl != FVC_IMPL_TC)) {
+        (impl != FVC_IMPL_SIMT && impl != FVC_IMPL_TC && impl != FVC_IMPL_TC_FAST)) {
         set_error("fvc_ctx_create: bad geometry B=%d H=%d W=%d levels=%d impl=%d (H, W must be multiples of 64)", B,
                   H, W, levels, impl);
         return nullptr;
@@ -925,6 +1006,87 @@ int64_t fvc_ctx_saturation_count(fvc_ctx* c, int reset, void* stream) {
     FVC_CUDA(cudaStreamSynchronize(s));
     if (reset) FVC_CUDA(cudaMemsetAsync(c->sat_count, 0, 4, s));
     return (int64_t)h;
+}
+
+/* calrealbits (net.py:57, 123-138, 155-168, 183-195) */
+int fvc_ctx_set_realbits(fvc_ctx* c, int enable, int mxrange) {
+    FVC_ARG(c != nullptr && mxrange >= 2 && mxrange <= 16384);
+    if (enable) {
+        c->mxrange = mxrange;
+        int rc = ensure_entropy_buffers(c);
+        if (rc) return rc;
+    }
+    c->realbits = enable ? 1 : 0;
+    return 0;
+}
+
+int64_t fvc_ctx_get_bitstream(fvc_ctx* c, int which, void* out_host, int64_t capacity, void* stream) {
+    if (!c || which < 0 || which > 2 || !c->sym_packed) {
+        set_error("fvc_ctx_get_bitstream: no bitstream (enable fvc_ctx_set_realbits and run a forward first)");
+        return FVC_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t nb = 0;
+    unsigned int err[3] = {0, 0, 0};
+    FVC_CUDA(cudaMemcpyAsync(&nb, c->stream_bytes + which, 4, cudaMemcpyDeviceToHost, s));
+    FVC_CUDA(cudaMemcpyAsync(err, c->ent_err, 12, cudaMemcpyDeviceToHost, s));
+    FVC_CUDA(cudaStreamSynchronize(s));
+    if (err[0] || err[1]) {
+        set_error("entropy coding: %u symbols outside [-mxrange, mxrange-2] (the reference's torchac call raises on these), "
+                  "%u empty probability intervals", err[0], err[1]);
+        cudaMemsetAsync(c->ent_err, 0, 12, s);
+        return FVC_ERR_STATE;
+    }
+    if (out_host) {
+        if ((int64_t)nb > capacity) { set_error("fvc_ctx_get_bitstream: capacity %lld < %u bytes", (long long)capacity, nb); return FVC_ERR_ARG; }
+        FVC_CUDA(cudaMemcpyAsync(out_host, c->stream[which], nb, cudaMemcpyDeviceToHost, s));
+        FVC_CUDA(cudaStreamSynchronize(s));
+    }
+    return (int64_t)nb;
+}
+
+/* The decoder of the codec: the three byte streams (device pointers) -> latents -> fvc_decode_from_latents' path.
+ * Order as a receiver must do it: z (factorized) -> sigma = respriorDecoder(z_hat) -> feature (Laplace(0, sigma)) ; mv. */
+int fvc_decode_bitstreams(fvc_ctx* c, const float* ref, const void* feat_stream, int64_t feat_bytes,
+                          const void* z_stream, int64_t z_bytes, const void* mv_stream, int64_t mv_bytes, float* recon_out,
+                          void* stream) {
+    FVC_ARG(c && ref && feat_stream && z_stream && mv_stream && recon_out);
+    if (fvc_ctx_missing_params(c) != 0) {
+        set_error("fvc_decode_bitstreams: %d parameters not set", fvc_ctx_missing_params(c));
+        return FVC_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t before = g_launch_count;
+    c->conv_event_used = 0;
+    int rc = ensure_entropy_buffers(c);
+    const int R = c->mxrange, L = c->rans_L;
+    int nloss = 0;
+    if (!rc) rc = launch_cdf_table_factorized(be_params(c->be_z), 64, R, c->cdf_tab_z, s);
+    if (!rc) rc = launch_cdf_table_factorized(be_params(c->be_mv), 128, R, c->cdf_tab_mv, s);
+    // z_hat (the pre-round buffers are reused to hold the decoded integer values)
+    if (!rc) rc = launch_rans_decode_factorized((const uint8_t*)z_stream, z_bytes, latent_count(c, 1), L, 64, R, c->cdf_tab_z, c->z, c->ent_err, s);
+    if (!rc) rc = launch_nhwc_to_act(c->z, c->z_hat, 64, 0, s);
+    if (!rc) rc = run_prior_decoder(c, s);
+    if (!rc) rc = launch_rans_decode_laplace((const uint8_t*)feat_stream, feat_bytes, latent_count(c, 0), L, R, c->sigma, c->feature, c->ent_err, s);
+    if (!rc) rc = launch_nhwc_to_act(c->feature, c->feat_hat, 96, 0, s);
+    if (!rc) rc = launch_rans_decode_factorized((const uint8_t*)mv_stream, mv_bytes, latent_count(c, 2), L, 128, R, c->cdf_tab_mv, c->mvfeature, c->ent_err, s);
+    if (!rc) rc = launch_nhwc_to_act(c->mvfeature, c->quant_mv, 128, 0, s);
+    if (!rc) rc = run_mv_decoder(c, s);
+    if (!rc) rc = run_motion_comp(c, nullptr, ref, s);
+    if (!rc) rc = run_res_decoder(c, s);
+    if (!rc) rc = launch_recon_losses(ref, c->prediction, c->warpframe, c->recon_res, 1, c->B, c->H * c->W, recon_out,
+                                      c->loss_partials, &nloss, s, 0);
+    c->launches += g_launch_count - before;
+    if (rc) return rc;
+    unsigned int err[3] = {0, 0, 0};
+    FVC_CUDA(cudaMemcpyAsync(err, c->ent_err, 12, cudaMemcpyDeviceToHost, s));
+    FVC_CUDA(cudaStreamSynchronize(s));
+    if (err[2]) {
+        set_error("fvc_decode_bitstreams: %u lanes could not be opened (wrong container, size or geometry)", err[2]);
+        cudaMemsetAsync(c->ent_err, 0, 12, s);
+        return FVC_ERR_ARG;
+    }
+    return 0;
 }
 
 int64_t fvc_ctx_launch_count(fvc_ctx* c) { return c ? c->launches : -1; }

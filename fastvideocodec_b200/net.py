@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import IMPL_SIMT, IMPL_TC, check, lib, ptr, stream_ptr
+from ._lib import IMPL_SIMT, IMPL_TC, IMPL_TC_FAST, check, lib, ptr, stream_ptr
 from .subnet import (Analysis_mv_net, Analysis_net, Analysis_prior_net, BitEstimator, ME_Spynet, Synthesis_mv_net,
                      Synthesis_net, Synthesis_prior_net, Warp_net, out_channel_N, out_channel_mv)
 from .synthetic import init_state_dict
@@ -45,9 +45,17 @@ def load_model(model, f):
     return 0
 
 
-def _default_impl():
+def _default_impl(precision=None):
+    """Engine selection: FVC_IMPL=simt picks the fp32 CUDA-core checker engine; otherwise the tcgen05 engine in
+    precision 'exact' (3 MMAs per product on fp16 hi/lo pairs: element-level parity with the fp32 reference) or
+    'fast' (1 fp16 MMA per product: metric-level parity only).  ``precision`` overrides FVC_PRECISION."""
     v = os.environ.get("FVC_IMPL", "tc").lower()
-    return IMPL_SIMT if v in ("simt", "0") else IMPL_TC
+    if v in ("simt", "0"):
+        return IMPL_SIMT
+    prec = (precision or os.environ.get("FVC_PRECISION", "exact")).lower()
+    if prec not in ("exact", "fast"):
+        raise ValueError("precision must be 'exact' or 'fast' (got %r)" % prec)
+    return IMPL_TC_FAST if prec == "fast" or v in ("fast", "tc_fast", "2") else IMPL_TC
 
 
 class _Context:
@@ -91,7 +99,9 @@ class _Context:
 
 
 class VideoCompressor(nn.Module):
-    def __init__(self, spynet_levels=4):
+    def __init__(self, spynet_levels=4, precision=None):
+        """Reference ctor takes no arguments (net.py:39); both keywords are extensions: ``spynet_levels`` (SURVEY
+        7.2-6, reference hard-codes 4) and ``precision`` in {'exact' (default), 'fast'}."""
         super().__init__()
         self.opticFlow = ME_Spynet(spynet_levels)
         self.mvEncoder = Analysis_mv_net()
@@ -108,7 +118,7 @@ class VideoCompressor(nn.Module):
         self.mxrange = 150
         self.calrealbits = False
         self.decoding_time = 0.0
-        self.impl = _default_impl()
+        self.impl = _default_impl(precision)
         self.max_contexts = int(os.environ.get("FVC_MAX_CONTEXTS", "6"))
         self._ctxs = {}
         self._pitems = None

@@ -10,11 +10,12 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_EXP, ACT_LRELU001, ACT_LRELU01, ACT_NONE, ACT_RELU, IMPL_SIMT, IMPL_TC, check, lib, ptr, stream_ptr
+from ._lib import (ACT_EXP, ACT_LRELU001, ACT_LRELU01, ACT_NONE, ACT_RELU, IMPL_SIMT, IMPL_TC, IMPL_TC_FAST, check, lib, ptr,
+                   stream_ptr)
 
 __all__ = ["avg_pool2", "upsample2x_bilinear", "flow_warp", "conv2d", "conv_transpose2d", "gdn",
            "quant_bits_factorized", "quant_bits_laplace", "recon_losses", "eb_forward", "gaussian_forward",
-           "pack_eb_params", "ACT_NONE", "ACT_RELU", "ACT_LRELU01", "ACT_LRELU001", "ACT_EXP", "IMPL_SIMT", "IMPL_TC"]
+           "pack_eb_params", "ACT_NONE", "ACT_RELU", "ACT_LRELU01", "ACT_LRELU001", "ACT_EXP", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_FAST"]
 
 
 def _cuda_f32(t, name):

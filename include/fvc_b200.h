@@ -44,7 +44,10 @@ extern "C" {
 
 /* convolution engines */
 #define FVC_IMPL_SIMT 0 /* fp32 CUDA-core implicit GEMM (checker / bring-up path) */
-#define FVC_IMPL_TC 1   /* tcgen05 + TMEM + TMA, fp16 hi/lo operand pairs (3 MMAs per product), fp32 accumulate */
+#define FVC_IMPL_TC 1   /* tcgen05 + TMEM + TMA, fp16 hi/lo operand pairs (3 MMAs per product), fp32 accumulate:
+                           precision 'exact' (element-level parity with the fp32 reference) */
+#define FVC_IMPL_TC_FAST 2 /* the same engine, precision 'fast': ONE fp16 MMA per product (hi halves only), fp32
+                              accumulate, long TMEM chains; metric-level parity only (SURVEY 7.2-1, configs[1]) */
 
 FVC_API int fvc_version(void);
 FVC_API const char* fvc_last_error(void);
@@ -108,6 +111,31 @@ FVC_API int fvc_eb_forward(const float* x, const float* packed_params, const flo
 /* fvc_gaussian_forward: GaussianConditional eval forward (scale_bound 0.11, likelihood_bound 1e-9). */
 FVC_API int fvc_gaussian_forward(const float* x, const float* scales, const float* means, float* xhat_out,
                          float* lik_out, float* bits_out, int64_t n, void* stream);
+
+/* Real entropy coding of the quantised latents — the `calrealbits` branch of net.py:123-138 (feature under
+ * Laplace(0, sigma)), 155-168 (z under bitEstimator_z), 183-195 (mv under bitEstimator_mv).
+ * Model = the integer CDF the reference hands to torchac (un-vendored; its published conversion restated):
+ *     Q[i] = round(F(i - mxrange - 0.5) * (2^16 - (2*mxrange - 1))) + i,  i in [0, 2*mxrange),  end of the last symbol 2^16;
+ * symbol s = q + mxrange in [0, 2*mxrange - 2].  Coder = rANS (32-bit state, 16-bit words), one independent stream per
+ * lane of lane_len consecutive symbols (NHWC order); container "FVR1" (fvc_entropy.cu).  The code length is within
+ * 32 bits per lane + header of the ideal sum(-log2(freq / 2^16)) that torchac's arithmetic coder also attains.
+ * Tables are uint32 [C][2*mxrange] (factorized, per channel) or [n][2*mxrange] (Laplace, per element: test use only). */
+FVC_API int fvc_cdf_table_factorized(const float* const* params, int C, int mxrange, uint32_t* table_out, void* stream);
+FVC_API int fvc_cdf_table_laplace(const float* sigma, int64_t n, int mxrange, uint32_t* table_out, void* stream);
+/* x: the PRE-round latent, fp32, n values in coding order with channel = index % C; q = round(x) is coded.
+ * stream_out (device, capacity >= fvc_entropy_stream_capacity(n, lane_len)); nbytes_out: device uint32;
+ * err_out: device uint32[3] = symbols outside [-mxrange, mxrange-2], empty intervals, unreadable lanes. */
+FVC_API int fvc_entropy_encode_factorized(const float* x, int64_t n, int C, const uint32_t* table, int mxrange,
+                                          int lane_len, void* stream_out, int64_t capacity, uint32_t* nbytes_out,
+                                          uint32_t* err_out, void* stream);
+FVC_API int fvc_entropy_encode_laplace(const float* x, const float* sigma, int64_t n, int mxrange, int lane_len,
+                                       void* stream_out, int64_t capacity, uint32_t* nbytes_out, uint32_t* err_out,
+                                       void* stream);
+FVC_API int fvc_entropy_decode_factorized(const void* stream_in, int64_t nbytes, int64_t n, int C, const uint32_t* table,
+                                          int mxrange, int lane_len, float* q_out, uint32_t* err_out, void* stream);
+FVC_API int fvc_entropy_decode_laplace(const void* stream_in, int64_t nbytes, int64_t n, const float* sigma, int mxrange,
+                                       int lane_len, float* q_out, uint32_t* err_out, void* stream);
+FVC_API int64_t fvc_entropy_stream_capacity(int64_t n, int lane_len);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole-path context: VideoCompressor.forward — net.py:70-220.
@@ -176,6 +204,19 @@ FVC_API int fvc_ctx_force_latents(fvc_ctx* ctx, const float* quant_mv, const flo
  * While it is non-zero, fvc_pframe_forward writes NaN into scalars_out and fvc_gop_forward_host fails with
  * FVC_ERR_STATE.  Synchronises the stream. */
 FVC_API int64_t fvc_ctx_saturation_count(fvc_ctx* ctx, int reset, void* stream);
+
+/* calrealbits (net.py:57): when enabled, every following fvc_pframe_forward entropy-codes the three quantised latents
+ * on the GPU (stream-ordered, no host synchronisation) and bpp_feature / bpp_z / bpp_mv / bpp in scalars_out are the
+ * REAL bits (8 x stream bytes, net.py:136) instead of the estimates.  mxrange = VideoCompressor.mxrange (150). */
+FVC_API int fvc_ctx_set_realbits(fvc_ctx* ctx, int enable, int mxrange);
+/* Byte stream of the last forward: which = 0 feature, 1 z, 2 mv.  out_host may be NULL (size query).  Returns the
+ * byte count; fails with FVC_ERR_STATE if a symbol was not codable.  Synchronises the stream. */
+FVC_API int64_t fvc_ctx_get_bitstream(fvc_ctx* ctx, int which, void* out_host, int64_t capacity, void* stream);
+/* The receiver: the three streams (DEVICE pointers) + the reference frame -> clamped reconstruction; decodes z,
+ * runs respriorDecoder for sigma, decodes feature and mv, then the path of fvc_decode_from_latents. */
+FVC_API int fvc_decode_bitstreams(fvc_ctx* ctx, const float* ref, const void* feat_stream, int64_t feat_bytes,
+                                  const void* z_stream, int64_t z_bytes, const void* mv_stream, int64_t mv_bytes,
+                                  float* recon_out, void* stream);
 
 /* Launch statistics since creation: kernels launched by this library through ctx. */
 FVC_API int64_t fvc_ctx_launch_count(fvc_ctx* ctx);

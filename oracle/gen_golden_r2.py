@@ -17,7 +17,7 @@ Writes
                                       within 2e-3 of a rounding tie (sparse), so that flips can be judged at HD
   tests/golden/pframe_L6_256.npz    : one P-frame at 256x256 of the reference class with ``self.L`` patched to 6
                                       (endecoder.py:318-319; moduleBasic extended with MEBasic(modelL5), (modelL6)),
-                                      weights init_state_dict(0, spynet_levels=6)
+                                      weights init_state_dict(0, spynet_levels=6, spynet_gain=1.8)
 """
 from __future__ import annotations
 
@@ -39,6 +39,10 @@ from oracle import ref_shim  # noqa: E402
 from oracle.gen_golden import _np  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
+# SpyNet init gain for the 6-level pyramid: every level doubles the flow of the level below, so the gain that gives
+# few-pixel flows with 4 levels (2.2: rms 4 px) explodes with 6 (rms 12.6 px, max 32 px on a 256 px frame, |latent| up to
+# 90); 1.8 keeps the 6-level flows in the same range (rms 3.1 px) - the regime a trained SpyNet works in.
+L6_GAIN = 1.8
 SCALARS = ["mse", "warploss", "interloss", "bpp_feature", "bpp_z", "bpp_mv", "bpp"]
 PREQUANT = {"quant_mv": "mvfeature", "z_hat": "z", "feat_hat": "feature"}
 
@@ -115,7 +119,7 @@ def build_reference_model_levels(sd, levels):
 
 
 def gen_l6():
-    sd = init_state_dict(0, spynet_levels=6)
+    sd = init_state_dict(0, spynet_levels=6, spynet_gain=L6_GAIN)
     model = build_reference_model_levels(sd, 6)
     frames = synthetic_gop(256, 256, gop=2, gop_id=31)[:, 0]
     ref, cur = frames[0:1], frames[1:2]

@@ -21,7 +21,7 @@ TIE_TOL = 1.8e-4  # |x - (k + 1/2)| of the REFERENCE pre-quantisation value for 
                   # a flip further from the tie than this means the pre-round value itself is off by more than that.
 
 
-def check_latent(name, got, want, prequant, tie_rule=True):
+def check_latent(name, got, want, prequant, tie_rule=True, extra=0):
     """North-star gate for quantised latents: bit-exact except <= 1e-4 of the elements, and every
     exception must be a rounding tie: it differs by exactly 1 and the reference's own pre-round value
     lies within TIE_TOL * max(1, rms(x)) of k + 1/2 (fp32 evaluation order alone moves such values across the tie; the
@@ -33,7 +33,10 @@ def check_latent(name, got, want, prequant, tie_rule=True):
     n_bad = int(diff.sum())
     if n_bad == 0:
         return 0.0
-    assert n_bad <= max(2, int(1e-4 * got.numel())), (name, n_bad, got.numel())
+    # `extra`: free-running feat_hat / z_hat only: every upstream quant_mv flip moves `feature` (and `z`) in its
+    # neighbourhood by ~1e-3 and may push elements there across their tie (second-order flips); the strict
+    # per-tensor bound for these two is enforced in the teacher-forced pass
+    assert n_bad <= max(2, int(1e-4 * got.numel())) + extra, (name, n_bad, got.numel(), extra)
     assert float((got - want)[diff].abs().max()) == 1.0, (name, "mismatch by more than one level")
     if not tie_rule:
         return n_bad / got.numel()
@@ -246,21 +249,34 @@ def test_compressai_style_likelihoods(dev):
 # whole P-frame against the reference's golden vectors
 # ------------------------------------------------------------------------------------------------
 def _flip_mask(model, gold, H, W, report=None):
-    """Free-running latent gates + the +-96 px receptive-field mask around feat_hat / quant_mv flips (z_hat only
-    feeds sigma).  The tie rule is applied here to quant_mv only, the one quantiser with nothing quantised upstream:
+    """Free-running latent gates + the receptive-field mask around feat_hat flips (_mask_feat_flips).  The tie rule is applied here to quant_mv only, the one quantiser with nothing quantised upstream:
     a quant_mv flip moves `feature` in its neighbourhood by ~1e-3, so free-running feat_hat / z_hat flips may be
     second-order; their tie rule is checked in the teacher-forced pass (_check_against, part B), where the
     reference's quant_mv is forced upstream and our own pre-round `feature` / `z` are rounded."""
     mask = torch.zeros((H, W), dtype=torch.bool)
+    n_mv = 0
     for name, scale in (("quant_mv", 16), ("feat_hat", 16), ("z_hat", 64)):
         a = model.get_intermediate(name).cpu()
-        frac = check_latent(name, a, gold[name], gold[PREQUANT[name]], tie_rule=(name == "quant_mv"))
+        frac = check_latent(name, a, gold[name], gold[PREQUANT[name]], tie_rule=(name == "quant_mv"),
+                            extra=0 if name == "quant_mv" else n_mv)
+        if name == "quant_mv":
+            n_mv = int((a != gold[name]).sum())
         if report is not None:
             report[name] = frac
-        for (_, _, y, x) in (a != gold[name]).nonzero().tolist():
-            cy, cx = y * scale + scale // 2, x * scale + scale // 2
-            mask[max(0, cy - 96):cy + 96, max(0, cx - 96):cx + 96] = True
+        if name == "feat_hat":
+            _mask_feat_flips(mask, a != gold[name])
     return mask
+
+
+def _mask_feat_flips(mask, diff):
+    """Receptive field of a flipped feat_hat element in the reconstructed frame: resDecoder = four k5 s2 transposed
+    convs, output pixels [16y - 30, 16y + 30] (measured on the oracle: |d recon| ~ 0.1 inside, exactly 0 outside);
+    masked with margin: +-48 px around the latent's centre.  Flipped quant_mv elements are NOT masked: one level of
+    one of the 128 mv channels moves the decoded frame by <= 2e-3 (measured on the oracle, 6 channels), well inside
+    the 1e-2 gate; z_hat only feeds sigma (rate, not reconstruction)."""
+    for (_, _, y, x) in diff.nonzero().tolist():
+        cy, cx = y * 16 + 8, x * 16 + 8
+        mask[max(0, cy - 48):cy + 48, max(0, cx - 48):cx + 48] = True
 
 
 INTERMEDIATES = ("estmv", "mvfeature", "mv_hat", "warpframe", "prediction", "feature", "z", "sigma", "recon_res")
@@ -277,8 +293,8 @@ def _check_against(model, gold, dev, masked_free_run=False, inter_tol=5e-4):
        intermediates <= inter_tol * scale, recon <= 1e-2 (north star) -- in fact <= 1e-3.
        (One latent that flips at a rounding tie moves decoded pixels by ~0.1 with random-init decoders, SURVEY 7.2-1
        caveat (i); forcing removes the flips instead of hiding their neighbourhood.)
-    C. masked_free_run (HD and larger): additionally the free-running reconstruction <= 1e-2 outside the +-96 px
-       receptive field of flipped latents, and the mask may not cover more than half of the frame.
+    C. masked_free_run (HD and larger): additionally the free-running reconstruction <= 1e-2 outside the +-48 px
+       receptive field of flipped feat_hat elements, and the mask may not cover more than half of the frame.
     """
     cur, ref = gold["cur"].to(dev), gold["ref"].to(dev)
     B, _, H, W = cur.shape
@@ -326,6 +342,17 @@ def _check_against(model, gold, dev, masked_free_run=False, inter_tol=5e-4):
     finally:
         model.force_latents(B, H, W, dev)
     return report
+
+
+def _assert_full_size_latent_rates(rep, gold):
+    """North-star fraction gate at full size (>= 1080p): quant_mv free running, feat_hat / z_hat of our own quantisers
+    with the reference's quant_mv forced upstream: <= 1e-4 of the elements each.  Free-running feat_hat / z_hat may in
+    addition carry the second-order flips induced by the quant_mv flips (at most one per flipped mv element)."""
+    assert rep["quant_mv"] <= 1e-4, rep["quant_mv"]
+    assert rep["forced_feat_hat"] <= 1e-4 and rep["forced_z_hat"] <= 1e-4, (rep["forced_feat_hat"], rep["forced_z_hat"])
+    n_mv = rep["quant_mv"] * gold["quant_mv"].numel()
+    for name in ("feat_hat", "z_hat"):
+        assert rep[name] <= 1e-4 + n_mv / gold[name].numel(), (name, rep[name])
 
 
 def _gold_from_oracle(sd, cur, ref, levels=4):
@@ -452,8 +479,7 @@ def test_hd_frame_matches_oracle(model, state_dict, dev):
     gold = _gold_from_oracle(state_dict, frames[1:2], frames[0:1])
     model.impl = _impls()[-1][1]
     rep = _check_against(model, gold, dev, masked_free_run=True)
-    for name in LATENTS:
-        assert rep[name] <= 1e-4, (name, rep[name])
+    _assert_full_size_latent_rates(rep, gold)
     print("HD open-loop parity report:", {k: float("%.3g" % v) for k, v in rep.items()})
 
 
@@ -504,7 +530,7 @@ def test_config4_4k_frame_matches_oracle(dev, levels):
     the oracle's levels=6 path is pinned against that class by tests/golden/pframe_L6_256.npz)."""
     from fastvideocodec_b200 import VideoCompressor
     from fastvideocodec_b200.synthetic import init_state_dict, synthetic_gop
-    sd = init_state_dict(0, spynet_levels=levels)
+    sd = init_state_dict(0, spynet_levels=levels, spynet_gain=2.2 if levels == 4 else 1.8)   # see gen_golden_r2.L6_GAIN
     m = VideoCompressor(spynet_levels=levels)
     m.load_state_dict(sd)
     m = m.to(dev).eval()
@@ -512,8 +538,7 @@ def test_config4_4k_frame_matches_oracle(dev, levels):
     frames = synthetic_gop(2176, 3840, gop=2, gop_id=7)[:, 0]
     gold = _gold_from_oracle(sd, frames[1:2], frames[0:1], levels=levels)
     rep = _check_against(m, gold, dev, masked_free_run=True)
-    for name in LATENTS:
-        assert rep[name] <= 1e-4, (name, rep[name])
+    _assert_full_size_latent_rates(rep, gold)
     print("4K L=%d parity report:" % levels, {k: float("%.3g" % v) for k, v in rep.items()})
     m.release()
 
@@ -526,7 +551,7 @@ def test_deeper_pyramid_matches_reference_golden_L6(dev, golden_pframe_L6_256, i
     from fastvideocodec_b200.synthetic import init_state_dict
     g = golden_pframe_L6_256
     m = VideoCompressor(spynet_levels=6)
-    m.load_state_dict(init_state_dict(0, spynet_levels=6))
+    m.load_state_dict(init_state_dict(0, spynet_levels=6, spynet_gain=1.8))
     m = m.to(dev).eval()
     m.impl = impl
     with torch.no_grad():
@@ -564,9 +589,8 @@ def test_config5_multiview_batch8(model, state_dict, dev):
         for n, scale in (("quant_mv", 16), ("feat_hat", 16), ("z_hat", 64)):
             a = lat[n][v:v + 1]
             check_latent(n, a, gold[n], gold[PREQUANT[n]], tie_rule=(n == "quant_mv"))
-            if scale == 16:
-                for (_, _, y, x) in (a != gold[n]).nonzero().tolist():
-                    mask[max(0, y * 16 + 8 - 96):y * 16 + 104, max(0, x * 16 + 8 - 96):x * 16 + 104] = True
+            if n == "feat_hat":
+                _mask_feat_flips(mask, a != gold[n])
         assert mask.float().mean().item() <= 0.5
         assert (rec8[v:v + 1] - gold["clipped"]).abs().masked_fill(mask, 0.0).max().item() <= 1e-2
         # the same view as a B=1 run: bit-identical frame, and every gate of _check_against against the oracle
@@ -781,8 +805,7 @@ def test_real_spynet_weights_match_oracle(real_model, real_state_dict, dev, size
     gold = _gold_from_oracle(real_state_dict, frames[1:2], frames[0:1])
     rep = _check_against(real_model, gold, dev, masked_free_run=size[0] >= 1088)
     if size[0] >= 1088:
-        for name in LATENTS:
-            assert rep[name] <= 1e-4, (name, rep[name])
+        _assert_full_size_latent_rates(rep, gold)
     assert real_model.saturation_count() == 0
     print("real SpyNet weights %dx%d:" % size, {k: float("%.3g" % v) for k, v in rep.items()})
     real_model.release()
@@ -820,12 +843,12 @@ def test_decoder_only_hd(model, state_dict, dev):
     assert err <= 1e-3, err
 
 
-def _sparse_tie_check(name, got_q, gold, pre_name, tie_rule=True):
+def _sparse_tie_check(name, got_q, gold, pre_name, tie_rule=True, extra=0):
     """check_latent against hd_gop10.npz: int8 latents + the reference's pre-round values near ties (sparse)."""
     want = gold["f1_" + name].float()
     diff = (got_q != want)
     n_bad = int(diff.sum())
-    assert n_bad <= max(2, int(1e-4 * want.numel())), (name, n_bad)
+    assert n_bad <= max(2, int(1e-4 * want.numel())) + extra, (name, n_bad, extra)
     if n_bad == 0:
         return 0.0
     assert float((got_q - want)[diff].abs().max()) == 1.0
@@ -857,12 +880,15 @@ def test_hd_gop10_closed_loop_matches_reference_golden(model, golden_hd_gop10, d
         out = model(frames[1].to(dev), frames[0].to(dev))
     mask = torch.zeros((1088, 1920), dtype=torch.bool)
     fracs = {}
-    for name in LATENTS:
+    n_mv = 0
+    for name in LATENTS:                      # quant_mv first
         a = model.get_intermediate(name).cpu()
-        fracs[name] = _sparse_tie_check(name, a, g, PREQUANT[name], tie_rule=(name == "quant_mv"))
-        if name != "z_hat":
-            for (_, _, y, x) in (a != g["f1_" + name].float()).nonzero().tolist():
-                mask[max(0, y * 16 + 8 - 96):y * 16 + 104, max(0, x * 16 + 8 - 96):x * 16 + 104] = True
+        fracs[name] = _sparse_tie_check(name, a, g, PREQUANT[name], tie_rule=(name == "quant_mv"),
+                                        extra=0 if name == "quant_mv" else n_mv)
+        if name == "quant_mv":
+            n_mv = int((a != g["f1_quant_mv"].float()).sum())
+        if name == "feat_hat":
+            _mask_feat_flips(mask, a != g["f1_" + name].float())
     assert mask.float().mean().item() <= 0.5
     want = torch.from_numpy(g["f1_clipped_u16"].numpy().astype("float32")) / 65535.0
     err = (out[0].cpu() - want).abs().masked_fill(mask, 0.0).max().item()
@@ -1011,3 +1037,76 @@ def test_two_devices_in_one_process(state_dict):
         outs.append((o[0].cpu(), float(o[7])))
         m.release()
     assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+
+
+# ------------------------------------------------------------------------------------------------
+# precision='fast' (one fp16 MMA per product): metric-level gates only
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fast_precision(dev, case):
+    """Single-pass fp16 operands, fp32 accumulation: error bounded by the operand rounding (2^-11 relative per
+    operand, random signs over the K = Cin*k*k products)."""
+    import torch.nn.functional as F
+    from fastvideocodec_b200 import ops
+    cin, cout, k, stride, transposed, act, H, W = case
+    g = torch.Generator().manual_seed(300 + cin * 7 + cout + k + stride)
+    x = torch.randn((2, cin, H, W), generator=g)
+    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    w = torch.randn(wshape, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn((cout,), generator=g) * 0.1
+    if transposed:
+        want = F.conv_transpose2d(x, w, b, stride=stride, padding=k // 2, output_padding=stride - 1)
+        got = ops.conv_transpose2d(x.to(dev), w.to(dev), b.to(dev), stride, act, ops.IMPL_TC_FAST).cpu()
+    else:
+        want = F.conv2d(x, w, b, stride=stride, padding=k // 2)
+        got = ops.conv2d(x.to(dev), w.to(dev), b.to(dev), stride, act, ops.IMPL_TC_FAST).cpu()
+    want = {0: lambda t: t, 1: torch.relu, 2: lambda t: F.leaky_relu(t, 0.1), 3: torch.exp}[act](want)
+    err = (got - want).abs().max().item()
+    assert err <= 4e-3 * max(1.0, want.abs().max().item()), (case, err)
+    assert err > 0.0 or cin * k * k < 64      # it really is the reduced-precision path
+
+
+@pytest.fixture(scope="module")
+def fast_model(dev, state_dict):
+    from fastvideocodec_b200 import VideoCompressor
+    m = VideoCompressor(precision="fast")
+    m.load_state_dict(state_dict)
+    return m.to(dev).eval()
+
+
+def test_fast_precision_config1_gop_metric_parity(fast_model, state_dict, dev):
+    """precision='fast' on BASELINE config 1 (256x256, GOP 10, closed loop) against the CPU oracle: the metric-level
+    north-star gates (bpp 0.5 %, PSNR 0.02 dB on the GOP means).  Latent flip rates are reported, not gated."""
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    frames = synthetic_gop(256, 256, gop=10, gop_id=0)[:, 0]
+    rows, rec = O.gop_forward(state_dict, frames)
+    _, sc = fast_model.gop_forward_host(frames.unsqueeze(1).contiguous())
+    bpp = sum(r[0] for r in rows) / len(rows)
+    psnr = sum(r[1] for r in rows) / len(rows)
+    got_bpp = float(sc[:, 6].mean())
+    got_psnr = sum(_psnr(m) for m in sc[:, 0].tolist()) / len(rows)
+    print("fast 256^2 GOP: bpp %.5f vs %.5f (%.3g), PSNR %.4f vs %.4f dB" % (got_bpp, bpp, abs(got_bpp - bpp) / bpp,
+                                                                        got_psnr, psnr))
+    assert abs(got_bpp - bpp) <= 0.005 * bpp
+    assert abs(got_psnr - psnr) <= 0.02
+
+
+def test_fast_precision_hd_gop_metric_parity(fast_model, golden_hd_gop10, dev):
+    """precision='fast' on the GOP bench.py times, closed loop, against the unmodified reference's rows:
+    bpp within 0.5 %, PSNR within 0.02 dB on the GOP means; frame-1 latent flip rates printed."""
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    g = golden_hd_gop10
+    frames = synthetic_gop(1088, 1920, gop=10, gop_id=int(g["gop_id"]))
+    with torch.no_grad():
+        fast_model(frames[1].to(dev), frames[0].to(dev))
+    flips = {n: (fast_model.get_intermediate(n).cpu() != g["f1_" + n].float()).float().mean().item() for n in LATENTS}
+    _, sc = fast_model.gop_forward_host(frames.contiguous().pin_memory(), want_recon=False)
+    rows = g["rows"]
+    got_bpp, want_bpp = float(sc[:, 6].double().mean()), rows[:, 6].mean().item()
+    got_psnr = sum(_psnr(m) for m in sc[:, 0].tolist()) / 9
+    want_psnr = rows[:, 7].mean().item()
+    print("fast HD GOP: bpp %.5f vs %.5f (%.3g), PSNR %.4f vs %.4f dB, frame-1 latent flip rates %s" %
+          (got_bpp, want_bpp, abs(got_bpp - want_bpp) / want_bpp, got_psnr, want_psnr, flips))
+    assert abs(got_bpp - want_bpp) <= 0.005 * want_bpp
+    assert abs(got_psnr - want_psnr) <= 0.02
+    fast_model.release()

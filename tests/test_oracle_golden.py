@@ -141,7 +141,7 @@ def test_oracle_matches_reference_deeper_pyramid_L6(golden_pframe_L6_256):
     """levels=6 (configs[3] "deeper flow pyramid") against the reference class with ME_Spynet.L patched to 6."""
     from fastvideocodec_b200.synthetic import init_state_dict
     g = golden_pframe_L6_256
-    sd = init_state_dict(0, spynet_levels=6)
+    sd = init_state_dict(0, spynet_levels=6, spynet_gain=1.8)
     out, cap = O.pframe_forward(sd, g["cur"], g["ref"], levels=6, capture=True)
     for name in ("estmv", "mv_hat", "mvfeature", "feature", "z", "sigma"):
         err = (cap[name] - g[name]).abs().max().item()
