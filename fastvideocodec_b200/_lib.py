@@ -75,12 +75,15 @@ def lib():
     """Loads (once) and returns the shared library; raises if it is not built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("FVC_LIB_PATH", LIB_PATH)   # override: A/B of two builds on one box (tools/ab_lib.py)
+        if not os.path.exists(path):
             raise RuntimeError(
                 "libfvc_b200.so is not built (%s). Run `python -m fastvideocodec_b200.build`; "
-                "there is no fallback path." % LIB_PATH)
-        handle = C.CDLL(LIB_PATH)
+                "there is no fallback path." % path)
+        handle = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
+            if path != LIB_PATH and not hasattr(handle, name):
+                continue                                    # an older build under test lacks newer entry points
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args

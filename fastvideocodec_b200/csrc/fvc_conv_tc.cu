@@ -30,6 +30,7 @@
 //   * Up to four partial-accumulator buffers (CT <= 128) let the issuers run a whole tile ahead of an epilogue.
 #include <cuda.h>
 #include <atomic>
+#include <type_traits>
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -579,7 +580,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     // everything above (barriers, TMEM allocation, bias staging: parameters only) overlapped the previous kernel's
     // tail; from here on activations written by earlier kernels are read and buffers they read are overwritten
+#ifndef FVC_NO_PDL_SYNC
     pdl_sync();
+#endif
 
     // register re-allocation per warpgroup: the control warps need few registers, the accumulator warps many
     if (warp < TC_ACC_WARP0) {
@@ -743,48 +746,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 }
                 uint32_t toff = (uint32_t)toffp[0] >> 4;
                 const unsigned long long gmask = ((unsigned long long)ps.gmask_hi << 32) | ps.gmask_lo;
-                for (; t < ntaps; ++t) {
-                    if ((gmask >> t) & 1ull) {
-                        // a new accumulation group starts here: hand the finished chain to the accumulator
-                        // warps; the next partial buffer must have been drained by them
-                        if (gopen) {
-                            if (lead) tc_commit_t<PAIR>(bar_afull + 8 * gpb);
-                            ++gg;
+                // The tap loop, instantiated for the k-step count of a tap's first weight tile: 4, or 2 for the hi-only
+                // half tile of 32-channel records in precision 'fast'.  (A run-time test of that count inside the loop
+                // cost the issue-bound 3x3 layers 5 %: the issue loop's instruction count is what bounds them.)
+                auto tap_loop = [&](auto ks0_tag) {
+                    constexpr int KS0 = decltype(ks0_tag)::value;
+                    for (; t < ntaps; ++t) {
+                        if ((gmask >> t) & 1ull) {
+                            // a new accumulation group starts here: hand the finished chain to the accumulator
+                            // warps; the next partial buffer must have been drained by them
+                            if (gopen) {
+                                if (lead) tc_commit_t<PAIR>(bar_afull + 8 * gpb);
+                                ++gg;
+                            }
+                            gpb = gg & nabm;
+                            { const long long c0 = dbg_on ? clock64() : 0;
+                              mbar_wait(bar_aempty + 8 * gpb, ((gg >> nabs) & 1u) ^ 1u);
+                              if (dbg_on) w_aempty += clock64() - c0; }
+                            tc_fence_after();
+                            gdcol = tmem_u + gpb * CT;
+                            gacc0 = 0u;
+                            gopen = true;
                         }
-                        gpb = gg & nabm;
-                        { const long long c0 = dbg_on ? clock64() : 0;
-                          mbar_wait(bar_aempty + 8 * gpb, ((gg >> nabs) & 1u) ^ 1u);
-                          if (dbg_on) w_aempty += clock64() - c0; }
-                        tc_fence_after();
-                        gdcol = tmem_u + gpb * CT;
-                        gacc0 = 0u;
-                        gopen = true;
+                        const uint32_t alo = pa16 + toff;
+                        toff = (uint32_t)toffp[t + 1] >> 4;   // prefetched for the next tap (table has one spare entry)
+    #pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (j == 1 && !two) break;
+                            if (slot == 0) {
+                                const long long c0 = dbg_on ? clock64() : 0;
+                                mbar_wait(bar_bfull + 8 * st, stph);
+                                if (dbg_on) w_bfull += clock64() - c0;
+                                blo = bst16 + st * stage16;
+                            }
+                            if (lead) {
+                                // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
+                                if (j == 1 && short2) issue_stage<2, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
+                                else issue_stage<KS0, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
+                            }
+                            gacc0 = 1u;
+                            blo += btile16;
+                            if (++slot == T || (t == ntaps - 1 && (j == 1 || !two))) {
+                                if (lead) tc_commit_t<PAIR>(bar_bempty + 8 * st);   // frees the stage when these MMAs retire
+                                if (++st == nst) { st = 0; stph ^= 1u; }
+                                slot = 0;
+                            }
+                        }
                     }
-                    const uint32_t alo = pa16 + toff;
-                    toff = (uint32_t)toffp[t + 1] >> 4;   // prefetched for the next tap (table has one spare entry)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        if (j == 1 && !two) break;
-                        if (slot == 0) {
-                            const long long c0 = dbg_on ? clock64() : 0;
-                            mbar_wait(bar_bfull + 8 * st, stph);
-                            if (dbg_on) w_bfull += clock64() - c0;
-                            blo = bst16 + st * stage16;
-                        }
-                        if (lead) {
-                            // every weight tile has 4 k-steps except the [lo | 0] tile of 32-channel records (2)
-                            if (j == 1 ? short2 : short1) issue_stage<2, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
-                            else issue_stage<4, PAIR>(gdcol, alo, ahi, blo, bhi, idesc, gacc0, ns, so0, do0, so1, do1);
-                        }
-                        gacc0 = 1u;
-                        blo += btile16;
-                        if (++slot == T || (t == ntaps - 1 && (j == 1 || !two))) {
-                            if (lead) tc_commit_t<PAIR>(bar_bempty + 8 * st);   // frees the stage when these MMAs retire
-                            if (++st == nst) { st = 0; stph ^= 1u; }
-                            slot = 0;
-                        }
-                    }
-                }
+                };
+                if (short1) tap_loop(std::integral_constant<int, 2>{});
+                else tap_loop(std::integral_constant<int, 4>{});
                 if (ps.gend && gopen) {
                     if (lead) tc_commit_t<PAIR>(bar_afull + 8 * gpb);      // chain complete -> accumulator warps
                     ++gg;

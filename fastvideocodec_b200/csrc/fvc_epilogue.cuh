@@ -51,7 +51,7 @@ __device__ __forceinline__ uint32_t ep_pack2(float a, float b) {
 // Range tracking of the stored hi halves: satm holds the running max |hi| of both 16-bit lanes (one HMNMX2 per two
 // elements).  A lane that reaches 0x7BFF (65504) was clamped by cvt.satfinite: the caller reports it (sat_count).
 __device__ __forceinline__ uint32_t ep_sat_track(uint32_t satm, uint32_t hi) {
-#if FVC_SPLIT_FP16
+#if FVC_SPLIT_FP16 && !defined(FVC_NO_SAT)
     __half2 m = __hmax2(*reinterpret_cast<__half2*>(&satm), __habs2(*reinterpret_cast<__half2*>(&hi)));
     return *reinterpret_cast<uint32_t*>(&m);
 #else

@@ -1011,8 +1011,12 @@ int64_t fvc_ctx_saturation_count(fvc_ctx* c, int reset, void* stream) {
 /* calrealbits (net.py:57, 123-138, 155-168, 183-195) */
 int fvc_ctx_set_realbits(fvc_ctx* c, int enable, int mxrange) {
     FVC_ARG(c != nullptr && mxrange >= 2 && mxrange <= 16384);
+    if (!c->sym_packed) c->mxrange = mxrange;          // fixed once the coder's buffers exist
+    else if (mxrange != c->mxrange) {
+        set_error("fvc_ctx_set_realbits: mxrange of a context cannot change (%d -> %d)", c->mxrange, mxrange);
+        return FVC_ERR_STATE;
+    }
     if (enable) {
-        c->mxrange = mxrange;
         int rc = ensure_entropy_buffers(c);
         if (rc) return rc;
     }

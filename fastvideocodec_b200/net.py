@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import torch_ops  # noqa: F401  (registers torch.ops.fvc.*)
 from ._lib import IMPL_SIMT, IMPL_TC, IMPL_TC_FAST, check, lib, ptr, stream_ptr
 from .subnet import (Analysis_mv_net, Analysis_net, Analysis_prior_net, BitEstimator, ME_Spynet, Synthesis_mv_net,
                      Synthesis_net, Synthesis_prior_net, Warp_net, out_channel_N, out_channel_mv)
@@ -68,6 +69,7 @@ class _Context:
         if not self.handle:
             raise _lib.FvcError("fvc_ctx_create failed: %s" % lib().fvc_last_error().decode())
         self.versions = None
+        self.realbits = False
 
     def sync_params(self, model):
         params = model._param_items()
@@ -165,8 +167,6 @@ class VideoCompressor(nn.Module):
         if self.training:
             raise NotImplementedError("training-mode (additive-noise) forward is outside the B200 inference hot "
                                       "path; call .eval() (reference net.py:73-99 noise branch)")
-        if self.calrealbits:
-            raise NotImplementedError("calrealbits (torchac range coding, net.py:123-138) is out of scope")
         for t in (input_image, referframe):
             if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] == 3):
                 raise TypeError("frames must be CUDA float32 [B,3,H,W] tensors")
@@ -178,11 +178,14 @@ class VideoCompressor(nn.Module):
         cur, ref = input_image.contiguous(), referframe.contiguous()
         with torch.cuda.device(cur.device):
             ctx = self._context(B, H, W, cur.device)
+            # calrealbits (net.py:57, 123-138, 155-168, 183-195): the three latents are entropy-coded on the GPU and the
+            # returned bpp_* are 8 x stream bytes / pixels instead of the estimates
+            if bool(self.calrealbits) != ctx.realbits:
+                check(lib().fvc_ctx_set_realbits(ctx.handle, int(bool(self.calrealbits)), int(self.mxrange)),
+                      "fvc_ctx_set_realbits")
+                ctx.realbits = bool(self.calrealbits)
             t0_dec = time.perf_counter()
-            recon = torch.empty_like(cur)
-            scalars = torch.empty(7, device=cur.device, dtype=torch.float32)
-            check(lib().fvc_pframe_forward(ctx.handle, ptr(cur), ptr(ref), ptr(recon), ptr(scalars), stream_ptr()),
-                  "fvc_pframe_forward")
+            recon, scalars = torch.ops.fvc.pframe_forward(cur, ref, ctx.handle)      # torch_ops.py -> fvc_pframe_forward
         self._last_ctx = ctx
         self.decoding_time = time.perf_counter() - t0_dec
         s = scalars
@@ -249,6 +252,55 @@ class VideoCompressor(nn.Module):
             recon = torch.empty_like(ref)
             check(lib().fvc_decode_from_latents(ctx.handle, ptr(ref), ptr(qmv), ptr(fh), ptr(recon), stream_ptr()),
                   "fvc_decode_from_latents")
+        self._last_ctx = ctx
+        return recon
+
+    STREAMS = ("feature", "z", "mv")
+
+    def compress(self, input_image, referframe):
+        """Encoder of the codec: ``forward`` with real entropy coding, returning the byte streams.
+
+        Returns ``(streams, clipped_recon, scalars)``: ``streams`` = {"feature", "z", "mv"} -> bytes (rANS containers,
+        csrc/fvc_entropy.cu), ``clipped_recon`` = the encoder-side reconstruction (next reference), ``scalars`` = the
+        7 reference scalars with REAL bpp.  ``decompress(streams, referframe)`` reproduces ``clipped_recon`` exactly."""
+        old = self.calrealbits
+        self.calrealbits = True
+        try:
+            out = self.forward(input_image, referframe)
+        finally:
+            self.calrealbits = old
+        ctx = self._last_ctx
+        streams = {}
+        with torch.cuda.device(input_image.device):
+            for k, name in enumerate(self.STREAMS):
+                n = check(lib().fvc_ctx_get_bitstream(ctx.handle, k, C.c_void_p(0), 0, stream_ptr()), "fvc_ctx_get_bitstream")
+                buf = (C.c_ubyte * max(n, 1))()
+                check(lib().fvc_ctx_get_bitstream(ctx.handle, k, buf, n, stream_ptr()), "fvc_ctx_get_bitstream")
+                streams[name] = bytes(buf[:n])
+        return streams, out[0], torch.stack(out[1:])
+
+    def decompress(self, streams, referframe):
+        """Decoder of the codec: byte streams + reference frame -> clamped reconstruction (fvc_decode_bitstreams):
+        z is decoded under bitEstimator_z, sigma = respriorDecoder(z_hat), feature under Laplace(0, sigma), mv under
+        bitEstimator_mv, then mvDecoder / motion compensation / resDecoder (net.py:77-80, 101-105)."""
+        if not (referframe.is_cuda and referframe.dtype == torch.float32 and referframe.dim() == 4):
+            raise TypeError("referframe must be a CUDA float32 [B,3,H,W] tensor")
+        B, _, H, W = referframe.shape
+        ref = referframe.contiguous()
+        import numpy as np
+        with torch.cuda.device(ref.device):
+            ctx = self._context(B, H, W, ref.device)
+            check(lib().fvc_ctx_set_realbits(ctx.handle, int(ctx.realbits), int(self.mxrange)), "fvc_ctx_set_realbits")
+            dev_streams = []
+            for name in self.STREAMS:
+                raw = streams[name]
+                pad = (-len(raw)) % 4
+                dev_streams.append(torch.from_numpy(np.frombuffer(raw + b"\0" * pad, dtype=np.uint8).copy()).to(ref.device))
+            recon = torch.empty_like(ref)
+            f, z, m = dev_streams
+            check(lib().fvc_decode_bitstreams(ctx.handle, ptr(ref), ptr(f), len(streams["feature"]), ptr(z),
+                                              len(streams["z"]), ptr(m), len(streams["mv"]), ptr(recon), stream_ptr()),
+                  "fvc_decode_bitstreams")
         self._last_ctx = ctx
         return recon
 

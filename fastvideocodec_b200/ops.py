@@ -15,7 +15,8 @@ from ._lib import (ACT_EXP, ACT_LRELU001, ACT_LRELU01, ACT_NONE, ACT_RELU, IMPL_
 
 __all__ = ["avg_pool2", "upsample2x_bilinear", "flow_warp", "conv2d", "conv_transpose2d", "gdn",
            "quant_bits_factorized", "quant_bits_laplace", "recon_losses", "eb_forward", "gaussian_forward",
-           "pack_eb_params", "ACT_NONE", "ACT_RELU", "ACT_LRELU01", "ACT_LRELU001", "ACT_EXP", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_FAST"]
+           "pack_eb_params", "cdf_table_factorized", "cdf_table_laplace", "entropy_encode_factorized",
+           "entropy_encode_laplace", "entropy_decode_factorized", "entropy_decode_laplace", "ACT_NONE", "ACT_RELU", "ACT_LRELU01", "ACT_LRELU001", "ACT_EXP", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_FAST"]
 
 
 def _cuda_f32(t, name):
@@ -173,3 +174,94 @@ def gaussian_forward(x, scales, means=None):
     check(lib().fvc_gaussian_forward(ptr(x), ptr(scales), mp, ptr(xh), ptr(lik), ptr(bits), x.numel(), stream_ptr()),
           "fvc_gaussian_forward")
     return xh, lik, bits
+
+
+# ------------------------------------------------------------------------------------------------
+# real entropy coding (calrealbits branch of net.py:123-138, 155-168, 183-195; csrc/fvc_entropy.cu)
+# ------------------------------------------------------------------------------------------------
+def cdf_table_factorized(params, mxrange=150):
+    """Integer CDF tables [C, 2*mxrange] (int64 view of the library's uint32) of a BitEstimator: what the reference
+    hands to torchac, ``cdf[i] = bitEstimator(i - mxrange - 0.5)`` converted to 16 bits (net.py:158-160)."""
+    ps = [_cuda_f32(p, "param").reshape(-1) for p in params]
+    Cc = ps[0].numel()
+    if len(ps) != 11 or any(p.numel() != Cc for p in ps):
+        raise ValueError("need 11 parameter vectors of length C")
+    arr = (C.c_void_p * 11)(*[p.data_ptr() for p in ps])
+    out = torch.empty((Cc, 2 * mxrange), device=ps[0].device, dtype=torch.int32)
+    check(lib().fvc_cdf_table_factorized(arr, Cc, int(mxrange), ptr(out), stream_ptr()), "fvc_cdf_table_factorized")
+    return out
+
+
+def cdf_table_laplace(sigma, mxrange=150):
+    """Per-element integer CDF tables sigma.shape + [2*mxrange] of Laplace(0, clamp(sigma)) (net.py:127-128, 141-143).
+    Test use: the coder itself never materialises them."""
+    sigma = _cuda_f32(sigma, "sigma")
+    out = torch.empty(tuple(sigma.shape) + (2 * mxrange,), device=sigma.device, dtype=torch.int32)
+    check(lib().fvc_cdf_table_laplace(ptr(sigma), sigma.numel(), int(mxrange), ptr(out), stream_ptr()),
+          "fvc_cdf_table_laplace")
+    return out
+
+
+def _entropy_finish(buf, nbytes, err, what):
+    e = err.cpu().tolist()
+    if e[0] or e[1] or e[2]:
+        raise _lib.FvcError("%s: %d symbols outside [-mxrange, mxrange-2], %d empty intervals, %d unreadable lanes"
+                            % (what, e[0], e[1], e[2]))
+    return bytes(buf[:int(nbytes.item())].cpu().numpy().tobytes())
+
+
+def entropy_encode_factorized(x_nhwc, table, mxrange=150, lane_len=8192):
+    """rANS-codes round(x) (x: [..., C] channels-last, fp32) under per-channel tables [C, 2*mxrange]; returns bytes."""
+    x = _cuda_f32(x_nhwc, "x")
+    Cc, n = x.shape[-1], x.numel()
+    cap = lib().fvc_entropy_stream_capacity(n, lane_len)
+    buf = torch.empty(cap, device=x.device, dtype=torch.uint8)
+    nbytes = torch.zeros(1, device=x.device, dtype=torch.int32)
+    err = torch.zeros(3, device=x.device, dtype=torch.int32)
+    check(lib().fvc_entropy_encode_factorized(ptr(x), n, Cc, ptr(table.contiguous()), int(mxrange), int(lane_len), ptr(buf),
+                                              cap, ptr(nbytes), ptr(err), stream_ptr()), "fvc_entropy_encode_factorized")
+    return _entropy_finish(buf, nbytes, err, "entropy_encode_factorized")
+
+
+def entropy_encode_laplace(x, sigma, mxrange=150, lane_len=8192):
+    x, sigma = _cuda_f32(x, "x"), _cuda_f32(sigma, "sigma")
+    n = x.numel()
+    cap = lib().fvc_entropy_stream_capacity(n, lane_len)
+    buf = torch.empty(cap, device=x.device, dtype=torch.uint8)
+    nbytes = torch.zeros(1, device=x.device, dtype=torch.int32)
+    err = torch.zeros(3, device=x.device, dtype=torch.int32)
+    check(lib().fvc_entropy_encode_laplace(ptr(x), ptr(sigma), n, int(mxrange), int(lane_len), ptr(buf), cap, ptr(nbytes),
+                                           ptr(err), stream_ptr()), "fvc_entropy_encode_laplace")
+    return _entropy_finish(buf, nbytes, err, "entropy_encode_laplace")
+
+
+def _stream_tensor(stream, device):
+    import numpy as np
+    pad = (-len(stream)) % 4
+    return torch.from_numpy(np.frombuffer(stream + b"\0" * pad, dtype=np.uint8).copy()).to(device)
+
+
+def entropy_decode_factorized(stream, shape_nhwc, table, mxrange=150, lane_len=8192):
+    """Inverse of entropy_encode_factorized: returns the integer-valued fp32 tensor of shape ``shape_nhwc``."""
+    dev = table.device
+    st = _stream_tensor(stream, dev)
+    q = torch.empty(tuple(shape_nhwc), device=dev, dtype=torch.float32)
+    err = torch.zeros(3, device=dev, dtype=torch.int32)
+    check(lib().fvc_entropy_decode_factorized(ptr(st), len(stream), q.numel(), shape_nhwc[-1], ptr(table.contiguous()),
+                                              int(mxrange), int(lane_len), ptr(q), ptr(err), stream_ptr()),
+          "fvc_entropy_decode_factorized")
+    if int(err[2]):
+        raise _lib.FvcError("entropy_decode_factorized: %d lanes could not be opened" % int(err[2]))
+    return q
+
+
+def entropy_decode_laplace(stream, sigma, mxrange=150, lane_len=8192):
+    sigma = _cuda_f32(sigma, "sigma")
+    st = _stream_tensor(stream, sigma.device)
+    q = torch.empty_like(sigma)
+    err = torch.zeros(3, device=sigma.device, dtype=torch.int32)
+    check(lib().fvc_entropy_decode_laplace(ptr(st), len(stream), q.numel(), ptr(sigma), int(mxrange), int(lane_len), ptr(q),
+                                           ptr(err), stream_ptr()), "fvc_entropy_decode_laplace")
+    if int(err[2]):
+        raise _lib.FvcError("entropy_decode_laplace: %d lanes could not be opened" % int(err[2]))
+    return q

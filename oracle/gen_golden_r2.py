@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference):
 
-    python -m oracle.gen_golden_r2 [real] [hd] [l6]
+    python -m oracle.gen_golden_r2 [real] [hd] [l6] [entropy]
 
 Writes
   tests/golden/spynet_real.npz      : the reference's own pretrained SpyNet weights, levels 1-4
@@ -132,17 +132,46 @@ def gen_l6():
     np.savez_compressed(os.path.join(GOLD, "pframe_L6_256.npz"), **_np(d))
 
 
+def gen_entropy():
+    """tests/golden/entropy_tables.npz: the float CDF tables of the calrealbits branch exactly as the reference builds
+    them (net.py:127-128 with torch.distributions.Laplace, 158-159 / 186-187 with its BitEstimator modules)."""
+    sd = init_state_dict(0)
+    g = torch.Generator().manual_seed(91)
+    for k in list(sd):                       # trained estimators are far from the N(0, 0.01) init: widen the test range
+        if k.startswith("bitEstimator"):
+            sd[k] = sd[k] + 0.5 * torch.randn(sd[k].shape, generator=g)
+    model = ref_shim.build_reference_model(sd)
+    mx = model.mxrange
+    d = {"mxrange": np.asarray(mx)}
+    with torch.no_grad():
+        for name, be in (("z", model.bitEstimator_z), ("mv", model.bitEstimator_mv)):
+            cdfs = [be(torch.zeros(1, be.f1.h.shape[1], 1, 1) + (i - 0.5)).view(-1, 1) for i in range(-mx, mx)]
+            d["cdf_" + name] = torch.cat(cdfs, 1)                                   # [C, 2*mxrange]
+        sigma = torch.exp(torch.randn((3, 5, 7), generator=g) * 2.5)
+        sigma[0, 0, :3] = torch.tensor([0.0, 1e-7, 1e12])
+        sg = sigma.clamp(1e-5, 1e10)
+        lap = torch.distributions.laplace.Laplace(torch.zeros_like(sg), sg)
+        d["lap_sigma"] = sigma
+        d["cdf_lap"] = torch.cat([lap.cdf(torch.zeros_like(sg) + (i - 0.5)).unsqueeze(-1) for i in range(-mx, mx)], -1)
+    for k in sd:
+        if k.startswith("bitEstimator"):
+            d["sd." + k] = sd[k]
+    np.savez_compressed(os.path.join(GOLD, "entropy_tables.npz"), **_np(d))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    what = sys.argv[1:] or ["real", "l6", "hd"]
+    what = sys.argv[1:] or ["real", "l6", "hd", "entropy"]
     if "real" in what:
         gen_real()
     if "l6" in what:
         gen_l6()
     if "hd" in what:
         gen_hd()
+    if "entropy" in what:
+        gen_entropy()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -1110,3 +1110,22 @@ def test_fast_precision_hd_gop_metric_parity(fast_model, golden_hd_gop10, dev):
     assert abs(got_bpp - want_bpp) <= 0.005 * want_bpp
     assert abs(got_psnr - want_psnr) <= 0.02
     fast_model.release()
+
+
+def test_torch_library_ops_run_the_library(model, golden_pframe_64, dev):
+    """torch.ops.fvc.* (torch_ops.py) are the same calls as the module / ops surface."""
+    from fastvideocodec_b200 import ops
+    g = golden_pframe_64
+    model.impl = _impls()[-1][1]
+    with torch.no_grad():
+        out = model(g["cur"].to(dev), g["ref"].to(dev))
+        ctx = model._last_ctx
+        recon, sc = torch.ops.fvc.pframe_forward(g["cur"].to(dev), g["ref"].to(dev), ctx.handle)
+    assert torch.equal(recon, out[0]) and torch.equal(sc, torch.stack(out[1:]))
+    rec2 = torch.ops.fvc.decode_from_latents(g["ref"].to(dev), g["quant_mv"].to(dev), g["feat_hat"].to(dev), ctx.handle)
+    assert (rec2.cpu() - g["clipped"]).abs().max().item() <= 1e-3
+    img, flow = torch.rand((1, 3, 32, 48), device=dev), torch.randn((1, 2, 32, 48), device=dev)
+    assert torch.equal(torch.ops.fvc.flow_warp(img, flow), ops.flow_warp(img, flow))
+    w, b = torch.randn((16, 8, 3, 3), device=dev) * 0.1, torch.zeros(16, device=dev)
+    x = torch.randn((1, 8, 16, 24), device=dev)
+    assert torch.equal(torch.ops.fvc.conv2d(x, w, b, 1, False, 1, 1), ops.conv2d(x, w, b, 1, 1))

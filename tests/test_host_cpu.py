@@ -273,3 +273,38 @@ def test_entropy_models_surface():
     m.set_RPM(False)
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 8, 2, 2), torch.zeros(1))
+
+
+def test_torch_library_ops_registered_with_fake_kernels():
+    """north_star / SURVEY 8b: the C-ABI entry points are reachable as torch.library custom ops (fvc::*); the fake
+    (meta) kernels propagate shapes without a GPU."""
+    import fastvideocodec_b200  # noqa: F401  (registers the ops)
+    x = torch.empty((2, 3, 128, 192), device="meta")
+    recon, scalars = torch.ops.fvc.pframe_forward(x, x, 0)
+    assert recon.shape == x.shape and scalars.shape == (7,)
+    q = torch.empty((2, 128, 8, 12), device="meta")
+    f = torch.empty((2, 96, 8, 12), device="meta")
+    assert torch.ops.fvc.decode_from_latents(x, q, f, 0).shape == x.shape
+    assert torch.ops.fvc.flow_warp(x, torch.empty((2, 2, 128, 192), device="meta")).shape == x.shape
+    y = torch.ops.fvc.conv2d(torch.empty((1, 64, 32, 32), device="meta"), torch.empty((96, 64, 5, 5), device="meta"),
+                             torch.empty(96, device="meta"), 2, False, 0, 1)
+    assert y.shape == (1, 96, 16, 16)
+    qq, bits = torch.ops.fvc.quant_bits_laplace(f, f)
+    assert qq.shape == f.shape and bits.shape == ()
+    # no CPU kernel is registered: the product path fails loudly without the CUDA library
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.fvc.flow_warp(torch.zeros((1, 3, 8, 8)), torch.zeros((1, 2, 8, 8)))
+
+
+def test_video_compressor_extensions_and_validation():
+    from fastvideocodec_b200 import VideoCompressor
+    from fastvideocodec_b200._lib import IMPL_TC, IMPL_TC_FAST
+    assert VideoCompressor().impl == IMPL_TC and VideoCompressor(precision="fast").impl == IMPL_TC_FAST
+    with pytest.raises(ValueError):
+        VideoCompressor(precision="bf16")
+    m = VideoCompressor()
+    assert m.calrealbits is False and m.mxrange == 150 and m.max_contexts >= 1
+    with pytest.raises(TypeError):
+        m.gop_forward_host(torch.zeros((2, 1, 3, 64, 64), dtype=torch.float64))
+    with pytest.raises(ValueError):
+        m.gop_forward_host(torch.zeros((1, 1, 3, 64, 64)))
