@@ -89,6 +89,22 @@ int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int 
     ep.acc_scale = 1.f;
     ep.act = act;
     ep.out_f32 = out_nhwc;
+    // test hook: FVC_CONV2D_VIA_ACT=1 (2: parity-planar) writes the result as an ACT record tensor, the way the layers
+    // of the frame pipeline hand their outputs on (exercises the ACT / TMA-store epilogues), and converts it back
+    ActT via;
+    memset(&via, 0, sizeof(via));
+    {
+        const char* va = getenv("FVC_CONV2D_VIA_ACT");
+        const int mode = va ? atoi(va) : 0;
+        if (mode && impl != FVC_IMPL_SIMT) {
+            via.B = B; via.H = Ho; via.W = Wo; via.Cp = pad_c(Cout);
+            via.parity = (mode == 2 && Ho % 2 == 0 && Wo % 2 == 0 && !(transposed && stride == 2)) ? 1 : 0;
+            if (tmp.get(&via.p, act_bytes(B, Ho, Wo, via.Cp))) return FVC_ERR_CUDA;
+            FVC_CUDA(cudaMemsetAsync(via.p, 0, act_bytes(B, Ho, Wo, via.Cp), s));
+            ep.out_act = via;
+            ep.out_f32 = nullptr;
+        }
+    }
     if (impl != FVC_IMPL_SIMT) {
         if (!tc_supported(L, in.Cp)) {
             set_error("fvc_conv2d: shape not supported by the tcgen05 engine");
@@ -101,6 +117,7 @@ int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int 
         if (rc == 0) rc = (cudaStreamSynchronize(s) == cudaSuccess) ? 0 : cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
         tc_plan_destroy(plan);
         if (rc) return rc;
+        if (via.p) return launch_act_to_nchw(via, Cout, y, s);
     } else {
         SimtWeights sw;
         rc = simt_pack_weights(L, w, in.Cp, std::max(pad_c(Cout), 32), &sw, s);

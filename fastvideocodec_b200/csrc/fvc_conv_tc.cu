@@ -95,6 +95,14 @@ struct alignas(64) TcParams {
     uint32_t acc_sleep_ns;
     unsigned long long* dbg;   // optional [8] cycle counters of block 0's MMA issuer (FVC_TC_DEBUG=1)
     int planes;       // 1 or 4 (parity-planar input)
+    // TMA-store epilogue: the ACT output tile is staged in shared memory ([sub-tile][segment][128 pixel rows][128 B],
+    // SWIZZLE_128B) and written with cp.async.bulk.tensor stores (full 128-byte lines, no LSU global traffic)
+    CUtensorMap mapO;
+    int tmast;        // 0: per-lane st.global epilogue; 1: staged + TMA stores (out_act only)
+    int o_mode;       // 0: plain NHWC output; 1: parity-planar output (4 plane boxes per segment); 2: stride-2 transposed
+                      //    conv (output pixel = 2q + phase: boxes with element stride 2)
+    int o_nseg;       // 128-byte segments per output record (Cp / 32)
+    uint32_t stg_bytes;
     Epilogue ep;
 };
 
@@ -186,6 +194,39 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 16 output channels (c0 % 16 == 0) of one pixel into the staging tile: the record [hi Cp | lo Cp] is cut into 128-byte
+// segments, one [128 rows][128 B] block per (sub-tile, segment); 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+// (SWIZZLE_128B, the layout the store's tensor map expects; it also makes the 32 lanes of a warp, which are 32
+// different rows writing the same logical chunk, hit 8 different bank groups: 4 wavefronts per 512 bytes, the minimum).
+__device__ __forceinline__ void stage_store16(uint32_t stg, int s, int nseg, int Cp, int row, int c0, const float* v16,
+                                              uint32_t& satm, bool with_lo) {
+    uint32_t hi[8], lo[8];
+    ep_pack8(v16, false, hi, lo, satm);
+    ep_pack8(v16 + 8, false, hi + 4, lo + 4, satm);
+    const uint32_t sw = (uint32_t)(row & 7);
+    {
+        const uint32_t off = 2u * (uint32_t)c0;                       // byte offset of the hi chunk pair in the record
+        const uint32_t blk = stg + ((((uint32_t)(s * nseg) + (off >> 7)) * 128u + (uint32_t)row) << 7);
+        const uint32_t ch = (off & 127u) >> 4;                         // even
+        st_shared_v4(blk + ((ch ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(blk + (((ch + 1u) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+    }
+    if (with_lo) {
+        const uint32_t off = 2u * (uint32_t)(Cp + c0);
+        const uint32_t blk = stg + ((((uint32_t)(s * nseg) + (off >> 7)) * 128u + (uint32_t)row) << 7);
+        const uint32_t ch = (off & 127u) >> 4;
+        st_shared_v4(blk + ((ch ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+        st_shared_v4(blk + (((ch + 1u) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+    }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -344,7 +385,8 @@ struct PassIter {
 // (ncu: the per-chunk version was stall_long_sb-bound and starved the MMA pipe).
 template <int NCH, bool RES>
 __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __restrict__ bias_s, const float* run,
-                                              int b, int sub, int ty, int tx, int th, int tw, uint32_t colbase) {
+                                              int b, int sub, int ty, int tx, int th, int tw, uint32_t colbase,
+                                              uint32_t stg) {
     const Epilogue& ep = P.ep;
     constexpr int HB = NCH > 4 ? 2 : NCH;   // chunks per batch (register budget: 96 regs at 576 threads)
     const int N = P.merged ? (P.N >> 1) : P.N, Cout = P.Cout, act = ep.act;   // channels per sub-tile
@@ -360,6 +402,8 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
     const e16* rec_res = nullptr;
     size_t pixC = 0;   // pixel index * Cout (fp32 NHWC tensors)
     const bool wlo = P.fast == 0;   // precision 'fast': only the hi halves of ACT outputs are written
+    // staging row of this thread's pixel (TMA-store epilogue): the order in which the store boxes enumerate the pixels
+    const int srow = P.o_mode == 1 ? ((((th & 1) << 1) | (tw & 1)) * 32 + (th >> 1) * 4 + (tw >> 1)) : (th * 8 + tw);
     uint32_t satm = 0; // running max |hi| of the ACT values this thread stores (range check, see ep_sat_track)
     auto enter_pixel = [&](int s) {
         cur_s = s;
@@ -496,7 +540,10 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
             }
             const int c0 = cc[j0];
             if (PAIR == 2) {
-                if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store16_packed(rec_out, ep.out_act.Cp, c0, v, false, satm, wlo);
+                if (ep.out_act.p && c0 < ep.out_act.Cp) {
+                    if (stg) stage_store16(stg, ss[j0], P.o_nseg, ep.out_act.Cp, srow, c0, v, satm, wlo);
+                    else ep_store16_packed(rec_out, ep.out_act.Cp, c0, v, false, satm, wlo);
+                }
                 if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store16_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm, wlo);
             } else {
                 if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false, satm, wlo);
@@ -524,12 +571,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     // 1024-byte alignment: SWIZZLE_128B atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t patch0 = base;                                   // npb patch buffers
-    const uint32_t bst0 = base + P.npb * P.patch_bytes;             // nst weight stages of T tiles
+    const uint32_t stg0 = base + P.npb * P.patch_bytes;             // staging tile of the TMA-store epilogue (or empty)
+    const uint32_t bst0 = stg0 + P.stg_bytes;                       // nst weight stages of T tiles
     const uint32_t bars = bst0 + P.nst * P.stage_bytes;             // mbarriers (8 B each)
     const uint32_t bar_pfull = bars, bar_pempty = bars + 16;        // [npb <= 2] each
     const uint32_t bar_bfull = bars + 32, bar_bempty = bars + 32 + 8 * 8;   // [nst <= 8] each
     const uint32_t bar_afull = bars + 32 + 16 * 8, bar_aempty = bar_afull + 32;  // partial buffers [<= 4] each
     const uint32_t tmem_slot = bar_aempty + 32;
+    const uint32_t bar_sfull = tmem_slot + 8, bar_sempty = tmem_slot + 16;   // staging tile of the TMA-store epilogue
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 256);   // [N <= 128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -553,6 +602,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, TC_ISSUERS);
         }
+        mbar_init(bar_sfull, 16);    // one arrive per accumulator warp: the tile is staged
+        mbar_init(bar_sempty, 1);    // the store manager: the bulk stores have read the staging tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -646,6 +697,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 if (progress) spins = 0;
                 else if (++spins > (1u << 25)) __trap();
             }
+        }
+        else if (lane == 1 && P.tmast) {
+            // ================= store manager: staged output tiles -> global memory (bulk tensor stores) =========
+            // one box per (sub-tile, segment) (x 4 planes for parity-planar outputs); walks the tiles like the
+            // accumulator warps
+            const int nseg = P.o_nseg;
+            uint32_t k = 0;
+            for (int tile = tile0; tile < ntiles; tile += tstride, ++k) {
+                int t = tile;
+                const int tx = (t % P.tiles_x) * xmul + xadd; t /= P.tiles_x;
+                const int ty = t % P.tiles_y; t /= P.tiles_y;
+                const int sub = t % P.nsub;
+                const int b = t / P.nsub;
+                mbar_wait(bar_sfull, k & 1u);
+                for (int sI = 0; sI < P.S; ++sI) {
+                    const int qx0 = (tx * P.SX + sI) * 8;
+                    if (qx0 >= P.Wq) break;
+                    for (int g = 0; g < nseg; ++g) {
+                        const uint32_t src = stg0 + (uint32_t)(sI * nseg + g) * 16384u;
+                        if (P.o_mode == 0) {
+                            tma_store_5d(&P.mapO, src, 0, g, qx0, ty * 16, b);
+                        } else if (P.o_mode == 1) {
+                            for (int pl = 0; pl < 4; ++pl)
+                                tma_store_5d(&P.mapO, src + (uint32_t)pl * 4096u, 0, g, qx0 >> 1, ty * 8, b * 4 + pl);
+                        } else {
+                            tma_store_5d(&P.mapO, src, 0, g, qx0 * 2 + P.sub[sub].px, ty * 32 + P.sub[sub].py, b);
+                        }
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(bar_sempty);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp >= 1 && warp <= TC_ISSUERS && rank == 0) {
         // ================================ MMA issuers ============================================
@@ -827,6 +912,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const uint32_t aempty_l = PAIR ? mapa_u32(bar_aempty, 0) : bar_aempty;   // the leader's issuers wait on it
         uint32_t gg = 0;
         float run[NCH * 8];
+        const uint32_t stg = P.tmast ? stg0 : 0u;
+        uint32_t tile_k = 0;      // tiles finished by this warp (phase of the staging barriers)
+        if (stg) {
+            // channels of the output records beyond the computed ones are never written by the epilogue: they must
+            // reach memory as zeros (the consumers multiply them by zero weights; NaN bit patterns would poison that)
+            for (uint32_t o = ((uint32_t)threadIdx.x - TC_ACC_WARP0 * 32u) * 16u; o < P.stg_bytes; o += 512u * 16u)
+                st_shared_v4(stg + o, 0u, 0u, 0u, 0u);
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // once per kernel, among the accumulator warps
+        }
         const int tiles_xy = P.tiles_x * P.tiles_y;
 #ifdef FVC_TC_ACCDBG
         const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == TC_ACC_WARP0;
@@ -911,6 +1005,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const int ty = t % P.tiles_y; t /= P.tiles_y;
             const int sub = t % P.nsub;
             const int b = t / P.nsub;
+            if (stg) {
+                // the staging tile is free once the previous tile's bulk stores have read it (store manager, warp 0);
+                // no warp waits for another accumulator warp here: a barrier across the 16 warps at this point cost
+                // the tensor-bound 3x3 layers 10 % (every tile then runs at the pace of its slowest warp)
+                mbar_wait_sleep(bar_sempty, (tile_k & 1u) ^ 1u, 32);
+            }
             if constexpr (!PARK) {
                 if constexpr (NCH % 2 == 0) {
                     if (P.merged) {
@@ -919,12 +1019,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         for (int i = 0; i < NCH / 2; ++i)
 #pragma unroll
                             for (int q = 0; q < 8; ++q) run[i * 8 + q] = run[2 * i * 8 + q] + run[(2 * i + 1) * 8 + q];
-                        tile_epilogue<NCH / 2, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase >> 1);
+                        tile_epilogue<NCH / 2, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase >> 1, stg);
                     } else {
-                        tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+                        tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
                     }
                 } else {
-                    tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+                    tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
                 }
             } else {
                 // 48/64 running sums + the epilogue state do not fit 96 registers (ncu: spill reloads
@@ -937,7 +1037,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
                 for (int i = NH; i < NCH; ++i) tc_st8(taddr + i * 8, reinterpret_cast<const uint32_t*>(run + i * 8));
                 tc_wait_st();
-                tile_epilogue<NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase);
+                tile_epilogue<NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
 #pragma unroll
                 for (int i = NH; i < NCH; ++i) {
                     tc_ld8(taddr + i * 8, reinterpret_cast<uint32_t*>(run + (i - NH) * 8));
@@ -949,12 +1049,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     if (PAIR) mbar_arrive_cluster(aempty_l + 8 * pb);
                     else mbar_arrive(bar_aempty + 8 * pb);
                 }
-                tile_epilogue<NCH - NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase + NH * 8);
+                tile_epilogue<NCH - NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase + NH * 8, stg);
+            }
+            if (stg) {
+                // generic-proxy writes of the staging tile -> visible to the async proxy, then hand over to the manager
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sfull);
+                ++tile_k;
             }
 #ifdef FVC_TC_ACCDBG
             if (adbg) a_epi += clock64() - e0;
 #endif
         }
+
 #ifdef FVC_TC_ACCDBG
         if (adbg && lane == 0) { P.dbg[4] = (unsigned long long)a_wait; P.dbg[5] = (unsigned long long)a_drain; P.dbg[6] = (unsigned long long)a_epi; }
 #endif
@@ -1171,7 +1279,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     }
     // ---- tile shape -------------------------------------------------------------------------------
     const int pw_align = env_int("FVC_TC_PW_ALIGN", 1);
-    const int smem_cap = 232448 - 1024 /*alignment*/ - 1024 /*barriers + bias*/;
+    const int smem_cap = 232448 - 1024 /*alignment*/ - 1024 /*barriers + bias*/ - env_int("FVC_TC_SMEM_RESERVE", 0);
     const int pitch = Cp == 8 ? 32 : 128;
     P.pitch = pitch;
     // CTA pairs (cta_group::2): two x-neighbouring tiles are one M = 256 MMA; each CTA stages half of every weight
@@ -1180,6 +1288,24 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0;
     P.pair = pair ? 1 : 0;
     const int tile_bytes = N * pitch / (pair ? 2 : 1);   // per CTA
+    // TMA-store epilogue (FVC_TC_TMAST: 0 off, 1 auto [default], 2 every eligible layer): the out_act tile is staged in
+    // shared memory and written by bulk tensor stores.  Eligible: an ACT output with >= 32-channel records, outputs of
+    // stride-2 transposed convolutions only when not parity-planar.  Auto skips the 7x7 layers with wide inputs: their
+    // patches leave no room for the staging tile next to a deep weight ring, and they are tensor-bound anyway.
+    const int tmast_env = env_int("FVC_TC_TMAST", 1);
+    int o_mode = 0;
+    bool tmast = tmast_env != 0 && ep.out_act.p != nullptr && ep.out_act.Cp >= 32 && ep.out_act.Cp <= 128;
+    if (tmast) {
+        if (L.os == 2) {
+            o_mode = 2;
+            if (ep.out_act.parity || env_int("FVC_TC_TMAST_OS2", 1) == 0) tmast = false;
+        } else if (ep.out_act.parity) {
+            o_mode = 1;
+            if ((Hout & 1) || (Wout & 1)) tmast = false;
+        }
+        if (tmast_env == 1 && L.k == 7 && Cp >= 32) tmast = false;
+    }
+    int o_nseg = tmast ? ep.out_act.Cp / 32 : 0;
     int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y, npb = 2, T = 1;
     // S sub-tiles of 128 pixels share every weight stage; CT = S*N accumulator columns per partial buffer,
     // CT/32 in {1,2,3,4,6,8} (template instantiations), CT <= 256.  Two patch buffers when that still leaves room
@@ -1204,11 +1330,18 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    for (int attempt = 0; attempt < 2 && !SX; ++attempt) {
+    if (attempt == 1) {
+        if (!tmast) break;
+        tmast = false;      // no shape leaves room for the staging tile: per-lane stores for this layer
+    }
     double best_eff = -1.0;
     for (int sx = std::max(1, sx_max); sx >= 1; --sx) {
         const int ct32 = sx * N / 32;
         if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
         if (merged && (ct32 & 1)) continue; // a thread must own both column blocks (hi, lo) of its channel chunks
+        if (tmast && (((merged ? ct32 / 2 : ct32) & 1) != 0)) continue;   // staged stores work on 16-channel pairs
+        const long stage_need = tmast ? (long)sx * o_nseg * 16384L : 0L;
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * pitch;
@@ -1219,7 +1352,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         if (eff <= best_eff + 0.02) continue;   // a smaller S must buy a real gain
         bool fits = false;
         for (int nb = 2; nb >= 1 && !fits; --nb) {
-            const long wroom = (long)smem_cap - (long)nb * (long)patch;
+            const long wroom = (long)smem_cap - (long)nb * (long)patch - stage_need;
             const long want = nb == 2 ? std::min<long>(48 * 1024, 6L * tile_bytes) : 2L * tile_bytes;
             if (wroom < want) continue;
             int t = (int)std::max<long>(1, std::min<long>(tmax, wroom / (4L * tile_bytes)));
@@ -1232,12 +1365,18 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         if (!fits) continue;
         best_eff = eff;
     }
+    }
     if (!SX) {
         set_error("tc_plan_create: no tile shape fits shared memory");
         delete plan;
         return FVC_ERR_STATE;
     }
     P.S = SX; P.SX = SX; P.PW = PW; P.PH = PH; P.nst = nst; P.npb = npb; P.T = T;
+    if (!tmast) o_nseg = 0;
+    P.tmast = tmast ? 1 : 0;
+    P.o_mode = o_mode;
+    P.o_nseg = o_nseg;
+    P.stg_bytes = tmast ? (uint32_t)(SX * o_nseg * 16384) : 0u;
     P.CT = SX * N;
     P.patch_bytes = (uint32_t)((((size_t)PH * PW * pitch) + 1023) & ~(size_t)1023);
     P.patch_tx = (uint32_t)((size_t)PH * PW * pitch);
@@ -1436,12 +1575,32 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             return FVC_ERR_CUDA;
         }
     }
+    if (tmast) {
+        const ActT& o = ep.out_act;
+        const cuuint64_t rec = (cuuint64_t)o.Cp * 4;
+        const int Wd = o.parity ? o.W / 2 : o.W, Hd = o.parity ? o.H / 2 : o.H;
+        cuuint64_t dims[5] = {64, (cuuint64_t)o_nseg, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)(o.B * (o.parity ? 4 : 1))};
+        cuuint64_t strides[4] = {128, rec, rec * Wd, rec * Wd * Hd};
+        cuuint32_t box[5] = {64, 1, 8, 16, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        if (o_mode == 1) { box[2] = 4; box[3] = 8; }
+        if (o_mode == 2) { box[2] = 16; box[3] = 32; estr[2] = 2; estr[3] = 2; }   // 8 x 16 pixels at stride 2
+        CUresult r = encode(&P.mapO, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 5,
+                            (void*)o.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(O) failed: %d (Cp=%d W=%d H=%d mode=%d)", (int)r, o.Cp, Wd, Hd, o_mode);
+            cudaFree(plan->wstream);
+            delete plan;
+            return FVC_ERR_CUDA;
+        }
+    }
     P.acc_sleep_ns = (uint32_t)env_int("FVC_TC_ACC_SLEEP", 100);
     if (env_int("FVC_TC_DEBUG", 0)) {
         if (cudaMalloc(&plan->dbg, 64) == cudaSuccess) cudaMemset(plan->dbg, 0, 64);
         P.dbg = plan->dbg;
     }
-    plan->smem = 1024 + (size_t)npb * P.patch_bytes + (size_t)nst * P.stage_bytes + 1024;
+    plan->smem = 1024 + (size_t)npb * P.patch_bytes + (size_t)P.stg_bytes + (size_t)nst * P.stage_bytes + 1024;
     int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;
     plan->grid = pair ? 2 * std::max(1, std::min(ntiles, sms / 2)) : std::max(1, std::min(ntiles, sms));
     *out = plan;

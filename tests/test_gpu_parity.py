@@ -1129,3 +1129,31 @@ def test_torch_library_ops_run_the_library(model, golden_pframe_64, dev):
     w, b = torch.randn((16, 8, 3, 3), device=dev) * 0.1, torch.zeros(16, device=dev)
     x = torch.randn((1, 8, 16, 24), device=dev)
     assert torch.equal(torch.ops.fvc.conv2d(x, w, b, 1, False, 1, 1), ops.conv2d(x, w, b, 1, 1))
+
+
+@pytest.mark.parametrize("case", CONV_CASES + [(64, 64, 3, 1, 0, 1, 40, 72), (128, 128, 3, 2, 1, 2, 20, 36),
+                                               (128, 128, 3, 1, 0, 2, 34, 50), (6, 64, 3, 1, 0, 1, 30, 44)])
+@pytest.mark.parametrize("layout", [1, 2])
+def test_tma_store_epilogue_bit_identical_to_lane_stores(dev, case, layout, monkeypatch):
+    """The TMA-store epilogue (ACT tile staged in shared memory, cp.async.bulk.tensor stores; plain, parity-planar and
+    stride-2-phase outputs) must write exactly the bytes of the per-lane st.global epilogue: same arithmetic, only
+    the way the records reach memory differs.  Outputs go through ACT records (FVC_CONV2D_VIA_ACT), as in the frame
+    pipeline; image sizes include partial tiles at both edges."""
+    from fastvideocodec_b200 import ops
+    cin, cout, k, stride, transposed, act, H, W = case
+    if cout < 8:
+        pytest.skip("2-3 output channels: fp32 outputs only in the pipeline")
+    torch.manual_seed(17)
+    x = torch.randn(2, cin, H, W)
+    w = torch.randn((cin, cout, k, k) if transposed else (cout, cin, k, k)) / (cin * k * k) ** 0.5
+    b = torch.randn(cout)
+    f = ops.conv_transpose2d if transposed else ops.conv2d
+    monkeypatch.setenv("FVC_CONV2D_VIA_ACT", str(layout))
+    monkeypatch.setenv("FVC_TC_TMAST", "2")
+    y_tma = f(x.to(dev), w.to(dev), b.to(dev), stride, act).cpu()
+    monkeypatch.setenv("FVC_TC_TMAST", "0")
+    y_lane = f(x.to(dev), w.to(dev), b.to(dev), stride, act).cpu()
+    monkeypatch.delenv("FVC_CONV2D_VIA_ACT")
+    y_f32 = f(x.to(dev), w.to(dev), b.to(dev), stride, act).cpu()
+    assert torch.equal(y_tma, y_lane), (y_tma - y_lane).abs().max().item()
+    assert (y_lane - y_f32).abs().max().item() <= 2e-6 * max(1.0, y_f32.abs().max().item())
