@@ -95,13 +95,14 @@ struct alignas(64) TcParams {
     uint32_t acc_sleep_ns;
     unsigned long long* dbg;   // optional [8] cycle counters of block 0's MMA issuer (FVC_TC_DEBUG=1)
     int planes;       // 1 or 4 (parity-planar input)
-    // TMA-store epilogue: the ACT output tile is staged in shared memory ([sub-tile][segment][128 pixel rows][128 B],
-    // SWIZZLE_128B) and written with cp.async.bulk.tensor stores (full 128-byte lines, no LSU global traffic)
+    // TMA-store epilogue (per warp): every accumulator warp stages the 32 pixels x 32 channels it owns in its own 4 KB of
+    // shared memory ([32 rows][64 B] hi block + lo block, SWIZZLE_64B) and writes them with two cp.async.bulk.tensor
+    // stores; no synchronisation across warps
     CUtensorMap mapO;
-    int tmast;        // 0: per-lane st.global epilogue; 1: staged + TMA stores (out_act only)
-    int o_mode;       // 0: plain NHWC output; 1: parity-planar output (4 plane boxes per segment); 2: stride-2 transposed
+    int tmast;        // 0: per-lane st.global epilogue; 1: per-warp staged TMA stores (out_act only)
+    int o_mode;       // 0: plain NHWC output; 1: parity-planar output (4 plane boxes); 2: stride-2 transposed
                       //    conv (output pixel = 2q + phase: boxes with element stride 2)
-    int o_nseg;       // 128-byte segments per output record (Cp / 32)
+    int o_nseg;       // 64-byte pieces of the hi half of an output record (Cp / 32); the lo half follows
     uint32_t stg_bytes;
     Epilogue ep;
 };
@@ -203,29 +204,22 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// 16 output channels (c0 % 16 == 0) of one pixel into the staging tile: the record [hi Cp | lo Cp] is cut into 128-byte
-// segments, one [128 rows][128 B] block per (sub-tile, segment); 16-byte chunk j of row r sits at chunk j ^ (r & 7)
-// (SWIZZLE_128B, the layout the store's tensor map expects; it also makes the 32 lanes of a warp, which are 32
-// different rows writing the same logical chunk, hit 8 different bank groups: 4 wavefronts per 512 bytes, the minimum).
-__device__ __forceinline__ void stage_store16(uint32_t stg, int s, int nseg, int Cp, int row, int c0, const float* v16,
-                                              uint32_t& satm, bool with_lo) {
+// 16 output channels (lc = 0 or 2: first or second chunk pair of the thread's 32 channels) of one pixel into the warp's
+// staging blocks: [32 rows][64 B] for the hi halves at wstg, the lo halves 2 KB further; 16-byte chunk j of row r sits at
+// chunk j ^ ((r >> 1) & 3) (SWIZZLE_64B, the layout the store's tensor map expects; the 32 lanes of the warp, 32 rows
+// writing the same logical chunk, then hit 8 different 16-byte bank groups: 4 wavefronts per 512 bytes, the minimum).
+__device__ __forceinline__ void stage_store16(uint32_t wstg, int row, int lc, const float* v16, uint32_t& satm,
+                                              bool with_lo) {
     uint32_t hi[8], lo[8];
     ep_pack8(v16, false, hi, lo, satm);
     ep_pack8(v16 + 8, false, hi + 4, lo + 4, satm);
-    const uint32_t sw = (uint32_t)(row & 7);
-    {
-        const uint32_t off = 2u * (uint32_t)c0;                       // byte offset of the hi chunk pair in the record
-        const uint32_t blk = stg + ((((uint32_t)(s * nseg) + (off >> 7)) * 128u + (uint32_t)row) << 7);
-        const uint32_t ch = (off & 127u) >> 4;                         // even
-        st_shared_v4(blk + ((ch ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
-        st_shared_v4(blk + (((ch + 1u) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
-    }
+    const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+    const uint32_t r0 = wstg + ((uint32_t)row << 6);
+    st_shared_v4(r0 + ((((uint32_t)lc) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+    st_shared_v4(r0 + ((((uint32_t)lc + 1u) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
     if (with_lo) {
-        const uint32_t off = 2u * (uint32_t)(Cp + c0);
-        const uint32_t blk = stg + ((((uint32_t)(s * nseg) + (off >> 7)) * 128u + (uint32_t)row) << 7);
-        const uint32_t ch = (off & 127u) >> 4;
-        st_shared_v4(blk + ((ch ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
-        st_shared_v4(blk + (((ch + 1u) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+        st_shared_v4(r0 + 2048u + ((((uint32_t)lc) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+        st_shared_v4(r0 + 2048u + ((((uint32_t)lc + 1u) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
     }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -383,7 +377,7 @@ struct PassIter {
 // loads (residual) of a batch of chunks are all issued before any of them is consumed and before the
 // batch's stores, so a thread pays one memory round trip per batch instead of one per chunk
 // (ncu: the per-chunk version was stall_long_sb-bound and starved the MMA pipe).
-template <int NCH, bool RES>
+template <int NCH, bool RES, bool STG = false>
 __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __restrict__ bias_s, const float* run,
                                               int b, int sub, int ty, int tx, int th, int tw, uint32_t colbase,
                                               uint32_t stg) {
@@ -401,9 +395,16 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
     e16 *rec_out = nullptr, *rec_relu = nullptr, *rec_sq = nullptr;
     const e16* rec_res = nullptr;
     size_t pixC = 0;   // pixel index * Cout (fp32 NHWC tensors)
+#ifdef FVC_NO_FAST
+    const bool wlo = true;
+#else
     const bool wlo = P.fast == 0;   // precision 'fast': only the hi halves of ACT outputs are written
-    // staging row of this thread's pixel (TMA-store epilogue): the order in which the store boxes enumerate the pixels
-    const int srow = P.o_mode == 1 ? ((((th & 1) << 1) | (tw & 1)) * 32 + (th >> 1) * 4 + (tw >> 1)) : (th * 8 + tw);
+#endif
+    // staging row of this thread's pixel inside its warp's block (TMA-store epilogue): the order in which the store
+    // boxes enumerate the warp's 4 x 8 pixels (parity-planar outputs: plane-major, 2 x 4 pixels per plane)
+    const int lth = th & 3;
+    const int srow = P.o_mode == 1 ? ((((lth & 1) << 1) | (tw & 1)) * 8 + (lth >> 1) * 4 + (tw >> 1)) : (lth * 8 + tw);
+    const int cA = (int)colbase - ((int)colbase / N) * N;      // first channel of this thread inside its sub-tile
     uint32_t satm = 0; // running max |hi| of the ACT values this thread stores (range check, see ep_sat_track)
     auto enter_pixel = [&](int s) {
         cur_s = s;
@@ -541,7 +542,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
             const int c0 = cc[j0];
             if (PAIR == 2) {
                 if (ep.out_act.p && c0 < ep.out_act.Cp) {
-                    if (stg) stage_store16(stg, ss[j0], P.o_nseg, ep.out_act.Cp, srow, c0, v, satm, wlo);
+                    if (STG && stg) stage_store16(stg, srow, (c0 - cA) >> 3, v, satm, wlo);
                     else ep_store16_packed(rec_out, ep.out_act.Cp, c0, v, false, satm, wlo);
                 }
                 if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store16_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm, wlo);
@@ -565,7 +566,9 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
 // quarter 4 times).
 // NCH: 8-column chunks of the running sum each accumulator thread owns (CT/4 = 8*NCH);
 // RES: the epilogue adds an ACT-format residual (ResBlock skip connection)
-template <int NCH, bool RES, bool PAIR>
+// STG: TMA-store epilogue compiled in (CT = 128 kernels only; a separate instantiation so that the default kernels
+// carry none of its code: compiled into the same kernel it cost the skip-connection variant 64 bytes of spills)
+template <int NCH, bool RES, bool PAIR, bool STG = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: SWIZZLE_128B atoms
@@ -578,7 +581,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const uint32_t bar_bfull = bars + 32, bar_bempty = bars + 32 + 8 * 8;   // [nst <= 8] each
     const uint32_t bar_afull = bars + 32 + 16 * 8, bar_aempty = bar_afull + 32;  // partial buffers [<= 4] each
     const uint32_t tmem_slot = bar_aempty + 32;
-    const uint32_t bar_sfull = tmem_slot + 8, bar_sempty = tmem_slot + 16;   // staging tile of the TMA-store epilogue
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 256);   // [N <= 128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -602,8 +604,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, TC_ISSUERS);
         }
-        mbar_init(bar_sfull, 16);    // one arrive per accumulator warp: the tile is staged
-        mbar_init(bar_sempty, 1);    // the store manager: the bulk stores have read the staging tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -697,40 +697,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 if (progress) spins = 0;
                 else if (++spins > (1u << 25)) __trap();
             }
-        }
-        else if (lane == 1 && P.tmast) {
-            // ================= store manager: staged output tiles -> global memory (bulk tensor stores) =========
-            // one box per (sub-tile, segment) (x 4 planes for parity-planar outputs); walks the tiles like the
-            // accumulator warps
-            const int nseg = P.o_nseg;
-            uint32_t k = 0;
-            for (int tile = tile0; tile < ntiles; tile += tstride, ++k) {
-                int t = tile;
-                const int tx = (t % P.tiles_x) * xmul + xadd; t /= P.tiles_x;
-                const int ty = t % P.tiles_y; t /= P.tiles_y;
-                const int sub = t % P.nsub;
-                const int b = t / P.nsub;
-                mbar_wait(bar_sfull, k & 1u);
-                for (int sI = 0; sI < P.S; ++sI) {
-                    const int qx0 = (tx * P.SX + sI) * 8;
-                    if (qx0 >= P.Wq) break;
-                    for (int g = 0; g < nseg; ++g) {
-                        const uint32_t src = stg0 + (uint32_t)(sI * nseg + g) * 16384u;
-                        if (P.o_mode == 0) {
-                            tma_store_5d(&P.mapO, src, 0, g, qx0, ty * 16, b);
-                        } else if (P.o_mode == 1) {
-                            for (int pl = 0; pl < 4; ++pl)
-                                tma_store_5d(&P.mapO, src + (uint32_t)pl * 4096u, 0, g, qx0 >> 1, ty * 8, b * 4 + pl);
-                        } else {
-                            tma_store_5d(&P.mapO, src, 0, g, qx0 * 2 + P.sub[sub].px, ty * 32 + P.sub[sub].py, b);
-                        }
-                    }
-                }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                mbar_arrive(bar_sempty);
-            }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp >= 1 && warp <= TC_ISSUERS && rank == 0) {
         // ================================ MMA issuers ============================================
@@ -912,15 +878,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const uint32_t aempty_l = PAIR ? mapa_u32(bar_aempty, 0) : bar_aempty;   // the leader's issuers wait on it
         uint32_t gg = 0;
         float run[NCH * 8];
-        const uint32_t stg = P.tmast ? stg0 : 0u;
-        uint32_t tile_k = 0;      // tiles finished by this warp (phase of the staging barriers)
-        if (stg) {
-            // channels of the output records beyond the computed ones are never written by the epilogue: they must
-            // reach memory as zeros (the consumers multiply them by zero weights; NaN bit patterns would poison that)
-            for (uint32_t o = ((uint32_t)threadIdx.x - TC_ACC_WARP0 * 32u) * 16u; o < P.stg_bytes; o += 512u * 16u)
-                st_shared_v4(stg + o, 0u, 0u, 0u, 0u);
-            asm volatile("bar.sync 1, 512;" ::: "memory");   // once per kernel, among the accumulator warps
-        }
+        // this warp's staging blocks (TMA-store epilogue: STG instantiations, CT = 128 only)
+        const uint32_t stg = (STG && P.tmast) ? stg0 + (uint32_t)(warp - TC_ACC_WARP0) * 4096u : 0u;
         const int tiles_xy = P.tiles_x * P.tiles_y;
 #ifdef FVC_TC_ACCDBG
         const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == TC_ACC_WARP0;
@@ -1005,11 +964,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const int ty = t % P.tiles_y; t /= P.tiles_y;
             const int sub = t % P.nsub;
             const int b = t / P.nsub;
-            if (stg) {
-                // the staging tile is free once the previous tile's bulk stores have read it (store manager, warp 0);
-                // no warp waits for another accumulator warp here: a barrier across the 16 warps at this point cost
-                // the tensor-bound 3x3 layers 10 % (every tile then runs at the pace of its slowest warp)
-                mbar_wait_sleep(bar_sempty, (tile_k & 1u) ^ 1u, 32);
+            if (STG && stg) {
+                // the warp's staging blocks are free once its previous bulk stores have READ them (a tile ago)
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
             }
             if constexpr (!PARK) {
                 if constexpr (NCH % 2 == 0) {
@@ -1021,7 +979,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                             for (int q = 0; q < 8; ++q) run[i * 8 + q] = run[2 * i * 8 + q] + run[(2 * i + 1) * 8 + q];
                         tile_epilogue<NCH / 2, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase >> 1, stg);
                     } else {
-                        tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
+                        tile_epilogue<NCH, RES, STG>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
                     }
                 } else {
                     tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
@@ -1051,18 +1009,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 }
                 tile_epilogue<NCH - NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase + NH * 8, stg);
             }
-            if (stg) {
-                // generic-proxy writes of the staging tile -> visible to the async proxy, then hand over to the manager
+            if (STG && stg) {
+                // generic-proxy writes of the staging blocks -> visible to the async proxy; then one lane issues the
+                // warp's stores: hi and lo piece of its 4 x 8 pixels (x 4 planes for parity-planar outputs)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_sfull);
-                ++tile_k;
+                if (lane == 0) {
+                    const int Nv = P.N;
+                    const int sI = (int)colbase / Nv, pc = ((int)colbase - sI * Nv) >> 5;    // sub-tile, 32-channel piece
+                    const int qx0 = (tx * P.SX + sI) * 8, qy0 = ty * 16 + quarter * 4;
+                    if (qx0 < P.Wq && qy0 < P.Hq) {
+                        const int nhalf = P.fast ? 1 : 2;
+                        for (int hl = 0; hl < nhalf; ++hl) {
+                            const uint32_t src = stg + (uint32_t)hl * 2048u;
+                            const int piece = pc + hl * P.o_nseg;
+                            if (P.o_mode == 0) {
+                                tma_store_5d(&P.mapO, src, 0, piece, qx0, qy0, b);
+                            } else if (P.o_mode == 1) {
+#pragma unroll
+                                for (int pl = 0; pl < 4; ++pl)
+                                    tma_store_5d(&P.mapO, src + (uint32_t)pl * 512u, 0, piece, qx0 >> 1, qy0 >> 1, b * 4 + pl);
+                            } else {
+                                tma_store_5d(&P.mapO, src, 0, piece, qx0 * 2 + P.sub[sub].px, qy0 * 2 + P.sub[sub].py, b);
+                            }
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
 #ifdef FVC_TC_ACCDBG
             if (adbg) a_epi += clock64() - e0;
 #endif
         }
 
+        if (STG && stg && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #ifdef FVC_TC_ACCDBG
         if (adbg && lane == 0) { P.dbg[4] = (unsigned long long)a_wait; P.dbg[5] = (unsigned long long)a_drain; P.dbg[6] = (unsigned long long)a_epi; }
 #endif
@@ -1288,22 +1268,21 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0;
     P.pair = pair ? 1 : 0;
     const int tile_bytes = N * pitch / (pair ? 2 : 1);   // per CTA
-    // TMA-store epilogue (FVC_TC_TMAST: 0 off, 1 auto [default], 2 every eligible layer): the out_act tile is staged in
-    // shared memory and written by bulk tensor stores.  Eligible: an ACT output with >= 32-channel records, outputs of
-    // stride-2 transposed convolutions only when not parity-planar.  Auto skips the 7x7 layers with wide inputs: their
-    // patches leave no room for the staging tile next to a deep weight ring, and they are tensor-bound anyway.
-    const int tmast_env = env_int("FVC_TC_TMAST", 1);
+    // TMA-store epilogue (FVC_TC_TMAST: 0 off [default], 1 on for every eligible layer): each accumulator warp stages
+    // its 32 pixels x 32 channels in shared memory and writes them with bulk tensor stores.  Eligible: an ACT output whose
+    // record width equals the MMA N (every channel computed), not merged, CT = 128 (each thread owns 32 channels of one
+    // sub-tile), outputs of stride-2 transposed convolutions only when not parity-planar.
+    const int tmast_env = env_int("FVC_TC_TMAST", 0);
     int o_mode = 0;
-    bool tmast = tmast_env != 0 && ep.out_act.p != nullptr && ep.out_act.Cp >= 32 && ep.out_act.Cp <= 128;
+    bool tmast = tmast_env != 0 && ep.out_act.p != nullptr && !merged && ep.out_act.Cp == N && N >= 32 && N <= 128;
     if (tmast) {
         if (L.os == 2) {
             o_mode = 2;
-            if (ep.out_act.parity || env_int("FVC_TC_TMAST_OS2", 1) == 0) tmast = false;
+            if (ep.out_act.parity) tmast = false;
         } else if (ep.out_act.parity) {
             o_mode = 1;
             if ((Hout & 1) || (Wout & 1)) tmast = false;
         }
-        if (tmast_env == 1 && L.k == 7 && Cp >= 32) tmast = false;
     }
     int o_nseg = tmast ? ep.out_act.Cp / 32 : 0;
     int SX = 0, nst = 0, PW = 0, PH = 16 + max_ext_y, npb = 2, T = 1;
@@ -1340,8 +1319,8 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         const int ct32 = sx * N / 32;
         if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
         if (merged && (ct32 & 1)) continue; // a thread must own both column blocks (hi, lo) of its channel chunks
-        if (tmast && (((merged ? ct32 / 2 : ct32) & 1) != 0)) continue;   // staged stores work on 16-channel pairs
-        const long stage_need = tmast ? (long)sx * o_nseg * 16384L : 0L;
+        if (tmast && ct32 != 4) continue;                 // per-warp staging: every thread owns 32 channels of one sub-tile
+        const long stage_need = tmast ? 16L * 4096L : 0L;   // 16 accumulator warps x (2 KB hi + 2 KB lo)
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * pitch;
@@ -1376,7 +1355,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     P.tmast = tmast ? 1 : 0;
     P.o_mode = o_mode;
     P.o_nseg = o_nseg;
-    P.stg_bytes = tmast ? (uint32_t)(SX * o_nseg * 16384) : 0u;
+    P.stg_bytes = tmast ? 16u * 4096u : 0u;
     P.CT = SX * N;
     P.patch_bytes = (uint32_t)((((size_t)PH * PW * pitch) + 1023) & ~(size_t)1023);
     P.patch_tx = (uint32_t)((size_t)PH * PW * pitch);
@@ -1579,14 +1558,15 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         const ActT& o = ep.out_act;
         const cuuint64_t rec = (cuuint64_t)o.Cp * 4;
         const int Wd = o.parity ? o.W / 2 : o.W, Hd = o.parity ? o.H / 2 : o.H;
-        cuuint64_t dims[5] = {64, (cuuint64_t)o_nseg, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)(o.B * (o.parity ? 4 : 1))};
-        cuuint64_t strides[4] = {128, rec, rec * Wd, rec * Wd * Hd};
-        cuuint32_t box[5] = {64, 1, 8, 16, 1};
+        // records as 64-byte pieces: [hi: Cp/32 pieces][lo: Cp/32 pieces]
+        cuuint64_t dims[5] = {32, (cuuint64_t)(2 * o_nseg), (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)(o.B * (o.parity ? 4 : 1))};
+        cuuint64_t strides[4] = {64, rec, rec * Wd, rec * Wd * Hd};
+        cuuint32_t box[5] = {32, 1, 8, 4, 1};                        // a warp's 4 x 8 pixels
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        if (o_mode == 1) { box[2] = 4; box[3] = 8; }
-        if (o_mode == 2) { box[2] = 16; box[3] = 32; estr[2] = 2; estr[3] = 2; }   // 8 x 16 pixels at stride 2
+        if (o_mode == 1) { box[2] = 4; box[3] = 2; }
+        if (o_mode == 2) { box[2] = 16; box[3] = 8; estr[2] = 2; estr[3] = 2; }   // 8 x 4 pixels at stride 2
         CUresult r = encode(&P.mapO, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 5,
-                            (void*)o.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            (void*)o.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled(O) failed: %d (Cp=%d W=%d H=%d mode=%d)", (int)r, o.Cp, Wd, Hd, o_mode);
@@ -1607,7 +1587,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     return 0;
 }
 
-template <int NCH, bool RES, bool PAIR>
+template <int NCH, bool RES, bool PAIR, bool STG = false>
 static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
     // the attribute is per device (and this function may run on several host threads): one bit per device ordinal
     static std::atomic<unsigned long long> attr_set{0};
@@ -1615,7 +1595,7 @@ static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
     FVC_CUDA(cudaGetDevice(&dev));
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_set.load(std::memory_order_acquire) & bit)) {
-        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES, PAIR, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set.fetch_or(bit, std::memory_order_release);
     }
     {
@@ -1638,7 +1618,7 @@ static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
         }
         cfg.attrs = at;
         cfg.numAttrs = na;
-        FVC_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<NCH, RES, PAIR>, plan->P));
+        FVC_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<NCH, RES, PAIR, STG>, plan->P));
     }
     g_launch_count++;
     FVC_CHECK_LAUNCH();
@@ -1656,6 +1636,10 @@ static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
 
 template <int NCH, bool RES>
 static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
+    if constexpr (NCH == 4) {
+        if (plan->P.tmast)
+            return plan->P.pair ? tc_launch_t3<NCH, RES, true, true>(plan, s) : tc_launch_t3<NCH, RES, false, true>(plan, s);
+    }
     return plan->P.pair ? tc_launch_t3<NCH, RES, true>(plan, s) : tc_launch_t3<NCH, RES, false>(plan, s);
 }
 
