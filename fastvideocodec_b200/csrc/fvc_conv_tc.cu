@@ -1300,7 +1300,10 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
                                                                                                         // one sub-tile per issuer
     const int sx_max = std::min(env_int("FVC_TC_SX", 4),
                                 std::max(1, std::min(merged ? 128 : ct_cap, ep.res_act.p ? env_int("FVC_TC_CTRES", 128) : 256) / N));
-    const int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), (pair ? env_int("FVC_TC_TPAIR", 512) : 256) / N));   // <= 32 KB per stage and CTA
+    int tmax = std::max(1, std::min(env_int("FVC_TC_T", 8), (pair ? env_int("FVC_TC_TPAIR", 512) : 256) / N));   // <= 32 KB per stage and CTA
+    // layers with a skip-connection / GDN operand: stages of 2 weight tiles (measured at 1080p, tools/layer_ab.py,
+    // profiles/r02_layer_times_T.txt: ResBlock conv2 0.508 -> 0.454 ms, 0.517 -> 0.471 ms; every other class prefers 8)
+    if (ep.res_act.p) tmax = std::min(tmax, std::max(1, env_int("FVC_TC_T_RES", 2)));
     // S trades weight re-reads / per-tile overhead (cost ~ one sub-tile's worth per tile, calibrated on
     // SpyNet level 0/1) against filling the 148 SMs: score = wave efficiency * S / (S + 1).
     int sms = 148;

@@ -3,8 +3,9 @@
 The reference builds these classes on CompressAI (``EntropyBottleneck``, ``GaussianConditional``,
 ``CompressionModel``), an un-vendored, un-pinned dependency (docker/Dockerfile:46).  This module keeps the
 reference's class names, constructor arguments, ``forward`` / ``get_estimate_bits`` signatures and the
-CompressAI parameter names (``_matrix{0-4}``, ``_bias{0-4}``, ``_factor{0-3}``, ``quantiles``) so that
-checkpoints load, and evaluates the likelihoods with the library's fused CUDA kernels
+CompressAI parameter and buffer names (``_matrix{0-4}``, ``_bias{0-4}``, ``_factor{0-3}``, ``quantiles``, ``target``
+[3], ``_offset`` / ``_quantized_cdf`` / ``_cdf_length``, ``likelihood_lower_bound.bound``, ``lower_bound_scale.bound``,
+``scale_table``, ``scale_bound``; as published for CompressAI 1.1-1.2, restated from memory) so that checkpoints load, and evaluates the likelihoods with the library's fused CUDA kernels
 (``fvc_eb_forward`` / ``fvc_gaussian_forward``) and the hyper-prior convolutions with the tcgen05 engine.
 
 In scope (eval forward only): ``RecProbModel.forward`` without the recurrent prior
@@ -37,7 +38,39 @@ def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
     return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
 
 
-class EntropyBottleneck(nn.Module):
+class _LowerBound(nn.Module):
+    """State-dict shape of CompressAI's ``LowerBound`` (one buffer ``bound``); the bound itself is applied inside the
+    CUDA kernels."""
+
+    def __init__(self, bound):
+        super().__init__()
+        self.register_buffer("bound", torch.Tensor([float(bound)]))
+
+
+class _EntropyModelBuffers(nn.Module):
+    """The buffers every CompressAI ``EntropyModel`` registers (``_offset``, ``_quantized_cdf``, ``_cdf_length``: the
+    range-coder tables written by ``update()``, empty until then) and ``likelihood_lower_bound.bound``, so that a
+    CompressAI-layout ``state_dict`` loads with ``strict=True``.  Table buffers take the checkpoint's shape on load,
+    as CompressAI's ``update_registered_buffers`` does."""
+
+    _RESIZABLE = ("_offset", "_quantized_cdf", "_cdf_length", "scale_table")
+
+    def _register_entropy_buffers(self, likelihood_bound):
+        self.likelihood_lower_bound = _LowerBound(likelihood_bound)
+        self.register_buffer("_offset", torch.IntTensor())
+        self.register_buffer("_quantized_cdf", torch.IntTensor())
+        self.register_buffer("_cdf_length", torch.IntTensor())
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for name in self._RESIZABLE:
+            key = prefix + name
+            if key in state_dict and hasattr(self, name) and getattr(self, name).shape != state_dict[key].shape:
+                buf = getattr(self, name)
+                setattr(self, name, torch.empty(state_dict[key].shape, dtype=state_dict[key].dtype, device=buf.device))
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class EntropyBottleneck(_EntropyModelBuffers):
     """CompressAI-compatible factorized prior (filters (3,3,3,3), init_scale 10, tail_mass 1e-9).
 
     Eval forward: ``x_hat = round(x - median) + median``; likelihood from the learned cumulative,
@@ -64,7 +97,9 @@ class EntropyBottleneck(nn.Module):
                 self.register_parameter("_factor%d" % i, nn.Parameter(torch.zeros(channels, f[i + 1], 1)))
         init_q = torch.tensor([-self.init_scale, 0.0, self.init_scale])
         self.quantiles = nn.Parameter(init_q.repeat(channels, 1, 1))
-        self.register_buffer("target", torch.tensor([math.log(2 / self.tail_mass - 1)] * 1))
+        target = math.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.Tensor([-target, 0, target]))      # CompressAI: shape [3]
+        self._register_entropy_buffers(likelihood_bound)
 
     def _medians(self):
         return self.quantiles[:, 0, 1].detach()
@@ -86,17 +121,19 @@ class EntropyBottleneck(nn.Module):
         return ops.eb_forward(x, self._packed().to(x.device), self._medians().to(x.device))
 
 
-class GaussianConditional(nn.Module):
+class GaussianConditional(_EntropyModelBuffers):
     """CompressAI-compatible conditional Gaussian: scale lower bound 0.11, likelihood bound 1e-9."""
 
     def __init__(self, scale_table=None, scale_bound=0.11, tail_mass=1e-9, likelihood_bound=1e-9):
         super().__init__()
         if scale_bound != 0.11 or likelihood_bound != 1e-9:
             raise ValueError("the CUDA kernel is specialised for scale_bound 0.11 and likelihood_bound 1e-9")
-        self.scale_bound = float(scale_bound)
         self.tail_mass = float(tail_mass)
+        self._register_entropy_buffers(likelihood_bound)
+        self.lower_bound_scale = _LowerBound(scale_bound)
         self.register_buffer("scale_table", torch.as_tensor(scale_table, dtype=torch.float32)
                              if scale_table is not None else torch.Tensor())
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
 
     def update_scale_table(self, scale_table, force=False):
         self.scale_table = torch.as_tensor(scale_table, dtype=torch.float32)

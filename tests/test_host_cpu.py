@@ -308,3 +308,28 @@ def test_video_compressor_extensions_and_validation():
         m.gop_forward_host(torch.zeros((2, 1, 3, 64, 64), dtype=torch.float64))
     with pytest.raises(ValueError):
         m.gop_forward_host(torch.zeros((1, 1, 3, 64, 64)))
+
+
+def test_entropy_models_load_compressai_layout_state_dict():
+    """a CompressAI-layout state_dict (``target`` of shape [3], the range-coder table buffers filled by
+    ``update()``, the LowerBound buffers) loads with strict=True."""
+    from fastvideocodec_b200.entropy_models import EntropyBottleneck, GaussianConditional
+    eb = EntropyBottleneck(8)
+    keys = set(eb.state_dict())
+    assert {"target", "_offset", "_quantized_cdf", "_cdf_length", "likelihood_lower_bound.bound", "quantiles",
+            "_matrix0", "_bias4", "_factor3"} <= keys
+    assert eb.state_dict()["target"].shape == (3,)
+    sd = {k: v.clone() for k, v in eb.state_dict().items()}
+    sd["_quantized_cdf"] = torch.zeros((8, 37), dtype=torch.int32)       # as written by CompressAI's update()
+    sd["_offset"] = torch.zeros(8, dtype=torch.int32)
+    sd["_cdf_length"] = torch.full((8,), 37, dtype=torch.int32)
+    EntropyBottleneck(8).load_state_dict(sd, strict=True)
+    gc = GaussianConditional(None)
+    assert {"_offset", "_quantized_cdf", "_cdf_length", "likelihood_lower_bound.bound", "lower_bound_scale.bound",
+            "scale_table", "scale_bound"} <= set(gc.state_dict())
+    sd = {k: v.clone() for k, v in gc.state_dict().items()}
+    sd["scale_table"] = torch.linspace(0.11, 256, 64)
+    sd["_quantized_cdf"] = torch.zeros((64, 100), dtype=torch.int32)
+    g2 = GaussianConditional(None)
+    g2.load_state_dict(sd, strict=True)
+    assert g2.scale_table.shape == (64,)
