@@ -198,9 +198,12 @@ struct Epilogue {
     ActT out_act;             // optional ACT output (p == nullptr: none)
     ActT out_act_relu;        // optional second ACT output holding relu(y)
     float* out_f32;           // optional fp32 NHWC output [B,Hout,Wout,Cout]
-    const float* gdn_beta;    // (unused placeholder kept for the SIMT engine's argument check)
-    const float* gdn_gamma;
+    // (I)GDN fused into the producing convolution's epilogue (tcgen05 engine; GDN.py:63-93): y = x / sqrt(norm) or
+    // x * sqrt(norm), norm_i = beta_i + sum_j gamma_ij x_j^2 as a second 128 x 64 x 64 MMA on the squared tile
+    const float* gdn_beta;    // [64] beta_eff; nullptr: no fused GDN
+    const e16* gdn_gamma;     // packed gamma_eff stream of the 1x1 "norm" convolution: tiles [hi][lo][hi], 64 rows x 128 B
     int gdn_inverse;
+    float gdn_scale;          // accumulator scale of the norm MMA: 1 / (sq_scale * weight scale of gamma)
     // tcgen05 engine only:
     ActT out_act_sq;          // optional ACT output holding sq_scale * y^2 (input of the GDN 1x1 convolution)
     float sq_scale;

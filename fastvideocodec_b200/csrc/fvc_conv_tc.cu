@@ -99,6 +99,8 @@ struct alignas(64) TcParams {
     // shared memory ([32 rows][64 B] hi block + lo block, SWIZZLE_64B) and writes them with two cp.async.bulk.tensor
     // stores; no synchronisation across warps
     CUtensorMap mapO;
+    CUtensorMap mapG;  // fused GDN: the packed gamma stream (three 64-row tiles)
+    int gdn;          // 1: fused (I)GDN epilogue (k_conv_tc<4, false, false, 2>)
     int tmast;        // 0: per-lane st.global epilogue; 1: per-warp staged TMA stores (out_act only)
     int o_mode;       // 0: plain NHWC output; 1: parity-planar output (4 plane boxes); 2: stride-2 transposed
                       //    conv (output pixel = 2q + phase: boxes with element stride 2)
@@ -561,15 +563,115 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
     if (ep.sat_count && ep_sat_hit(satm)) atomicAdd(ep.sat_count, 1u);
 }
 
+// Fused (I)GDN tile epilogue (GDN.py:63-93) of one accumulator thread: 32 output channels of one pixel (CT = 128).
+//   1. x = acc * scale + bias (kept in `run`); x^2 * 2^-6 as fp16 hi/lo into the shared-memory staging tile, laid out as
+//      the K-major SWIZZLE_128B A operand of an MMA: per sub-tile a hi and a lo block of [128 pixel rows][64 ch = 128 B];
+//   2. all 16 accumulator warps meet; one thread issues, per sub-tile, the 12 MMAs
+//      norm = sq_hi*g_hi + sq_hi*g_lo + sq_lo*g_hi (same tiles, same order, same single TMEM chain as the stand-alone
+//      1x1 "norm" convolution this replaces: bit-identical), D in TMEM columns behind the two partial buffers;
+//   3. every thread reads its 32 norm columns back, y = x / sqrt(beta + norm) (IGDN: x * sqrt(.)) with x rounded to
+//      the 22-bit hi/lo record precision exactly as the unfused path read it back from memory, and stores y.
+// Saves, per (I)GDN: the raw and the squared ACT tensors (written and read back) and one launch.
+__device__ __forceinline__ void gdn_tile_epilogue(const TcParams& P, const float* __restrict__ bias_s,
+                                                  const float* __restrict__ gbeta_s, float* run, int b, int sub, int ty,
+                                                  int tx, int th, int tw, uint32_t colbase, uint32_t stgA, uint32_t gdnB,
+                                                  uint32_t tmem_base, int quarter, uint32_t bar_gw, uint32_t bar_gdone,
+                                                  uint32_t& gphase) {
+    const Epilogue& ep = P.ep;
+    const int N = P.N;                                    // 64
+    const int s0 = (int)colbase / N, cA = (int)colbase - s0 * N;
+    const int qy = ty * 16 + th, qx = (tx * P.SX + s0) * 8 + tw;
+    const int oy = qy * P.os + P.sub[sub].py, ox = qx * P.os + P.sub[sub].px;
+    const bool ok = qy < P.Hq && qx < P.Wq;
+    const bool wlo = P.fast == 0;
+    uint32_t satm = 0;
+    // ---- 1. x in place, squares into the A-operand staging tile ------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 32; ++i) run[i] = fmaf(run[i], ep.acc_scale, bias_s[cA + i]);
+    {
+        const int row = th * 8 + tw;
+        const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t blk_hi = stgA + (uint32_t)(s0 * 2) * 16384u + ((uint32_t)row << 7), blk_lo = blk_hi + 16384u;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float sq[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sq[q] = run[16 * j + q] * run[16 * j + q] * ep.sq_scale;
+            uint32_t hi[8], lo[8];
+            ep_pack8(sq, false, hi, lo, satm);
+            ep_pack8(sq + 8, false, hi + 4, lo + 4, satm);
+            const uint32_t ch = (uint32_t)(cA + 16 * j) >> 3;   // 16-byte chunk of the 128-byte row (even)
+            st_shared_v4(blk_hi + ((ch ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(blk_hi + (((ch + 1u) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+            st_shared_v4(blk_lo + ((ch ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+            st_shared_v4(blk_lo + (((ch + 1u) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+        }
+    }
+    // ---- 2. second MMA: norm = gamma . x^2 ----------------------------------------------------------------------
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (threadIdx.x == TC_ACC_WARP0 * 32) {
+        tc_fence_after();
+        mbar_wait(bar_gw, 0);                             // gamma tiles resident (completes once per kernel)
+        const uint64_t d0 = make_desc(0, 1024u, 2u);      // K-major SWIZZLE_128B, 8-row groups 1024 B apart
+        for (int s = 0; s < P.S; ++s) {
+            const uint32_t a_hi = stgA + (uint32_t)(s * 2) * 16384u, a_lo = a_hi + 16384u;
+            const uint32_t dcol = tmem_base + 2u * (uint32_t)P.CT + (uint32_t)(s * N);
+            const uint32_t aa[3] = {a_hi, a_hi, a_lo};    // x tiles [g_hi][g_lo][g_hi] of the packed stream
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma(dcol, d0 | (uint64_t)(((aa[t] + 32u * k) & 0x3FFFFu) >> 4),
+                           d0 | (uint64_t)(((gdnB + 8192u * t + 32u * k) & 0x3FFFFu) >> 4), P.idesc, (t | k) ? 1u : 0u);
+        }
+        tc_commit(bar_gdone);
+    }
+    mbar_wait(bar_gdone, gphase);
+    gphase ^= 1u;
+    tc_fence_after();
+    // ---- 3. normalise and store ---------------------------------------------------------------------------------
+    e16* rec_out = ok ? ep.out_act.p + act_pixel_offset(ep.out_act, b, oy, ox) : nullptr;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2u * (uint32_t)P.CT + colbase;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        uint32_t d[16];
+        tc_ld16(taddr + 16 * j, d);
+        tc_wait_ld();
+        float y[16];
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) {
+            // x as the unfused path read it back from its hi/lo record
+            const float x0 = run[16 * j + q], x1 = run[16 * j + q + 1];
+            const uint32_t h = ep_pack2(x0, x1);
+            float h0, h1, l0, l1;
+            e2f2(h, h0, h1);
+            e2f2(ep_pack2(x0 - h0, x1 - h1), l0, l1);
+            const float r0 = h0 + l0, r1 = h1 + l1;
+            const float n0 = fmaf(__uint_as_float(d[q]), ep.gdn_scale, gbeta_s[cA + 16 * j + q]);
+            const float n1 = fmaf(__uint_as_float(d[q + 1]), ep.gdn_scale, gbeta_s[cA + 16 * j + q + 1]);
+            y[q] = ep.gdn_inverse ? r0 * sqrtf(n0) : r0 / sqrtf(n0);
+            y[q + 1] = ep.gdn_inverse ? r1 * sqrtf(n1) : r1 / sqrtf(n1);
+        }
+        if (ok) ep_store16_packed(rec_out, ep.out_act.Cp, cA + 16 * j, y, false, satm, wlo);
+    }
+    tc_fence_before();   // the norm columns are read: the next tile's MMAs may overwrite them after the next barrier
+    if (ep.sat_count && ep_sat_hit(satm)) atomicAdd(ep.sat_count, 1u);
+}
+
 // Warp roles: 0 = TMA producer (weight stream + patches), 1, 2 = MMA issuers (warp 1 owns the TMEM
 // allocation), 3..18 = accumulator / epilogue warps (any 16 consecutive warps cover every TMEM lane
 // quarter 4 times).
 // NCH: 8-column chunks of the running sum each accumulator thread owns (CT/4 = 8*NCH);
 // RES: the epilogue adds an ACT-format residual (ResBlock skip connection)
-// STG: TMA-store epilogue compiled in (CT = 128 kernels only; a separate instantiation so that the default kernels
-// carry none of its code: compiled into the same kernel it cost the skip-connection variant 64 bytes of spills)
-template <int NCH, bool RES, bool PAIR, bool STG = false>
+// MODE 1: TMA-store epilogue, MODE 2: fused (I)GDN epilogue (CT = 128 kernels only; separate instantiations so that the
+// default kernels carry none of their code: compiled into the same kernel the staged stores cost the skip-connection
+// variant 64 bytes of spills)
+template <int NCH, bool RES, bool PAIR, int MODE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcParams P) {
+    constexpr bool STG = MODE == 1;    // TMA-store epilogue
+    constexpr bool GDN = MODE == 2;    // fused (I)GDN epilogue
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: SWIZZLE_128B atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -581,6 +683,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const uint32_t bar_bfull = bars + 32, bar_bempty = bars + 32 + 8 * 8;   // [nst <= 8] each
     const uint32_t bar_afull = bars + 32 + 16 * 8, bar_aempty = bar_afull + 32;  // partial buffers [<= 4] each
     const uint32_t tmem_slot = bar_aempty + 32;
+    const uint32_t bar_gw = tmem_slot + 8, bar_gdone = tmem_slot + 16;   // fused GDN: gamma tiles loaded / norm MMAs done
+    const uint32_t gdnB = stg0 + (uint32_t)P.S * 32768u;                 // fused GDN: three 8 KB gamma tiles after the
+                                                                         // A-operand staging tile (hi + lo block per sub-tile)
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 256);   // [N <= 128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -604,6 +709,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, TC_ISSUERS);
         }
+        if (GDN) {
+            mbar_init(bar_gw, 1);
+            mbar_init(bar_gdone, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -622,6 +731,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     if (threadIdx.x >= 128 && (int)threadIdx.x - 128 < P.N) {
         const int c = (int)threadIdx.x - 128;
         bias_s[c] = c < P.Cout ? P.ep.bias[c] : 0.f;
+        if (GDN && c < 64) bias_s[128 + c] = P.ep.gdn_beta[c];   // beta_eff behind the (<= 128) bias values
     }
     tc_fence_before();
     __syncthreads();
@@ -643,6 +753,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         // Two independent iterators; whichever ring has a free slot is served (a blocking wait on one
         // ring would starve the other: the patch of the next pass frees only when the current pass ends).
         if (elect_one()) {
+            if (GDN) {   // the (I)GDN's gamma tiles stay resident for the whole kernel
+                mbar_expect_tx(bar_gw, 3u * 8192u);
+                for (int t = 0; t < 3; ++t) tma_load_2d(gdnB + 8192u * (uint32_t)t, &P.mapG, bar_gw, 0, t * 64);
+            }
             PassIter wc, pc;
             wc.xmul = xmul; wc.xadd = xadd;
             wc.tile = tile0; wc.pass = 0; wc.decode(P);
@@ -880,6 +994,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         float run[NCH * 8];
         // this warp's staging blocks (TMA-store epilogue: STG instantiations, CT = 128 only)
         const uint32_t stg = (STG && P.tmast) ? stg0 + (uint32_t)(warp - TC_ACC_WARP0) * 4096u : 0u;
+        uint32_t gphase = 0;      // phase of the fused GDN's "norm MMAs done" barrier
         const int tiles_xy = P.tiles_x * P.tiles_y;
 #ifdef FVC_TC_ACCDBG
         const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == TC_ACC_WARP0;
@@ -969,7 +1084,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
             }
-            if constexpr (!PARK) {
+            if constexpr (GDN) {
+                gdn_tile_epilogue(P, bias_s, bias_s + 128, run, b, sub, ty, tx, th, tw, colbase, stg0, gdnB, tmem_base,
+                                  quarter, bar_gw, bar_gdone, gphase);
+            } else if constexpr (!PARK) {
                 if constexpr (NCH % 2 == 0) {
                     if (P.merged) {
                         // columns come in 8-wide blocks [w_hi products | w_lo products]: fold them
@@ -1186,7 +1304,11 @@ static int env_int(const char* name, int dflt) {
 int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, int Wout, const Epilogue& ep,
                    TcPlan** out, cudaStream_t s, bool fast) {
     FVC_ARG(tc_supported(L, in.Cp));
-    FVC_ARG(ep.gdn_beta == nullptr);
+    const bool gdn = ep.gdn_beta != nullptr;   // (I)GDN fused into this convolution's epilogue
+    if (gdn) {
+        FVC_ARG(ep.gdn_gamma && L.Cout == 64 && ep.out_act.p && ep.out_act.Cp == 64 && !ep.res_act.p && !ep.res_f32 &&
+                !ep.out_f32 && !ep.out_act_relu.p && !ep.out_act_sq.p && ep.act == FVC_ACT_NONE);
+    }
     FVC_ARG((L.st == 2) == (in.parity != 0));
     PFN_encodeTiled encode = get_encode();
     if (!encode) {
@@ -1205,7 +1327,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // Cout <= 16 ("merged"): padded channels of the output records are never written (the buffers are
     // zero-initialised) and the MMA N = 32 carries w_hi and w_lo row blocks side by side.
     const int merge_max = env_int("FVC_TC_MERGED", 32);
-    const bool merged = !fast && ((Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 0)));
+    const bool merged = !fast && !gdn && ((Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 0)));
     if (merged) chans = cdiv(L.Cout, 16) * 16;
     const int N = merged ? 2 * chans : std::max(16, cdiv(chans, 16) * 16);   // MMA N
     P.N = N;
@@ -1265,7 +1387,8 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // CTA pairs (cta_group::2): two x-neighbouring tiles are one M = 256 MMA; each CTA stages half of every weight
     // tile, which halves the weight bytes staged through shared memory and the B-operand reads per SM.
     // Measured at 1080p (tools/layer_ab.py): pairs win or tie on every layer.
-    const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0;
+    // (the fused GDN epilogue issues cta_group::1 MMAs of its own: such a kernel cannot mix in cta_group::2)
+    const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0 && !gdn;
     P.pair = pair ? 1 : 0;
     const int tile_bytes = N * pitch / (pair ? 2 : 1);   // per CTA
     // TMA-store epilogue (FVC_TC_TMAST: 0 off [default], 1 on for every eligible layer): each accumulator warp stages
@@ -1322,8 +1445,10 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         const int ct32 = sx * N / 32;
         if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
         if (merged && (ct32 & 1)) continue; // a thread must own both column blocks (hi, lo) of its channel chunks
-        if (tmast && ct32 != 4) continue;                 // per-warp staging: every thread owns 32 channels of one sub-tile
-        const long stage_need = tmast ? 16L * 4096L : 0L;   // 16 accumulator warps x (2 KB hi + 2 KB lo)
+        if ((tmast || gdn) && ct32 != 4) continue;        // staging: every thread owns 32 channels of one sub-tile
+        // TMA stores: 16 accumulator warps x (2 KB hi + 2 KB lo); fused GDN: A-operand tile (hi + lo block per sub-tile)
+        // + three 8 KB gamma tiles
+        const long stage_need = tmast ? 16L * 4096L : (gdn ? (long)sx * 32768L + 24576L : 0L);
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * pitch;
@@ -1358,7 +1483,8 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     P.tmast = tmast ? 1 : 0;
     P.o_mode = o_mode;
     P.o_nseg = o_nseg;
-    P.stg_bytes = tmast ? 16u * 4096u : 0u;
+    P.stg_bytes = tmast ? 16u * 4096u : (gdn ? (uint32_t)SX * 32768u + 24576u : 0u);
+    P.gdn = gdn ? 1 : 0;
     P.CT = SX * N;
     P.patch_bytes = (uint32_t)((((size_t)PH * PW * pitch) + 1023) & ~(size_t)1023);
     P.patch_tx = (uint32_t)((size_t)PH * PW * pitch);
@@ -1366,9 +1492,10 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     P.stage_bytes = (uint32_t)T * P.btile_bytes;
     // partial-accumulator buffers: 4 when they fit the 512 TMEM columns (the MMA issuers then run up to a whole
     // tile ahead of an epilogue), else 2
-    P.nab_log2 = (4 * P.CT <= 512 && env_int("FVC_TC_NAB", 4) >= 4) ? 2 : 1;
+    P.nab_log2 = (4 * P.CT <= 512 && env_int("FVC_TC_NAB", 4) >= 4 && !gdn) ? 2 : 1;
     uint32_t cols = 32;
-    while (cols < (uint32_t)((1 << P.nab_log2) * P.CT)) cols <<= 1;
+    // fused GDN: the norm accumulators (S x 64 columns) live behind the two partial buffers
+    while (cols < (uint32_t)((1 << P.nab_log2) * P.CT + (gdn ? SX * 64 : 0))) cols <<= 1;
     P.tmem_cols = cols;
     P.tiles_x = pair ? cdiv(cdiv(P.Wq, 8 * SX), 2) : cdiv(P.Wq, 8 * SX);
     P.tiles_y = cdiv(P.Hq, 16);
@@ -1557,6 +1684,21 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             return FVC_ERR_CUDA;
         }
     }
+    if (gdn) {
+        cuuint64_t gd[2] = {64, 3 * 64};
+        cuuint64_t gs[1] = {128};
+        cuuint32_t gb[2] = {64, 64};
+        cuuint32_t ge[2] = {1, 1};
+        CUresult r = encode(&P.mapG, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2,
+                            (void*)ep.gdn_gamma, gd, gs, gb, ge, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(gamma) failed: %d", (int)r);
+            cudaFree(plan->wstream);
+            delete plan;
+            return FVC_ERR_CUDA;
+        }
+    }
     if (tmast) {
         const ActT& o = ep.out_act;
         const cuuint64_t rec = (cuuint64_t)o.Cp * 4;
@@ -1590,7 +1732,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     return 0;
 }
 
-template <int NCH, bool RES, bool PAIR, bool STG = false>
+template <int NCH, bool RES, bool PAIR, int MODE = 0>
 static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
     // the attribute is per device (and this function may run on several host threads): one bit per device ordinal
     static std::atomic<unsigned long long> attr_set{0};
@@ -1598,7 +1740,7 @@ static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
     FVC_CUDA(cudaGetDevice(&dev));
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_set.load(std::memory_order_acquire) & bit)) {
-        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES, PAIR, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        FVC_CUDA(cudaFuncSetAttribute(k_conv_tc<NCH, RES, PAIR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set.fetch_or(bit, std::memory_order_release);
     }
     {
@@ -1621,7 +1763,7 @@ static int tc_launch_t3(TcPlan* plan, cudaStream_t s) {
         }
         cfg.attrs = at;
         cfg.numAttrs = na;
-        FVC_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<NCH, RES, PAIR, STG>, plan->P));
+        FVC_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<NCH, RES, PAIR, MODE>, plan->P));
     }
     g_launch_count++;
     FVC_CHECK_LAUNCH();
@@ -1641,7 +1783,10 @@ template <int NCH, bool RES>
 static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
     if constexpr (NCH == 4) {
         if (plan->P.tmast)
-            return plan->P.pair ? tc_launch_t3<NCH, RES, true, true>(plan, s) : tc_launch_t3<NCH, RES, false, true>(plan, s);
+            return plan->P.pair ? tc_launch_t3<NCH, RES, true, 1>(plan, s) : tc_launch_t3<NCH, RES, false, 1>(plan, s);
+        if constexpr (!RES) {
+            if (plan->P.gdn) return tc_launch_t3<NCH, false, false, 2>(plan, s);
+        }
     }
     return plan->P.pair ? tc_launch_t3<NCH, RES, true>(plan, s) : tc_launch_t3<NCH, RES, false>(plan, s);
 }
@@ -1663,6 +1808,14 @@ int tc_plan_launch(TcPlan* plan, cudaStream_t s) {
     }
     set_error("tc_plan_launch: unsupported accumulator width %d", plan->P.CT);
     return FVC_ERR_STATE;
+}
+
+// packed weight stream and accumulator scale of a plan (the fused GDN epilogue of the producing convolution uses the
+// stand-alone norm convolution's gamma stream: tiles [hi][lo][hi] of 64 rows x 128 B)
+const e16* tc_plan_wstream(const TcPlan* plan) { return plan ? plan->wstream : nullptr; }
+float tc_plan_acc_scale(const TcPlan* plan) { return plan ? plan->P.ep.acc_scale : 0.f; }
+bool tc_plan_is_gdn_norm_layout(const TcPlan* plan) {
+    return plan && !plan->P.merged && plan->P.N == 64 && plan->P.pitch == 128 && plan->P.fast == 0;
 }
 
 void tc_plan_destroy(TcPlan* plan) {

@@ -98,6 +98,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
                    TcPlan** plan, cudaStream_t s, bool fast = false);
 int tc_plan_launch(TcPlan* plan, cudaStream_t s);
 void tc_plan_destroy(TcPlan* plan);
+const e16* tc_plan_wstream(const TcPlan* plan);
+float tc_plan_acc_scale(const TcPlan* plan);
+bool tc_plan_is_gdn_norm_layout(const TcPlan* plan);
 bool tc_supported(const ConvLayer& L, int CinP);
 
 }  // namespace fvc

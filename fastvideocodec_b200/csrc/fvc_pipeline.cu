@@ -78,6 +78,7 @@ struct fvc_ctx {
     int64_t launches = 0;
     bool profile = false;
     bool use_few = true;     // FVC_FEW=0 routes the 2-3 output-channel layers through the tensor-core engine
+    bool gdn_fused = true;   // FVC_GDN_FUSED=0: (I)GDN as a separate 1x1 "norm" convolution launch (round-1 form)
     double last_conv_seconds = -1.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
     std::vector<std::string> conv_event_names;
@@ -440,6 +441,35 @@ static int run_conv_gdn(fvc_ctx* c, const std::string& conv, const std::string& 
     const bool tc = c->impl != FVC_IMPL_SIMT;
     // squares are stored scaled by 2^-6 so that |x| up to ~2000 stays inside the fp16 range of the hi half
     const float sq_scale = 1.f / 64.f;
+    if (tc && c->gdn_fused) {
+        // (I)GDN inside the producing convolution's epilogue (north_star; GDN.py:63-93): the squared tile goes to shared
+        // memory as the A operand of a second MMA against gamma_eff, the stand-alone "#norm" convolution's packed
+        // weight stream (always the 3-product hi/lo form, also in precision 'fast').  The plan of that convolution
+        // is created (never launched) to own the stream and its scale.
+        const std::string nname = gdn + "#norm";
+        ConvRt& n = c->conv[nname];
+        if (!n.tc) {
+            Epilogue en = make_ep(n);
+            en.bias = n.bias;
+            en.act = FVC_ACT_NONE;
+            en.acc_scale = 1.f / sq_scale;
+            en.res_act = raw;
+            en.res_mode = g.inverse ? 2 : 1;
+            en.out_act = out;
+            int rc = tc_plan_create(n.L, n.w_raw, sq, out.H, out.W, en, &n.tc, s, false);
+            if (rc) return rc;
+        }
+        if (tc_plan_is_gdn_norm_layout(n.tc)) {
+            Epilogue ef = make_ep(r);
+            ef.out_act = out;
+            ef.sq_scale = sq_scale;
+            ef.gdn_beta = n.bias;
+            ef.gdn_gamma = tc_plan_wstream(n.tc);
+            ef.gdn_scale = tc_plan_acc_scale(n.tc);
+            ef.gdn_inverse = g.inverse;
+            return run_conv(c, conv, in, out.H, out.W, ef, s);
+        }
+    }
     if (tc) {
         ep.out_act_sq = sq;
         ep.sq_scale = sq_scale;
@@ -777,6 +807,8 @@ fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl) {
     c->profile = prof && prof[0] == '1';
     const char* few = getenv("FVC_FEW");
     c->use_few = !(few && few[0] == '0');
+    const char* gf = getenv("FVC_GDN_FUSED");
+    c->gdn_fused = !(gf && gf[0] == '0');
     if (build_layers(c) || build_buffers(c)) {
         fvc_ctx_destroy(c);
         return nullptr;
@@ -862,6 +894,13 @@ int fvc_ctx_set_param(fvc_ctx* c, const char* key_c, const float* data, int64_t 
             if (rc) return rc;
             if (n.tc) { tc_plan_destroy(n.tc); n.tc = nullptr; }
             n.have_w = n.have_b = true;
+            // the producing convolution's plan refers to the norm plan's gamma stream (fused epilogue): rebuild it
+            std::string prod = mod;   // resEncoder.gdnK -> resEncoder.convK, resDecoder.igdnK -> resDecoder.deconvK
+            size_t pg = prod.find("igdn");
+            if (pg != std::string::npos) prod.replace(pg, 4, "deconv");
+            else if ((pg = prod.find("gdn")) != std::string::npos) prod.replace(pg, 3, "conv");
+            auto pi = c->conv.find(prod);
+            if (pi != c->conv.end() && pi->second.tc) { tc_plan_destroy(pi->second.tc); pi->second.tc = nullptr; }
         }
         return 0;
     }

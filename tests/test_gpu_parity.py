@@ -1157,3 +1157,27 @@ def test_tma_store_epilogue_bit_identical_to_lane_stores(dev, case, layout, monk
     y_f32 = f(x.to(dev), w.to(dev), b.to(dev), stride, act).cpu()
     assert torch.equal(y_tma, y_lane), (y_tma - y_lane).abs().max().item()
     assert (y_lane - y_f32).abs().max().item() <= 2e-6 * max(1.0, y_f32.abs().max().item())
+
+
+def test_fused_gdn_bit_identical_to_separate_norm_convolution(dev, state_dict, monkeypatch):
+    """(I)GDN fused into the producing convolution's epilogue (second MMA on the squared tile) against the round-1
+    form (raw + squared ACT tensors, separate 1x1 "norm" convolution launch): same tiles, same MMA order, same
+    rounding of x -> bit-identical frames, latents and scalars; six launches fewer per frame."""
+    from fastvideocodec_b200 import VideoCompressor
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    fr = synthetic_gop(192, 320, gop=2, gop_id=8).to(dev)       # partial tiles at every resolution of the residual codec
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("FVC_GDN_FUSED", fused)
+        m = VideoCompressor()
+        m.load_state_dict(state_dict)
+        m = m.to(dev).eval()
+        m.impl = _impls()[-1][1]
+        with torch.no_grad():
+            out = m(fr[1], fr[0])
+        res[fused] = (out, m.get_intermediate("feature"), m.get_intermediate("recon_res"), m.launch_count())
+        m.release()
+    a, b = res["1"], res["0"]
+    assert torch.equal(a[0][0], b[0][0]) and all(float(x) == float(y) for x, y in zip(a[0][1:], b[0][1:]))
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    print("launches fused %d vs separate %d" % (a[3], b[3]))
