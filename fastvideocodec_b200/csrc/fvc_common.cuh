@@ -204,6 +204,15 @@ struct Epilogue {
     const e16* gdn_gamma;     // packed gamma_eff stream of the 1x1 "norm" convolution: tiles [hi][lo][hi], 64 rows x 128 B
     int gdn_inverse;
     float gdn_scale;          // accumulator scale of the norm MMA: 1 / (sq_scale * weight scale of gamma)
+    // Fused 3x3 "tail" convolution with 2-3 output channels (mvDecoder.deconv8 after deconv7, Warp_net conv6 after
+    // conv5.conv2; tcgen05 engine): this layer's output y never reaches memory; a second MMA multiplies the staged y
+    // tile by the tail's weights regrouped as a 1x1 convolution with 9 * Cout_tail (padded to 32) outputs, one per
+    // (tap, channel); the per-pixel partial products P go out as fp32 [B,H,W,tap_cq] and k_tapsum adds the 9 shifted
+    // taps.  nullptr: not fused.
+    const e16* tap_w;         // packed stream of the regrouped weights: 32-row tiles, per 64-channel segment [hi][lo], then [hi]
+    float* tap_out;           // P
+    float tap_scale;          // 1 / weight scale of tap_w
+    int tap_cq;               // floats per pixel of P (multiple of 4, <= 32)
     // tcgen05 engine only:
     ActT out_act_sq;          // optional ACT output holding sq_scale * y^2 (input of the GDN 1x1 convolution)
     float sq_scale;

@@ -101,6 +101,8 @@ struct alignas(64) TcParams {
     CUtensorMap mapO;
     CUtensorMap mapG;  // fused GDN: the packed gamma stream (three 64-row tiles)
     int gdn;          // 1: fused (I)GDN epilogue (k_conv_tc<4, false, false, 2>)
+    int tap;          // 1: fused tail convolution (k_conv_tc<4, RES, false, 3>); mapG then maps the regrouped weights
+    uint32_t tap_idesc;   // instruction descriptor of the second MMA (M = 128, N = 32)
     int tmast;        // 0: per-lane st.global epilogue; 1: per-warp staged TMA stores (out_act only)
     int o_mode;       // 0: plain NHWC output; 1: parity-planar output (4 plane boxes); 2: stride-2 transposed
                       //    conv (output pixel = 2q + phase: boxes with element stride 2)
@@ -660,6 +662,127 @@ __device__ __forceinline__ void gdn_tile_epilogue(const TcParams& P, const float
     if (ep.sat_count && ep_sat_hit(satm)) atomicAdd(ep.sat_count, 1u);
 }
 
+// Fused tail convolution, tile epilogue of one accumulator thread (32 output channels of one pixel, CT = 128):
+//   1. y = act(acc * scale + bias) (+ skip), rounded to the hi/lo record exactly as the tail convolution would have read
+//      it from memory, written as fp16 hi/lo into the A-operand staging tile: per sub-tile and 64-channel segment a hi
+//      and a lo block of [128 pixel rows][128 B] (K-major SWIZZLE_128B);
+//   2. all 16 accumulator warps meet; one thread issues per sub-tile y_hi*w_hi + y_hi*w_lo (per segment) + y_lo*w_hi
+//      against the 32-row weight tiles (rows = (tap, channel) of the tail's 3x3 kernel), D in TMEM behind the partials;
+//   3. every thread reads its share of the 32 columns and stores P (fp32) for its pixel.
+template <bool RES>
+__device__ __forceinline__ void tap_tile_epilogue(const TcParams& P, const float* __restrict__ bias_s, float* run, int b,
+                                                  int sub, int ty, int tx, int th, int tw, uint32_t colbase,
+                                                  uint32_t stgA, uint32_t tapB, uint32_t tmem_base, int quarter,
+                                                  uint32_t bar_gw, uint32_t bar_gdone, uint32_t& gphase) {
+    const Epilogue& ep = P.ep;
+    const int N = P.N;                                    // 64 or 128 = channels of y per pixel
+    const int nseg = N >> 6;                              // 64-channel segments
+    const int s0 = (int)colbase / N, cA = (int)colbase - s0 * N;
+    const int qy = ty * 16 + th, qx = (tx * P.SX + s0) * 8 + tw;
+    const int oy = qy * P.os + P.sub[sub].py, ox = qx * P.os + P.sub[sub].px;
+    const bool ok = qy < P.Hq && qx < P.Wq;
+    uint32_t satm = 0;
+    // ---- 1. y -> staging ------------------------------------------------------------------------------------------
+    {
+        const int row = th * 8 + tw;
+        const uint32_t sw = (uint32_t)(row & 7);
+        // blocks of sub-tile s0: [seg][hi, lo]; this thread's 32 channels lie in segment cA / 64
+        const uint32_t blk_hi = stgA + (uint32_t)((s0 * nseg + (cA >> 6)) * 2) * 16384u + ((uint32_t)row << 7);
+        const uint32_t blk_lo = blk_hi + 16384u;
+        const e16* rec_res = nullptr;
+        if (RES && ok) rec_res = ep.res_act.p + act_pixel_offset(ep.res_act, b, oy, ox);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float v[16];
+            uint32_t rh[8], rl[8];
+            if (RES) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) rh[q] = rl[q] = 0u;
+                if (ok) {
+                    ld_global_nc_v8(rec_res + cA + 16 * j, rh);
+                    ld_global_nc_v8(rec_res + ep.res_act.Cp + cA + 16 * j, rl);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                float w = fmaf(run[16 * j + q], ep.acc_scale, bias_s[cA + 16 * j + q]);
+                if (ep.act == FVC_ACT_RELU) w = fmaxf(w, 0.f);
+                else if (ep.act == FVC_ACT_LRELU01) w = w > 0.f ? w : w * 0.1f;
+                v[q] = w;
+            }
+            if (RES) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float a0, a1, b0, b1;
+                    e2f2(rh[q], a0, a1);
+                    e2f2(rl[q], b0, b1);
+                    v[2 * q] += a0 + b0;
+                    v[2 * q + 1] += a1 + b1;
+                }
+            }
+            uint32_t hi[8], lo[8];
+            ep_pack8(v, false, hi, lo, satm);
+            ep_pack8(v + 8, false, hi + 4, lo + 4, satm);
+            const uint32_t ch = (uint32_t)((cA & 63) + 16 * j) >> 3;
+            st_shared_v4(blk_hi + ((ch ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(blk_hi + (((ch + 1u) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+            st_shared_v4(blk_lo + ((ch ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+            st_shared_v4(blk_lo + (((ch + 1u) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+        }
+    }
+    // ---- 2. second MMA: P = y . W' ----------------------------------------------------------------------------------
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (threadIdx.x == TC_ACC_WARP0 * 32) {
+        tc_fence_after();
+        mbar_wait(bar_gw, 0);                             // weight tiles resident (completes once per kernel)
+        const uint64_t d0 = make_desc(0, 1024u, 2u);
+        for (int s = 0; s < P.S; ++s) {
+            const uint32_t dcol = tmem_base + 2u * (uint32_t)P.CT + (uint32_t)(s * 32);
+            uint32_t first = 0u;
+            // stream order: per segment [w_hi][w_lo] (against y_hi), then per segment [w_hi] (against y_lo)
+            for (int t = 0; t < 3 * nseg; ++t) {
+                const int g = t < 2 * nseg ? (t >> 1) : (t - 2 * nseg);
+                const uint32_t a = stgA + (uint32_t)((s * nseg + g) * 2 + (t < 2 * nseg ? 0 : 1)) * 16384u;
+                const uint32_t w = tapB + 4096u * (uint32_t)t;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tc_mma(dcol, d0 | (uint64_t)(((a + 32u * k) & 0x3FFFFu) >> 4),
+                           d0 | (uint64_t)(((w + 32u * k) & 0x3FFFFu) >> 4), P.tap_idesc, first);
+                    first = 1u;
+                }
+            }
+        }
+        tc_commit(bar_gdone);
+    }
+    mbar_wait(bar_gdone, gphase);
+    gphase ^= 1u;
+    tc_fence_after();
+    // ---- 3. P out: the sub-tile's 32 columns are shared by its N / 32 threads per pixel ------------------------------
+    {
+        const int share = 1024 / N;                        // 16 (N = 64) or 8 (N = 128) columns per thread
+        const int c0 = (cA >> 5) * share;                  // first column of this thread
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2u * (uint32_t)P.CT + (uint32_t)(s0 * 32 + c0);
+        float* dst = ok ? ep.tap_out + (((size_t)b * P.Hout + oy) * P.Wout + ox) * (size_t)ep.tap_cq : nullptr;
+        for (int q0 = 0; q0 < share; q0 += 8) {
+            uint32_t d[8];
+            tc_ld8(taddr + q0, d);
+            tc_wait_ld();
+            if (ok) {
+#pragma unroll
+                for (int q = 0; q < 8; q += 4)
+                    if (c0 + q0 + q < ep.tap_cq)
+                        *reinterpret_cast<float4*>(dst + c0 + q0 + q) =
+                            make_float4(__uint_as_float(d[q]) * ep.tap_scale, __uint_as_float(d[q + 1]) * ep.tap_scale,
+                                        __uint_as_float(d[q + 2]) * ep.tap_scale, __uint_as_float(d[q + 3]) * ep.tap_scale);
+            }
+        }
+    }
+    tc_fence_before();
+    if (ep.sat_count && ep_sat_hit(satm)) atomicAdd(ep.sat_count, 1u);
+}
+
 // Warp roles: 0 = TMA producer (weight stream + patches), 1, 2 = MMA issuers (warp 1 owns the TMEM
 // allocation), 3..18 = accumulator / epilogue warps (any 16 consecutive warps cover every TMEM lane
 // quarter 4 times).
@@ -672,6 +795,7 @@ template <int NCH, bool RES, bool PAIR, int MODE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ TcParams P) {
     constexpr bool STG = MODE == 1;    // TMA-store epilogue
     constexpr bool GDN = MODE == 2;    // fused (I)GDN epilogue
+    constexpr bool TAP = MODE == 3;    // fused 3x3 tail convolution (tap-split second MMA)
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: SWIZZLE_128B atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -684,8 +808,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     const uint32_t bar_afull = bars + 32 + 16 * 8, bar_aempty = bar_afull + 32;  // partial buffers [<= 4] each
     const uint32_t tmem_slot = bar_aempty + 32;
     const uint32_t bar_gw = tmem_slot + 8, bar_gdone = tmem_slot + 16;   // fused GDN: gamma tiles loaded / norm MMAs done
-    const uint32_t gdnB = stg0 + (uint32_t)P.S * 32768u;                 // fused GDN: three 8 KB gamma tiles after the
-                                                                         // A-operand staging tile (hi + lo block per sub-tile)
+    // fused GDN: three 8 KB gamma tiles after the A-operand staging tile (hi + lo block per sub-tile); fused tail
+    // convolution: 3 * N/64 weight tiles of 4 KB after the staging tile (hi + lo block per sub-tile and segment)
+    const uint32_t gdnB = stg0 + (TAP ? (uint32_t)P.S * (uint32_t)(P.N >> 6) * 32768u : (uint32_t)P.S * 32768u);
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 256);   // [N <= 128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -709,7 +834,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, TC_ISSUERS);
         }
-        if (GDN) {
+        if (GDN || TAP) {
             mbar_init(bar_gw, 1);
             mbar_init(bar_gdone, 1);
         }
@@ -756,6 +881,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             if (GDN) {   // the (I)GDN's gamma tiles stay resident for the whole kernel
                 mbar_expect_tx(bar_gw, 3u * 8192u);
                 for (int t = 0; t < 3; ++t) tma_load_2d(gdnB + 8192u * (uint32_t)t, &P.mapG, bar_gw, 0, t * 64);
+            }
+            if (TAP) {   // regrouped weights of the fused tail convolution
+                const int nt = 3 * (P.N >> 6);
+                mbar_expect_tx(bar_gw, (uint32_t)nt * 4096u);
+                for (int t = 0; t < nt; ++t) tma_load_2d(gdnB + 4096u * (uint32_t)t, &P.mapG, bar_gw, 0, t * 32);
             }
             PassIter wc, pc;
             wc.xmul = xmul; wc.xadd = xadd;
@@ -1087,6 +1217,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             if constexpr (GDN) {
                 gdn_tile_epilogue(P, bias_s, bias_s + 128, run, b, sub, ty, tx, th, tw, colbase, stg0, gdnB, tmem_base,
                                   quarter, bar_gw, bar_gdone, gphase);
+            } else if constexpr (TAP) {
+                tap_tile_epilogue<RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg0, gdnB, tmem_base, quarter,
+                                       bar_gw, bar_gdone, gphase);
             } else if constexpr (!PARK) {
                 if constexpr (NCH % 2 == 0) {
                     if (P.merged) {
@@ -1302,7 +1435,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, int Wout, const Epilogue& ep,
-                   TcPlan** out, cudaStream_t s, bool fast) {
+                   TcPlan** out, cudaStream_t s, bool fast, bool no_merge) {
     FVC_ARG(tc_supported(L, in.Cp));
     const bool gdn = ep.gdn_beta != nullptr;   // (I)GDN fused into this convolution's epilogue
     if (gdn) {
@@ -1327,7 +1460,13 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // Cout <= 16 ("merged"): padded channels of the output records are never written (the buffers are
     // zero-initialised) and the MMA N = 32 carries w_hi and w_lo row blocks side by side.
     const int merge_max = env_int("FVC_TC_MERGED", 32);
-    const bool merged = !fast && !gdn && ((Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 0)));
+    const bool tap = ep.tap_w != nullptr;      // fused tail convolution (second MMA against regrouped weights)
+    if (tap) {
+        FVC_ARG(!gdn && ep.tap_out && (L.Cout == 64 || L.Cout == 128) && ep.tap_cq >= 4 && ep.tap_cq <= 32 &&
+                (ep.tap_cq & 3) == 0 && !ep.out_act.p && !ep.out_f32 && !ep.res_f32 && !ep.out_act_relu.p &&
+                !ep.out_act_sq.p && (!ep.res_act.p || ep.res_mode == 0));
+    }
+    const bool merged = !fast && !gdn && !no_merge && ((Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 0)));
     if (merged) chans = cdiv(L.Cout, 16) * 16;
     const int N = merged ? 2 * chans : std::max(16, cdiv(chans, 16) * 16);   // MMA N
     P.N = N;
@@ -1388,7 +1527,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // tile, which halves the weight bytes staged through shared memory and the B-operand reads per SM.
     // Measured at 1080p (tools/layer_ab.py): pairs win or tie on every layer.
     // (the fused GDN epilogue issues cta_group::1 MMAs of its own: such a kernel cannot mix in cta_group::2)
-    const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0 && !gdn;
+    const bool pair = N % 16 == 0 && env_int("FVC_TC_PAIR", 1) != 0 && !gdn && !tap;
     P.pair = pair ? 1 : 0;
     const int tile_bytes = N * pitch / (pair ? 2 : 1);   // per CTA
     // TMA-store epilogue (FVC_TC_TMAST: 0 off [default], 1 on for every eligible layer): each accumulator warp stages
@@ -1445,10 +1584,13 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         const int ct32 = sx * N / 32;
         if ((sx * N) % 32 != 0 || !(ct32 == 1 || ct32 == 2 || ct32 == 3 || ct32 == 4 || ct32 == 6 || ct32 == 8)) continue;
         if (merged && (ct32 & 1)) continue; // a thread must own both column blocks (hi, lo) of its channel chunks
-        if ((tmast || gdn) && ct32 != 4) continue;        // staging: every thread owns 32 channels of one sub-tile
+        if ((tmast || gdn || tap) && ct32 != 4) continue;   // staging: every thread owns 32 channels of one sub-tile
         // TMA stores: 16 accumulator warps x (2 KB hi + 2 KB lo); fused GDN: A-operand tile (hi + lo block per sub-tile)
         // + three 8 KB gamma tiles
-        const long stage_need = tmast ? 16L * 4096L : (gdn ? (long)sx * 32768L + 24576L : 0L);
+        // fused tail: A-operand tile (hi + lo block per sub-tile and 64-channel segment) + 3 * N/64 weight tiles of 4 KB
+        const long stage_need = tmast ? 16L * 4096L
+                                      : (gdn ? (long)sx * 32768L + 24576L
+                                             : (tap ? (long)sx * (N / 64) * 32768L + 3L * (N / 64) * 4096L : 0L));
         int pw = 8 * sx + max_ext_x;
         pw = cdiv(pw, pw_align) * pw_align;
         size_t patch = (size_t)PH * pw * pitch;
@@ -1484,7 +1626,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     P.o_mode = o_mode;
     P.o_nseg = o_nseg;
     P.stg_bytes = tmast ? 16u * 4096u : (gdn ? (uint32_t)SX * 32768u + 24576u : 0u);
+    if (tap) P.stg_bytes = (((uint32_t)SX * (uint32_t)(N / 64) * 32768u + 3u * (uint32_t)(N / 64) * 4096u) + 1023u) & ~1023u;
     P.gdn = gdn ? 1 : 0;
+    P.tap = tap ? 1 : 0;
     P.CT = SX * N;
     P.patch_bytes = (uint32_t)((((size_t)PH * PW * pitch) + 1023) & ~(size_t)1023);
     P.patch_tx = (uint32_t)((size_t)PH * PW * pitch);
@@ -1492,10 +1636,10 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     P.stage_bytes = (uint32_t)T * P.btile_bytes;
     // partial-accumulator buffers: 4 when they fit the 512 TMEM columns (the MMA issuers then run up to a whole
     // tile ahead of an epilogue), else 2
-    P.nab_log2 = (4 * P.CT <= 512 && env_int("FVC_TC_NAB", 4) >= 4 && !gdn) ? 2 : 1;
+    P.nab_log2 = (4 * P.CT <= 512 && env_int("FVC_TC_NAB", 4) >= 4 && !gdn && !tap) ? 2 : 1;
     uint32_t cols = 32;
-    // fused GDN: the norm accumulators (S x 64 columns) live behind the two partial buffers
-    while (cols < (uint32_t)((1 << P.nab_log2) * P.CT + (gdn ? SX * 64 : 0))) cols <<= 1;
+    // fused GDN / tail: the second MMA's accumulators (S x 64 / S x 32 columns) live behind the two partial buffers
+    while (cols < (uint32_t)((1 << P.nab_log2) * P.CT + (gdn ? SX * 64 : (tap ? SX * 32 : 0)))) cols <<= 1;
     P.tmem_cols = cols;
     P.tiles_x = pair ? cdiv(cdiv(P.Wq, 8 * SX), 2) : cdiv(P.Wq, 8 * SX);
     P.tiles_y = cdiv(P.Hq, 16);
@@ -1699,6 +1843,24 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
             return FVC_ERR_CUDA;
         }
     }
+    if (tap) {
+        const int nt = 3 * (N / 64);
+        cuuint64_t gd[2] = {64, (cuuint64_t)(nt * 32)};
+        cuuint64_t gs[1] = {128};
+        cuuint32_t gb[2] = {64, 32};
+        cuuint32_t ge[2] = {1, 1};
+        CUresult r = encode(&P.mapG, (FVC_SPLIT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2,
+                            (void*)ep.tap_w, gd, gs, gb, ge, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(tail weights) failed: %d", (int)r);
+            cudaFree(plan->wstream);
+            delete plan;
+            return FVC_ERR_CUDA;
+        }
+        const uint32_t fmt = FVC_SPLIT_FP16 ? 0u : 1u;
+        P.tap_idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    }
     if (tmast) {
         const ActT& o = ep.out_act;
         const cuuint64_t rec = (cuuint64_t)o.Cp * 4;
@@ -1787,6 +1949,7 @@ static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
         if constexpr (!RES) {
             if (plan->P.gdn) return tc_launch_t3<NCH, false, false, 2>(plan, s);
         }
+        if (plan->P.tap) return tc_launch_t3<NCH, RES, false, 3>(plan, s);
     }
     return plan->P.pair ? tc_launch_t3<NCH, RES, true>(plan, s) : tc_launch_t3<NCH, RES, false>(plan, s);
 }
@@ -1814,6 +1977,10 @@ int tc_plan_launch(TcPlan* plan, cudaStream_t s) {
 // stand-alone norm convolution's gamma stream: tiles [hi][lo][hi] of 64 rows x 128 B)
 const e16* tc_plan_wstream(const TcPlan* plan) { return plan ? plan->wstream : nullptr; }
 float tc_plan_acc_scale(const TcPlan* plan) { return plan ? plan->P.ep.acc_scale : 0.f; }
+// layout the fused tail convolution expects of its regrouped 1x1 weights: N = 32 rows, not merged, 128-byte rows
+bool tc_plan_is_tap_layout(const TcPlan* plan) {
+    return plan && !plan->P.merged && plan->P.N == 32 && plan->P.pitch == 128 && plan->P.fast == 0;
+}
 bool tc_plan_is_gdn_norm_layout(const TcPlan* plan) {
     return plan && !plan->P.merged && plan->P.N == 64 && plan->P.pitch == 128 && plan->P.fast == 0;
 }

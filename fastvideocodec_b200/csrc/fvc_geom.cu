@@ -586,6 +586,64 @@ int launch_reduce_partials(const float* partials, int n, int groups, double scal
     return 0;
 }
 
+// ----------------------------------------------------------------------------------------------
+// fused 3x3 tail convolutions (mvDecoder.deconv8, Warp_net conv6): weight regrouping and the tap sum
+// ----------------------------------------------------------------------------------------------
+__global__ void k_tapsplit_weights(const float* __restrict__ w, float* __restrict__ o, int Cin, int Cout, int rows) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * Cin) return;
+    const int ci = i % Cin, q = i / Cin;          // q = tap * Cout + co
+    float v = 0.f;
+    if (q < 9 * Cout) {
+        const int tap = q / Cout, co = q - tap * Cout;
+        v = w[((size_t)co * Cin + ci) * 9 + tap];  // OIHW 3x3: tap = r * 3 + s
+    }
+    o[i] = v;
+}
+int launch_tapsplit_weights(const float* w3x3, float* w1x1, int Cin, int Cout, int rows, cudaStream_t s) {
+    k_tapsplit_weights<<<cdiv(rows * Cin, 256), 256, 0, s>>>(w3x3, w1x1, Cin, Cout, rows);
+    g_launch_count++;
+    FVC_CHECK_LAUNCH();
+    return 0;
+}
+// one thread per output pixel; a block covers 128 pixels of one image row, so the 3 x 130 partial-product records it
+// gathers from are read once from HBM and served from L1 afterwards (each record is used by 9 output pixels)
+template <int CO>
+__global__ void __launch_bounds__(128) k_tapsum(const float* __restrict__ P, const float* __restrict__ bias,
+                                                float* __restrict__ out, int H, int W, int cq) {
+    pdl_sync();
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y % H, b = blockIdx.y / H;
+    if (x >= W) return;
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int yy = y + r - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int xx = x + t - 1;
+            if (xx < 0 || xx >= W) continue;
+            const float* p = P + (((size_t)b * H + yy) * W + xx) * (size_t)cq + (r * 3 + t) * CO;
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[c] += p[c];     // fixed order (r, s): deterministic
+        }
+    }
+    float* o = out + (((size_t)b * H + y) * W + x) * CO;
+#pragma unroll
+    for (int c = 0; c < CO; ++c) o[c] = acc[c] + bias[c];
+}
+int launch_tapsum(const float* P, const float* bias, float* out, int B, int H, int W, int Cout, int cq, cudaStream_t s) {
+    FVC_ARG((Cout == 2 || Cout == 3) && 9 * Cout <= cq && (int64_t)B * H <= 65535);
+    dim3 grid((unsigned)cdiv(W, 128), (unsigned)(B * H));
+    if (Cout == 2) FVC_CUDA(launch_pdl(k_tapsum<2>, grid, dim3(128), 0, s, P, bias, out, H, W, cq));
+    else FVC_CUDA(launch_pdl(k_tapsum<3>, grid, dim3(128), 0, s, P, bias, out, H, W, cq));
+    g_launch_count++;
+    FVC_CHECK_LAUNCH();
+    return 0;
+}
+
 // sums6 = mse, warploss, interloss, bits_feature, bits_z, bits_mv ->
 // scalars7 = mse, warploss, interloss, bpp_feature, bpp_z, bpp_mv, bpp   (net.py:212-220)
 __global__ void k_finalize_scalars(const float* __restrict__ sums6, float n_pix, float* __restrict__ out,

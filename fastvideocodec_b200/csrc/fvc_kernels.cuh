@@ -29,6 +29,10 @@ int launch_gdn_reparam(const float* beta, const float* gamma, float* beta_eff, f
 int launch_recon_losses(const float* cur, const float* pred, const float* warp, const float* res, int res_nhwc3,
                         int B, int HW, float* clipped, float* partials, int* nblocks_out, cudaStream_t s,
                         int clip_mse = 0);
+// fused 3x3 tail convolutions: w1x1[(r*3+s)*Cout + co][ci] = w[co][ci][r][s] (rows beyond 9*Cout zero), and the sum of
+// the 9 shifted per-pixel partial products: out[b,y,x,co] = bias[co] + sum_{r,s} P[b,y+r-1,x+s-1,(r*3+s)*Cout+co]
+int launch_tapsplit_weights(const float* w3x3, float* w1x1, int Cin, int Cout, int rows, cudaStream_t s);
+int launch_tapsum(const float* P, const float* bias, float* out, int B, int H, int W, int Cout, int cq, cudaStream_t s);
 int launch_finalize_scalars(const float* sums6, float n_pix, float* scalars7, const unsigned int* sat_count,
                             cudaStream_t s);
 int launch_reduce_partials(const float* partials, int n, int groups, double scale, float* out, cudaStream_t s);
@@ -95,12 +99,13 @@ int launch_conv_few(const ConvLayer& L, const float* w_packed, const float* bias
 struct TcPlan;  // opaque
 // fast = 1: one MMA per product on the hi halves only (fp16 operands, ~11 significant bits), ACT outputs carry hi only
 int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, int Wout, const Epilogue& ep,
-                   TcPlan** plan, cudaStream_t s, bool fast = false);
+                   TcPlan** plan, cudaStream_t s, bool fast = false, bool no_merge = false);
 int tc_plan_launch(TcPlan* plan, cudaStream_t s);
 void tc_plan_destroy(TcPlan* plan);
 const e16* tc_plan_wstream(const TcPlan* plan);
 float tc_plan_acc_scale(const TcPlan* plan);
 bool tc_plan_is_gdn_norm_layout(const TcPlan* plan);
+bool tc_plan_is_tap_layout(const TcPlan* plan);
 bool tc_supported(const ConvLayer& L, int CinP);
 
 }  // namespace fvc

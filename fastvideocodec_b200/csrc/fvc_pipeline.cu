@@ -79,6 +79,8 @@ struct fvc_ctx {
     bool profile = false;
     bool use_few = true;     // FVC_FEW=0 routes the 2-3 output-channel layers through the tensor-core engine
     bool gdn_fused = true;   // FVC_GDN_FUSED=0: (I)GDN as a separate 1x1 "norm" convolution launch (round-1 form)
+    bool tail_fused = true;  // FVC_TAIL_FUSED=0: mvDecoder.deconv8 / warpnet.conv6 as their own 3x3 convolution launches
+    float* taps_buf = nullptr;   // per-pixel partial products of a fused tail convolution, fp32 [B,H,W,<=28]
     double last_conv_seconds = -1.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
     std::vector<std::string> conv_event_names;
@@ -230,6 +232,9 @@ static int build_layers(fvc_ctx* c) {
         snprintf(buf, sizeof(buf), "resDecoder.igdn%d#norm", i);
         add_conv(c, buf, 64, 64, 1, 1, 0, FVC_ACT_NONE, 64);
     }
+    // fused 3x3 tails (tcgen05 engine): the tail's weights regrouped as a 1x1 convolution with (tap, channel) outputs
+    add_conv(c, "mvDecoder.deconv8#taps", 128, 32, 1, 1, 0, FVC_ACT_NONE, 128);
+    add_conv(c, "warpnet.conv6#taps", 64, 32, 1, 1, 0, FVC_ACT_NONE, 64);
     c->be_z.name = "bitEstimator_z"; c->be_z.C = 64;
     c->be_mv.name = "bitEstimator_mv"; c->be_mv.C = 128;
     // device storage for parameters
@@ -239,6 +244,7 @@ static int build_layers(fvc_ctx* c) {
         if (c->alloc(&r.w_raw, nw * sizeof(float))) return FVC_ERR_CUDA;
         if (c->alloc(&r.bias, (size_t)r.L.Cout * sizeof(float))) return FVC_ERR_CUDA;
     }
+    for (const char* tn : {"mvDecoder.deconv8#taps", "warpnet.conv6#taps"}) c->conv[tn].have_b = true;   // zero bias
     for (auto& kv : c->gdn) {
         GdnRt& g = kv.second;
         if (c->alloc(&g.beta_raw, 64 * 4) || c->alloc(&g.gamma_raw, 64 * 64 * 4) || c->alloc(&g.beta_eff, 64 * 4) ||
@@ -338,6 +344,7 @@ static int build_buffers(fvc_ctx* c) {
     A(c->alloc(&c->bits_counts, 3 * sizeof(int)));
     A(c->alloc(&c->scalars, 8 * 4));
     A(c->alloc(&c->sat_count, 4));
+    if (c->impl != FVC_IMPL_SIMT) A(c->alloc(&c->taps_buf, (size_t)B * H * W * 28 * 4));
 #undef A
     return 0;
 }
@@ -488,8 +495,35 @@ static int run_conv_gdn(fvc_ctx* c, const std::string& conv, const std::string& 
     return run_conv(c, nname, sq, out.H, out.W, en, s);
 }
 
+// Fused 3x3 tail (SURVEY 7.1-8 / VERDICT r1 #4b,c): fills the producer's epilogue with the tail's regrouped weights.
+// `tail` = name of the 3x3 convolution with 2-3 outputs, `y` = geometry of the producer's output (never written).
+static int tail_epilogue(fvc_ctx* c, const std::string& tail, ActT y, Epilogue& ep, cudaStream_t s) {
+    ConvRt& t = c->conv[tail + "#taps"];
+    ConvRt& tl = c->conv[tail];
+    if (!t.have_w) {
+        set_error("parameters of %s not set", tail.c_str());
+        return FVC_ERR_STATE;
+    }
+    if (!t.tc) {   // created (never launched): owns the packed 32-row weight tiles and their scale
+        Epilogue et = make_ep(t);
+        et.bias = t.bias;
+        et.out_f32 = c->taps_buf;
+        int rc = tc_plan_create(t.L, t.w_raw, y, y.H, y.W, et, &t.tc, s, false, true);
+        if (rc) return rc;
+    }
+    if (!tc_plan_is_tap_layout(t.tc)) {
+        set_error("unexpected weight layout for the fused tail %s", tail.c_str());
+        return FVC_ERR_STATE;
+    }
+    ep.tap_w = tc_plan_wstream(t.tc);
+    ep.tap_scale = tc_plan_acc_scale(t.tc);
+    ep.tap_out = c->taps_buf;
+    ep.tap_cq = (9 * tl.L.Cout + 3) & ~3;
+    return 0;
+}
+
 static int res_block(fvc_ctx* c, int idx, ActT x_relu, ActT x_skip, ActT tmp, ActT out, ActT out_relu,
-                     cudaStream_t s) {
+                     cudaStream_t s, const char* fused_tail = nullptr) {
     char n1[64], n2[64];
     snprintf(n1, sizeof(n1), "warpnet.conv%d.conv1", idx);
     snprintf(n2, sizeof(n2), "warpnet.conv%d.conv2", idx);
@@ -499,8 +533,13 @@ static int res_block(fvc_ctx* c, int idx, ActT x_relu, ActT x_skip, ActT tmp, Ac
     if (rc) return rc;
     ep = make_ep(c->conv[n2]);
     ep.res_act = x_skip;
-    ep.out_act = out;
-    ep.out_act_relu = out_relu;
+    if (fused_tail) {   // the block's output only feeds a 3x3 tail: it stays in the SM (second MMA), P goes out
+        rc = tail_epilogue(c, fused_tail, out, ep, s);
+        if (rc) return rc;
+    } else {
+        ep.out_act = out;
+        ep.out_act_relu = out_relu;
+    }
     return run_conv(c, n2, tmp, out.H, out.W, ep, s);
 }
 
@@ -563,9 +602,20 @@ static int run_mv_decoder(fvc_ctx* c, cudaStream_t s) {
         snprintf(nm, sizeof(nm), "mvDecoder.deconv%d", i);
         Epilogue ep = make_ep(c->conv[nm]);
         int sh = 4 - (i + 1) / 2;
+        int rc;
+        if (i == 7 && c->tail_fused) {
+            // deconv7 -> LeakyReLU -> deconv8 (synthesis_mv.py:77-79) in one kernel + the tap sum: the 128-channel
+            // full-resolution tensor (1.07 GB at 1080p) is never written
+            rc = tail_epilogue(c, "mvDecoder.deconv8", c->d[7], ep, s);
+            if (!rc) rc = run_conv(c, nm, in, H, W, ep, s);
+            if (rc) return rc;
+            ConvRt& t8 = c->conv["mvDecoder.deconv8"];
+            PK("@k_tapsum:mv", launch_tapsum(c->taps_buf, t8.bias, c->mv_hat, c->B, H, W, 2, ep.tap_cq, s));
+            break;
+        }
         if (i < 8) ep.out_act = c->d[i];
         else ep.out_f32 = c->mv_hat;
-        int rc = run_conv(c, nm, in, H >> sh, W >> sh, ep, s);
+        rc = run_conv(c, nm, in, H >> sh, W >> sh, ep, s);
         if (rc) return rc;
         if (i < 8) in = c->d[i];
     }
@@ -659,8 +709,13 @@ static int run_motion_comp(fvc_ctx* c, const float* cur, const float* ref, cudaS
     PK("@k_upadd_act:half", launch_upadd_act(c->wc3, c->wc1, c->wc3u, c->wc3u_r, s));
     R(res_block(c, 4, c->wc3u_r, c->wc3u, c->wt4, c->wc4, no_act(), s));
     PK("@k_upadd_act:full", launch_upadd_act(c->wc4, c->wc0, c->wc4u, c->wc4u_r, s));
-    R(res_block(c, 5, c->wc4u_r, c->wc4u, c->wt5, c->wc5, no_act(), s));
-    {
+    if (c->tail_fused) {
+        // ResBlock 5's conv2 (+ skip) -> conv6 (endecoder.py:294-295) in one kernel + the tap sum
+        R(res_block(c, 5, c->wc4u_r, c->wc4u, c->wt5, c->wc5, no_act(), s, "warpnet.conv6"));
+        ConvRt& t6 = c->conv["warpnet.conv6"];
+        PK("@k_tapsum:warpnet", launch_tapsum(c->taps_buf, t6.bias, c->wres, c->B, H, W, 3, 28, s));
+    } else {
+        R(res_block(c, 5, c->wc4u_r, c->wc4u, c->wt5, c->wc5, no_act(), s));
         Epilogue ep = make_ep(c->conv["warpnet.conv6"]);
         ep.out_f32 = c->wres;
         R(run_conv(c, "warpnet.conv6", c->wc5, H, W, ep, s));
@@ -809,6 +864,8 @@ fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl) {
     c->use_few = !(few && few[0] == '0');
     const char* gf = getenv("FVC_GDN_FUSED");
     c->gdn_fused = !(gf && gf[0] == '0');
+    const char* tf = getenv("FVC_TAIL_FUSED");
+    c->tail_fused = impl != FVC_IMPL_SIMT && !(tf && tf[0] == '0');
     if (build_layers(c) || build_buffers(c)) {
         fvc_ctx_destroy(c);
         return nullptr;
@@ -860,6 +917,17 @@ int fvc_ctx_set_param(fvc_ctx* c, const char* key_c, const float* data, int64_t 
             }
             if (r.tc) { tc_plan_destroy(r.tc); r.tc = nullptr; }
             r.have_w = true;
+            // a fused tail's regrouped weights follow its 3x3 weights; the producer's plan points at their stream
+            const char* prod = mod == "mvDecoder.deconv8" ? "mvDecoder.deconv7" : (mod == "warpnet.conv6" ? "warpnet.conv5.conv2" : nullptr);
+            if (prod) {
+                ConvRt& t = c->conv[mod + "#taps"];
+                rc = launch_tapsplit_weights(r.w_raw, t.w_raw, r.L.Cin, r.L.Cout, 32, s);
+                if (rc) return rc;
+                if (t.tc) { tc_plan_destroy(t.tc); t.tc = nullptr; }
+                t.have_w = true;
+                ConvRt& pr = c->conv[prod];
+                if (pr.tc) { tc_plan_destroy(pr.tc); pr.tc = nullptr; }
+            }
             return 0;
         }
         if (leaf == "bias") {

@@ -1181,3 +1181,30 @@ def test_fused_gdn_bit_identical_to_separate_norm_convolution(dev, state_dict, m
     assert torch.equal(a[0][0], b[0][0]) and all(float(x) == float(y) for x, y in zip(a[0][1:], b[0][1:]))
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     print("launches fused %d vs separate %d" % (a[3], b[3]))
+
+
+def test_fused_tails_match_separate_convolutions(dev, state_dict, monkeypatch):
+    """mvDecoder.deconv7->deconv8 and Warp_net conv5.conv2->conv6 fused (the wide tensor stays in the SM: second MMA
+    against the tail's weights regrouped per (tap, channel), then the 9-tap sum) against the separate 3x3 launches.
+    Same products from the same 22-bit rounded y; only the fp32 summation order over the 9 taps differs."""
+    from fastvideocodec_b200 import VideoCompressor
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    fr = synthetic_gop(192, 320, gop=2, gop_id=8).to(dev)
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("FVC_TAIL_FUSED", fused)
+        m = VideoCompressor()
+        m.load_state_dict(state_dict)
+        m = m.to(dev).eval()
+        m.impl = _impls()[-1][1]
+        with torch.no_grad():
+            out = m(fr[1], fr[0])
+        res[fused] = (out, m.get_intermediate("mv_hat"), m.get_intermediate("warpnet_res"), m.get_intermediate("quant_mv"),
+                      m.launch_count())
+        m.release()
+    a, b = res["1"], res["0"]
+    assert torch.equal(a[3], b[3])                                   # upstream of both tails: identical
+    assert (a[1] - b[1]).abs().max().item() <= 2e-6 * max(1.0, b[1].abs().max().item())
+    assert (a[2] - b[2]).abs().max().item() <= 2e-6 * max(1.0, b[2].abs().max().item())
+    assert abs(float(a[0][7]) - float(b[0][7])) <= 1e-4 * float(b[0][7])
+    print("launches fused %d vs separate %d" % (a[4], b[4]))
