@@ -201,13 +201,12 @@ __device__ __forceinline__ void store_record(const ActT& t, e16* rec, const floa
 __global__ void k_spynet_prep(const float* __restrict__ im1, const float* __restrict__ im2,
                               const float* __restrict__ flow_prev, ActT X, float* __restrict__ flow_up) {
     pdl_sync();
-    int H = X.H, W = X.W;
-    int64_t n = (int64_t)X.B * H * W;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int x = (int)(i % W);
-    int y = (int)((i / W) % H);
-    int b = (int)(i / ((int64_t)W * H));
+    const int H = X.H, W = X.W;
+    // 2-D grid: x from blockIdx.x, (b, y) from blockIdx.y (no 64-bit divisions per thread)
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = (int)blockIdx.y % H, b = (int)blockIdx.y / H;
+    if (x >= W) return;
+    const int64_t i = ((int64_t)b * H + y) * W + x;
     float ux = 0.f, uy = 0.f;
     if (flow_prev) {
         int h = H >> 1, w = W >> 1;
@@ -237,8 +236,9 @@ __global__ void k_spynet_prep(const float* __restrict__ im1, const float* __rest
 int launch_spynet_prep(const float* im1, const float* im2, const float* flow_prev, ActT X, float* flow_up,
                        cudaStream_t s) {
     FVC_ARG(X.Cp == 32 || X.Cp == 8);
-    int64_t n = (int64_t)X.B * X.H * X.W;
-    FVC_CUDA(launch_pdl(k_spynet_prep, LAUNCH_1D(n, 128), 0, s, im1, im2, flow_prev, X, flow_up));
+    FVC_ARG((int64_t)X.B * X.H <= 65535);
+    FVC_CUDA(launch_pdl(k_spynet_prep, dim3((unsigned)cdiv(X.W, 128), (unsigned)(X.B * X.H)), dim3(128), 0, s, im1, im2,
+                        flow_prev, X, flow_up));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -250,13 +250,12 @@ int launch_spynet_prep(const float* im1, const float* im2, const float* flow_pre
 __global__ void k_mc_prep(const float* __restrict__ ref, const float* __restrict__ mv, float* __restrict__ warpframe,
                           ActT X) {
     pdl_sync();
-    int H = X.H, W = X.W;
-    int64_t n = (int64_t)X.B * H * W;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int x = (int)(i % W);
-    int y = (int)((i / W) % H);
-    int b = (int)(i / ((int64_t)W * H));
+    const int H = X.H, W = X.W;
+    // 2-D grid: x from blockIdx.x, (b, y) from blockIdx.y (no 64-bit divisions per thread)
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = (int)blockIdx.y % H, b = (int)blockIdx.y / H;
+    if (x >= W) return;
+    const int64_t i = ((int64_t)b * H + y) * W + x;
     float2 f = reinterpret_cast<const float2*>(mv)[i];
     WarpTaps t = warp_taps(x, y, f.x, f.y, W, H);
     size_t hw = (size_t)H * W;
@@ -273,8 +272,9 @@ __global__ void k_mc_prep(const float* __restrict__ ref, const float* __restrict
 }
 int launch_mc_prep(const float* ref, const float* mv, float* warpframe, ActT X, cudaStream_t s) {
     FVC_ARG(X.Cp == 32 || X.Cp == 8);
-    int64_t n = (int64_t)X.B * X.H * X.W;
-    FVC_CUDA(launch_pdl(k_mc_prep, LAUNCH_1D(n, 128), 0, s, ref, mv, warpframe, X));
+    FVC_ARG((int64_t)X.B * X.H <= 65535);
+    FVC_CUDA(launch_pdl(k_mc_prep, dim3((unsigned)cdiv(X.W, 128), (unsigned)(X.B * X.H)), dim3(128), 0, s, ref, mv,
+                        warpframe, X));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -284,13 +284,12 @@ int launch_mc_prep(const float* ref, const float* mv, float* warpframe, ActT X, 
 __global__ void k_mc_finish(const float* __restrict__ res, const float* __restrict__ warpframe,
                             const float* __restrict__ cur, float* __restrict__ pred, ActT R) {
     pdl_sync();
-    int H = R.H, W = R.W;
-    int64_t n = (int64_t)R.B * H * W;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int x = (int)(i % W);
-    int y = (int)((i / W) % H);
-    int b = (int)(i / ((int64_t)W * H));
+    const int H = R.H, W = R.W;
+    // 2-D grid: x from blockIdx.x, (b, y) from blockIdx.y (no 64-bit divisions per thread)
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = (int)blockIdx.y % H, b = (int)blockIdx.y / H;
+    if (x >= W) return;
+    const int64_t i = ((int64_t)b * H + y) * W + x;
     size_t hw = (size_t)H * W;
     size_t po = (size_t)y * W + x;
     float v[3];
@@ -306,8 +305,9 @@ __global__ void k_mc_finish(const float* __restrict__ res, const float* __restri
 int launch_mc_finish(const float* res, const float* warpframe, const float* cur, float* pred, ActT R,
                      cudaStream_t s) {
     FVC_ARG(R.Cp == 32 || R.Cp == 8);
-    int64_t n = (int64_t)R.B * R.H * R.W;
-    FVC_CUDA(launch_pdl(k_mc_finish, LAUNCH_1D(n, 128), 0, s, res, warpframe, cur, pred, R));
+    FVC_ARG((int64_t)R.B * R.H <= 65535);
+    FVC_CUDA(launch_pdl(k_mc_finish, dim3((unsigned)cdiv(R.W, 128), (unsigned)(R.B * R.H)), dim3(128), 0, s, res,
+                        warpframe, cur, pred, R));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -520,26 +520,25 @@ __global__ void k_recon_losses(const float* __restrict__ cur, const float* __res
                                int HW, float* __restrict__ clipped, float* __restrict__ partials, int clip_mse) {
     pdl_sync();
     __shared__ float red[32];
-    int64_t n = (int64_t)B * 3 * HW;
+    // one pixel (3 channels) per thread and step; (b, pixel) from a 32-bit index (B * HW < 2^31 checked on the host)
+    const int npx = B * HW;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float r;
-        if (res_nhwc3) {
-            int p = (int)(i % HW);
-            int c = (int)((i / HW) % 3);
-            int b = (int)(i / ((int64_t)3 * HW));
-            r = res[((size_t)b * HW + p) * 3 + c];
-        } else {
-            r = res[i];
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < npx; i += (int)(gridDim.x * blockDim.x)) {
+        const int b = i / HW, p = i - b * HW;
+        const size_t plane0 = (size_t)b * 3 * HW + p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const size_t o = plane0 + (size_t)c * HW;
+            const float r = res_nhwc3 ? res[(size_t)i * 3 + c] : res[o];
+            const float c0 = cur[o], p0 = pred[o], w0 = warp[o];
+            const float rec = p0 + r;
+            const float cl = fminf(fmaxf(rec, 0.f), 1.f);
+            clipped[o] = cl;
+            const float d0 = (clip_mse ? cl : rec) - c0, d1 = w0 - c0, d2 = p0 - c0;
+            s0 = fmaf(d0, d0, s0);
+            s1 = fmaf(d1, d1, s1);
+            s2 = fmaf(d2, d2, s2);
         }
-        float c0 = cur[i], p0 = pred[i], w0 = warp[i];
-        float rec = p0 + r;
-        const float cl = fminf(fmaxf(rec, 0.f), 1.f);
-        clipped[i] = cl;
-        float d0 = (clip_mse ? cl : rec) - c0, d1 = w0 - c0, d2 = p0 - c0;
-        s0 = fmaf(d0, d0, s0);
-        s1 = fmaf(d1, d1, s1);
-        s2 = fmaf(d2, d2, s2);
     }
     s0 = block_sum(s0, red);
     s1 = block_sum(s1, red);
@@ -553,8 +552,9 @@ __global__ void k_recon_losses(const float* __restrict__ cur, const float* __res
 int launch_recon_losses(const float* cur, const float* pred, const float* warp, const float* res, int res_nhwc3,
                         int B, int HW, float* clipped, float* partials, int* nblocks_out, cudaStream_t s,
                         int clip_mse) {
-    int64_t n = (int64_t)B * 3 * HW;
-    int blocks = (int)std::min<int64_t>(cdiv64(n, 256 * 4), 148 * 8);
+    FVC_ARG((int64_t)B * HW < (1ll << 31));
+    int64_t n = (int64_t)B * HW;
+    int blocks = (int)std::min<int64_t>(cdiv64(n, 256 * 2), 148 * 8);
     if (blocks < 1) blocks = 1;
     FVC_CUDA(launch_pdl(k_recon_losses, blocks, 256, 0, s, cur, pred, warp, res, res_nhwc3, B, HW, clipped, partials, clip_mse));
     g_launch_count++;
