@@ -1466,7 +1466,7 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
                 (ep.tap_cq & 3) == 0 && !ep.out_act.p && !ep.out_f32 && !ep.res_f32 && !ep.out_act_relu.p &&
                 !ep.out_act_sq.p && (!ep.res_act.p || ep.res_mode == 0));
     }
-    const bool merged = !fast && !gdn && !no_merge && ((Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 0)));
+    const bool merged = !fast && !gdn && !no_merge && ((Cp >= 32 && L.Cout <= merge_max) || (Cp == 8 && L.Cout <= env_int("FVC_TC_MERGED_NARROW", 32)));
     if (merged) chans = cdiv(L.Cout, 16) * 16;
     const int N = merged ? 2 * chans : std::max(16, cdiv(chans, 16) * 16);   // MMA N
     P.N = N;

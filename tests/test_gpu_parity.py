@@ -1208,3 +1208,29 @@ def test_fused_tails_match_separate_convolutions(dev, state_dict, monkeypatch):
     assert (a[2] - b[2]).abs().max().item() <= 2e-6 * max(1.0, b[2].abs().max().item())
     assert abs(float(a[0][7]) - float(b[0][7])) <= 1e-4 * float(b[0][7])
     print("launches fused %d vs separate %d" % (a[4], b[4]))
+
+
+def test_lsvc_forward_matches_oracle_larger_frames(dev, state_dict):
+    """LSVC tree GOP (models.py:1344-1411) at 192x320 with 6 P-frames (three tree layers: batches of 6 / 2 / 4) against
+    the oracle's restatement (pinned to the unmodified reference at 64x64): bpp / losses within 0.5 %, frames of the
+    FIRST tree layer (they depend on no quantiser of this GOP but the mv latents) element-wise, all frames in the mean."""
+    from fastvideocodec_b200.lsvc import LSVC, graph_from_batch, refidx_from_graph
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    x = synthetic_gop(192, 320, gop=7, gop_id=14)[:, 0]
+    g, layers, parents = graph_from_batch(6)
+    want = O.lsvc_forward(state_dict, x, layers, parents, refidx_from_graph(g, 6))
+    m = LSVC("LSVC-128")
+    m.load_state_dict(state_dict)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        out = m(x.to(dev))
+    for i, n in enumerate(["rec_loss", "warp_loss", "mc_loss", "bpp_res", "bpp"], start=3):
+        a, b = float(out[i]), float(want[i])
+        assert abs(a - b) <= 0.005 * abs(b), (n, a, b)
+    first = [t - 1 for t in layers[0] if t <= 6]
+    for i, n in ((1, "mc"), (2, "warped")):
+        d = (out[i].cpu() - want[i]).abs()
+        assert d[first].max().item() <= 5e-3, (n, d[first].max().item())      # a tie-flipped mv latent moves these by ~2e-3
+        assert d.mean().item() <= 2e-3, (n, d.mean().item())
+    assert (out[0].cpu() - want[0]).abs().mean().item() <= 2e-3
+    m.release()
