@@ -361,11 +361,17 @@ struct PassIter {
     int b, sub, ty, tx;
     int xmul, xadd;     // CTA pairs: tile column = 2 * (pair column) + CTA rank
     __device__ __forceinline__ void decode(const TcParams& P) {
+        // the sub-convolution (output phase of a stride-2 transposed convolution) varies fastest: the 4 phases of a
+        // q-tile read the same input patch and now run at the same time on neighbouring CTAs, so three of the four
+        // patch loads hit L2 (phase-major order re-read the whole input from DRAM once per phase: 1.07 GB instead of
+        // 0.27 GB for mvDecoder.deconv7, ncu)
+        // (rotated by the q-tile index: a persistent CTA strides by a multiple of 4 tiles and would otherwise always get
+        // the same phase, and the phases have 1, 2, 2 and 4 taps)
         int t = tile;
+        sub = (t + t / P.nsub) % P.nsub; t /= P.nsub;
         tx = (t % P.tiles_x) * xmul + xadd; t /= P.tiles_x;
-        ty = t % P.tiles_y; t /= P.tiles_y;
-        sub = t % P.nsub;
-        b = t / P.nsub;
+        ty = t % P.tiles_y;
+        b = t / P.tiles_y;
     }
     __device__ __forceinline__ bool valid(int ntiles) const { return tile < ntiles; }
     __device__ __forceinline__ void next(const TcParams& P, int stride) {
@@ -1125,21 +1131,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         // this warp's staging blocks (TMA-store epilogue: STG instantiations, CT = 128 only)
         const uint32_t stg = (STG && P.tmast) ? stg0 + (uint32_t)(warp - TC_ACC_WARP0) * 4096u : 0u;
         uint32_t gphase = 0;      // phase of the fused GDN's "norm MMAs done" barrier
-        const int tiles_xy = P.tiles_x * P.tiles_y;
 #ifdef FVC_TC_ACCDBG
         const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == TC_ACC_WARP0;
         long long a_wait = 0, a_drain = 0, a_epi = 0;
 #endif
         for (int tile = tile0; tile < ntiles; tile += tstride) {
-            const int ng = P.sub[(tile / tiles_xy) % P.nsub].ngroups;
+            const int ng = P.sub[(tile + tile / P.nsub) % P.nsub].ngroups;
             if (RES) {
                 // pull this thread's skip-connection records into L2 while the tile's MMAs run (the epilogue's
                 // loads then hit L2 instead of paying DRAM latency in the middle of the store stream)
                 int t = tile;
+                const int sub = (t + t / P.nsub) % P.nsub; t /= P.nsub;
                 const int tx = (t % P.tiles_x) * xmul + xadd; t /= P.tiles_x;
-                const int ty = t % P.tiles_y; t /= P.tiles_y;
-                const int sub = t % P.nsub;
-                const int b = t / P.nsub;
+                const int ty = t % P.tiles_y;
+                const int b = t / P.tiles_y;
                 const int Nv = P.merged ? (P.N >> 1) : P.N;
                 const int cb = P.merged ? (int)(colbase >> 1) : (int)colbase;
                 const int nc = P.merged ? NCH * 4 : NCH * 8;
@@ -1205,10 +1210,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             // address arithmetic cannot be hoisted above the drain loop, where it would spill `run`
             int t = tile;
             asm volatile("" : "+r"(t));
+            const int sub = (t + t / P.nsub) % P.nsub; t /= P.nsub;
             const int tx = (t % P.tiles_x) * xmul + xadd; t /= P.tiles_x;
-            const int ty = t % P.tiles_y; t /= P.tiles_y;
-            const int sub = t % P.nsub;
-            const int b = t / P.nsub;
+            const int ty = t % P.tiles_y;
+            const int b = t / P.tiles_y;
             if (STG && stg) {
                 // the warp's staging blocks are free once its previous bulk stores have READ them (a tile ago)
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
