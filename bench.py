@@ -426,7 +426,7 @@ def run_ours(args, rank, world, local_rank):
                 "scaling": "weak", "vs_baseline": None, "dtype": {"tc": "f16 hi/lo pairs x3 MMAs (fp32 accumulate)", "tc-fast": "f16 x1 MMA (fp32 accumulate)",
                                                   "simt": "f32"}[impl_name],
                 "data": "synthetic",
-                "config": {"workload": CONFIGS[args.config][3],
+                "config": {"workload": CONFIGS[args.config][3] + (" (%d views per rank)" % BATCH if args.config == "multiview" else ""),
                            "engine": impl_name, "l2": "per-frame working set (GBs of activations) exceeds the 126 MB L2",
                            "parallelism": "gop-sharded x%d, no data-path collective" % world},
                 "clocks": clk.summary(),
@@ -456,6 +456,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config == "multiview" and world > 1 and BATCH % world == 0:
+        BATCH //= world      # configs[4] "one view per GPU": the 8 camera views are split over the ranks (8 GPUs: B = 1 each)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
