@@ -154,6 +154,12 @@ struct fvc_ctx {
         *p = reinterpret_cast<T*>(q);
         return 0;
     }
+    // geometry only, storage borrowed from `like` (a tensor that is never written or read through this handle: it only
+    // shapes the TMA descriptors of a plan that is created for its packed weights and never launched)
+    void alias_act(ActT* t, int h, int w, int Cp, int parity, void* like) {
+        t->B = B; t->H = h; t->W = w; t->Cp = Cp; t->parity = parity;
+        t->p = reinterpret_cast<e16*>(like);
+    }
     int alloc_act(ActT* t, int h, int w, int Cp, int parity) {
         t->B = B; t->H = h; t->W = w; t->Cp = Cp; t->parity = parity;
         return alloc(&t->p, act_bytes(B, h, w, Cp));
@@ -288,6 +294,7 @@ static int build_buffers(fvc_ctx* c) {
     A(c->alloc_act(&c->quant_mv, H / 16, W / 16, 128, 0));
     for (int i = 1; i <= 7; ++i) {
         int sh = 4 - (i + 1) / 2;  // deconv1 -> H/8, deconv2 -> H/8, deconv3 -> H/4, ...
+        if (i == 7 && c->tail_fused) continue;   // deconv7's output stays in the SM (fused deconv8): 1.07 GB at 1080p
         A(c->alloc_act(&c->d[i], H >> sh, W >> sh, 128, 0));
     }
     A(c->alloc(&c->mv_hat, (size_t)B * H * W * 2 * 4));
@@ -314,15 +321,19 @@ static int build_buffers(fvc_ctx* c) {
     A(c->alloc_act(&c->wc4u, H, W, 64, 0));
     A(c->alloc_act(&c->wc4u_r, H, W, 64, 0));
     A(c->alloc_act(&c->wt5, H, W, 64, 0));
-    A(c->alloc_act(&c->wc5, H, W, 64, 0));
+    if (!c->tail_fused) A(c->alloc_act(&c->wc5, H, W, 64, 0));   // else: stays in the SM (fused conv6)
     A(c->alloc(&c->wres, (size_t)B * H * W * 3 * 4));
     A(c->alloc(&c->prediction, (size_t)B * 3 * H * W * 4));
     A(c->alloc_act(&c->residual, H, W, c->cp_narrow, 1));
     for (int i = 0; i < 3; ++i) {
-        A(c->alloc_act(&c->r_raw[i], H >> (i + 1), W >> (i + 1), 64, 0));
         A(c->alloc_act(&c->r[i], H >> (i + 1), W >> (i + 1), 64, 1));
-        A(c->alloc_act(&c->r_sq[i], H >> (i + 1), W >> (i + 1), 64, 0));
-        A(c->alloc_act(&c->g_sq[i], H >> (3 - i), W >> (3 - i), 64, 0));
+        if (c->gdn_fused) {   // raw conv output and its squares never leave the SM: geometry only
+            c->alias_act(&c->r_raw[i], H >> (i + 1), W >> (i + 1), 64, 0, c->r[i].p);
+            c->alias_act(&c->r_sq[i], H >> (i + 1), W >> (i + 1), 64, 0, c->r[i].p);
+        } else {
+            A(c->alloc_act(&c->r_raw[i], H >> (i + 1), W >> (i + 1), 64, 0));
+            A(c->alloc_act(&c->r_sq[i], H >> (i + 1), W >> (i + 1), 64, 0));
+        }
     }
     A(c->alloc(&c->feature, (size_t)B * (H / 16) * (W / 16) * 96 * 4));
     A(c->alloc_act(&c->featabs, H / 16, W / 16, 128, 0));
@@ -335,8 +346,14 @@ static int build_buffers(fvc_ctx* c) {
     A(c->alloc(&c->sigma, (size_t)B * (H / 16) * (W / 16) * 96 * 4));
     A(c->alloc_act(&c->feat_hat, H / 16, W / 16, 128, 0));
     for (int i = 0; i < 3; ++i) {
-        A(c->alloc_act(&c->g_raw[i], H >> (3 - i), W >> (3 - i), 64, 0));
         A(c->alloc_act(&c->g[i], H >> (3 - i), W >> (3 - i), 64, 0));
+        if (c->gdn_fused) {
+            c->alias_act(&c->g_raw[i], H >> (3 - i), W >> (3 - i), 64, 0, c->g[i].p);
+            c->alias_act(&c->g_sq[i], H >> (3 - i), W >> (3 - i), 64, 0, c->g[i].p);
+        } else {
+            A(c->alloc_act(&c->g_raw[i], H >> (3 - i), W >> (3 - i), 64, 0));
+            A(c->alloc_act(&c->g_sq[i], H >> (3 - i), W >> (3 - i), 64, 0));
+        }
     }
     A(c->alloc(&c->recon_res, (size_t)B * H * W * 3 * 4));
     A(c->alloc(&c->loss_partials, (size_t)148 * 8 * 3 * 4));
@@ -345,6 +362,10 @@ static int build_buffers(fvc_ctx* c) {
     A(c->alloc(&c->scalars, 8 * 4));
     A(c->alloc(&c->sat_count, 4));
     if (c->impl != FVC_IMPL_SIMT) A(c->alloc(&c->taps_buf, (size_t)B * H * W * 28 * 4));
+    if (c->tail_fused) {   // geometry of the two tensors that stay in the SM (they shape never-launched plans)
+        c->alias_act(&c->d[7], H, W, 128, 0, c->taps_buf);
+        c->alias_act(&c->wc5, H, W, 64, 0, c->taps_buf);
+    }
 #undef A
     return 0;
 }
@@ -862,10 +883,11 @@ fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl) {
     c->profile = prof && prof[0] == '1';
     const char* few = getenv("FVC_FEW");
     c->use_few = !(few && few[0] == '0');
-    const char* gf = getenv("FVC_GDN_FUSED");
-    c->gdn_fused = !(gf && gf[0] == '0');
-    const char* tf = getenv("FVC_TAIL_FUSED");
-    c->tail_fused = impl != FVC_IMPL_SIMT && !(tf && tf[0] == '0');
+
+    const char* gf0 = getenv("FVC_GDN_FUSED");
+    c->gdn_fused = impl != FVC_IMPL_SIMT && !(gf0 && gf0[0] == '0');
+    const char* tf0 = getenv("FVC_TAIL_FUSED");
+    c->tail_fused = impl != FVC_IMPL_SIMT && !(tf0 && tf0[0] == '0');
     if (build_layers(c) || build_buffers(c)) {
         fvc_ctx_destroy(c);
         return nullptr;
@@ -1233,6 +1255,10 @@ int64_t fvc_ctx_get_tensor(fvc_ctx* c, const char* name_c, float* out, int64_t c
         if (cnt > capacity) { set_error("capacity too small"); return FVC_ERR_ARG; }
         int rc = launch_nhwc_to_nchw(fi->second.p, out, B, fi->second.C, fi->second.h, fi->second.w, s);
         return rc ? rc : cnt;
+    }
+    if (c->tail_fused && (n == "mvdec_d7" || n == "warpnet_c5")) {
+        set_error("%s is not materialised: it stays in the SM (fused tail convolution; FVC_TAIL_FUSED=0 restores it)", name_c);
+        return FVC_ERR_STATE;
     }
     auto ai = act.find(n);
     if (ai != act.end()) {
