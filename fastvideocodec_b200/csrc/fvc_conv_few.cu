@@ -40,6 +40,19 @@ __global__ void k_few_pack(const float* __restrict__ w, float* __restrict__ out,
     out[i] = ci < Cin ? w[((size_t)co * Cin + ci) * K * K + tap] : 0.f;
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): d.{x,y} += a.{x,y} * b.{x,y}, two IEEE fp32 FMAs per instruction.  The operands are
+// adjacent register pairs of the float4s already loaded from shared memory, so no moves are needed.
+__device__ __forceinline__ void ffma2(float2& d, float ax, float ay, float bx, float by) {
+    asm("{\n\t.reg .b64 a, b, c;\n\t"
+        "mov.b64 a, {%2, %3};\n\t"
+        "mov.b64 b, {%4, %5};\n\t"
+        "mov.b64 c, {%0, %1};\n\t"
+        "fma.rn.f32x2 c, a, b, c;\n\t"
+        "mov.b64 {%0, %1}, c;\n\t}"
+        : "+f"(d.x), "+f"(d.y)
+        : "f"(ax), "f"(ay), "f"(bx), "f"(by));
+}
+
 template <int K, int CO>
 __global__ void __launch_bounds__(128) k_conv_few(const __grid_constant__ FewParams P) {
     pdl_sync();
@@ -49,11 +62,12 @@ __global__ void __launch_bounds__(128) k_conv_few(const __grid_constant__ FewPar
     float4* wq = smf + PH * 4 * PW;            // [K*K][4][CO]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-    float acc[4][CO];
+    // two partial sums per (pixel, output): even and odd input channels of each float4 (packed FFMA2); added at the end
+    float2 acc[4][CO];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int c = 0; c < CO; ++c) acc[p][c] = 0.f;
+        for (int c = 0; c < CO; ++c) acc[p][c] = make_float2(0.f, 0.f);
     const int nchunk = P.Cin / 16;
     const int Cp = P.in.Cp;
     for (int chunk = 0; chunk < nchunk; ++chunk) {
@@ -104,10 +118,8 @@ __global__ void __launch_bounds__(128) k_conv_few(const __grid_constant__ FewPar
                         const float4 w = wq[((r * K + s) * 4 + c4) * CO + c];
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
-                            acc[p][c] = fmaf(v[p + r].x, w.x, acc[p][c]);
-                            acc[p][c] = fmaf(v[p + r].y, w.y, acc[p][c]);
-                            acc[p][c] = fmaf(v[p + r].z, w.z, acc[p][c]);
-                            acc[p][c] = fmaf(v[p + r].w, w.w, acc[p][c]);
+                            ffma2(acc[p][c], v[p + r].x, v[p + r].y, w.x, w.y);
+                            ffma2(acc[p][c], v[p + r].z, v[p + r].w, w.z, w.w);
                         }
                     }
                 }
@@ -125,7 +137,7 @@ __global__ void __launch_bounds__(128) k_conv_few(const __grid_constant__ FewPar
         float o[CO];
 #pragma unroll
         for (int c = 0; c < CO; ++c) {
-            o[c] = acc[p][c] + P.bias[c];
+            o[c] = (acc[p][c].x + acc[p][c].y) + P.bias[c];
             if (P.res_f32) o[c] += P.res_f32[pix * CO + c];
         }
         if (CO == 2) *reinterpret_cast<float2*>(P.out_f32 + pix * 2) = make_float2(o[0], o[1]);
