@@ -676,10 +676,10 @@ __device__ __forceinline__ void gdn_tile_epilogue(const TcParams& P, const float
 //      against the 32-row weight tiles (rows = (tap, channel) of the tail's 3x3 kernel), D in TMEM behind the partials;
 //   3. every thread reads its share of the 32 columns and stores P (fp32) for its pixel.
 template <bool RES>
-__device__ __forceinline__ void tap_tile_epilogue(const TcParams& P, const float* __restrict__ bias_s, float* run, int b,
-                                                  int sub, int ty, int tx, int th, int tw, uint32_t colbase,
-                                                  uint32_t stgA, uint32_t tapB, uint32_t tmem_base, int quarter,
-                                                  uint32_t bar_gw, uint32_t bar_gdone, uint32_t& gphase) {
+__device__ __forceinline__ void tap_stage_issue(const TcParams& P, const float* __restrict__ bias_s, float* run, int b,
+                                                int sub, int ty, int tx, int th, int tw, uint32_t colbase,
+                                                uint32_t stgA, uint32_t tapB, uint32_t tmem_base, uint32_t bar_gw,
+                                                uint32_t bar_gdone) {
     const Epilogue& ep = P.ep;
     const int N = P.N;                                    // 64 or 128 = channels of y per pixel
     const int nseg = N >> 6;                              // 64-channel segments
@@ -762,6 +762,20 @@ __device__ __forceinline__ void tap_tile_epilogue(const TcParams& P, const float
         }
         tc_commit(bar_gdone);
     }
+    if (ep.sat_count && ep_sat_hit(satm)) atomicAdd(ep.sat_count, 1u);
+}
+
+// Second half of the fused tail epilogue, one tile later (software pipeline: the accumulators of the next tile are
+// drained while this tile's second MMA runs): wait for the MMA, read the thread's share of the 32 columns, store P.
+__device__ __forceinline__ void tap_finish(const TcParams& P, int b, int sub, int ty, int tx, int th, int tw,
+                                           uint32_t colbase, uint32_t tmem_base, int quarter, uint32_t bar_gdone,
+                                           uint32_t& gphase) {
+    const Epilogue& ep = P.ep;
+    const int N = P.N;
+    const int s0 = (int)colbase / N, cA = (int)colbase - s0 * N;
+    const int qy = ty * 16 + th, qx = (tx * P.SX + s0) * 8 + tw;
+    const int oy = qy * P.os + P.sub[sub].py, ox = qx * P.os + P.sub[sub].px;
+    const bool ok = qy < P.Hq && qx < P.Wq;
     mbar_wait(bar_gdone, gphase);
     gphase ^= 1u;
     tc_fence_after();
@@ -786,7 +800,6 @@ __device__ __forceinline__ void tap_tile_epilogue(const TcParams& P, const float
         }
     }
     tc_fence_before();
-    if (ep.sat_count && ep_sat_hit(satm)) atomicAdd(ep.sat_count, 1u);
 }
 
 // Warp roles: 0 = TMA producer (weight stream + patches), 1, 2 = MMA issuers (warp 1 owns the TMEM
@@ -1131,6 +1144,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         // this warp's staging blocks (TMA-store epilogue: STG instantiations, CT = 128 only)
         const uint32_t stg = (STG && P.tmast) ? stg0 + (uint32_t)(warp - TC_ACC_WARP0) * 4096u : 0u;
         uint32_t gphase = 0;      // phase of the fused GDN's "norm MMAs done" barrier
+        bool tap_pending = false; // fused tail: a tile whose second MMA is in flight (finished one tile later)
+        int pb_b = 0, pb_sub = 0, pb_ty = 0, pb_tx = 0;
 #ifdef FVC_TC_ACCDBG
         const bool adbg = P.dbg != nullptr && blockIdx.x == 0 && warp == TC_ACC_WARP0;
         long long a_wait = 0, a_drain = 0, a_epi = 0;
@@ -1223,8 +1238,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 gdn_tile_epilogue(P, bias_s, bias_s + 128, run, b, sub, ty, tx, th, tw, colbase, stg0, gdnB, tmem_base,
                                   quarter, bar_gw, bar_gdone, gphase);
             } else if constexpr (TAP) {
-                tap_tile_epilogue<RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg0, gdnB, tmem_base, quarter,
-                                       bar_gw, bar_gdone, gphase);
+                // software pipeline over tiles: this tile's accumulators are already drained (above) while the previous
+                // tile's second MMA was running; now finish the previous tile, then stage and issue this one
+                if (tap_pending) tap_finish(P, pb_b, pb_sub, pb_ty, pb_tx, th, tw, colbase, tmem_base, quarter, bar_gdone, gphase);
+                tap_stage_issue<RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg0, gdnB, tmem_base, bar_gw, bar_gdone);
+                tap_pending = true; pb_b = b; pb_sub = sub; pb_ty = ty; pb_tx = tx;
             } else if constexpr (!PARK) {
                 if constexpr (NCH % 2 == 0) {
                     if (P.merged) {
@@ -1298,6 +1316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #endif
         }
 
+        if (TAP && tap_pending) tap_finish(P, pb_b, pb_sub, pb_ty, pb_tx, th, tw, colbase, tmem_base, quarter, bar_gdone, gphase);
         if (STG && stg && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #ifdef FVC_TC_ACCDBG
         if (adbg && lane == 0) { P.dbg[4] = (unsigned long long)a_wait; P.dbg[5] = (unsigned long long)a_drain; P.dbg[6] = (unsigned long long)a_epi; }
