@@ -30,6 +30,9 @@ _SIGNATURES = {
     "fvc_upsample2x_bilinear": (_i, [_f, _f, _i, _i, _i, _i, C.c_float, _s]),
     "fvc_flow_warp": (_i, [_f, _f, _f, _i, _i, _i, _i, _s]),
     "fvc_conv2d": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _s]),
+    "fvc_conv_op_create": (_i, [C.POINTER(C.c_void_p), _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _s]),
+    "fvc_conv_op_run": (_i, [C.c_void_p, _f, _f, _s]),
+    "fvc_conv_op_destroy": (None, [C.c_void_p]),
     "fvc_gdn": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _s]),
     "fvc_quant_bits_factorized": (_i, [_f, C.POINTER(C.c_void_p), _f, _f, _i, _i, _i, _i, _s]),
     "fvc_quant_bits_laplace": (_i, [_f, _f, _f, _f, _l, _s]),

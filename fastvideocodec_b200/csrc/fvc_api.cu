@@ -62,72 +62,125 @@ int fvc_flow_warp(const float* img, const float* flow, float* out, int B, int C,
     return launch_flow_warp_nchw(img, flow, out, B, C, H, W, (cudaStream_t)stream);
 }
 
-int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W, int Cout,
-               int k, int stride, int transposed, int act, int impl, void* stream) {
+// One convolution with its packed weights, its engine plan and its staging tensors, kept across calls.  The plan binds
+// the input / output buffers (TMA descriptors), so the handle owns them and is specific to one input shape.
+struct fvc_conv_op {
+    ConvLayer L;
+    int B = 0, Cin = 0, H = 0, W = 0, Cout = 0, Ho = 0, Wo = 0, impl = 0, device = 0;
+    ActT in{}, via{};
+    float* out_nhwc = nullptr;
+    float* bias = nullptr;
+    TcPlan* plan = nullptr;
+    SimtWeights sw{};
+    Epilogue ep{};
+};
+
+void fvc_conv_op_destroy(fvc_conv_op* op) {
+    if (!op) return;
+    if (op->plan) tc_plan_destroy(op->plan);
+    cudaFree(op->sw.w);
+    cudaFree(op->in.p);
+    cudaFree(op->via.p);
+    cudaFree(op->out_nhwc);
+    cudaFree(op->bias);
+    delete op;
+}
+
+int fvc_conv_op_create(fvc_conv_op** out, const float* w, const float* bias, int B, int Cin, int H, int W, int Cout, int k,
+                       int stride, int transposed, int act, int impl, void* stream) {
     NEED_DEVICE();
-    FVC_ARG(x && w && bias && y);
+    FVC_ARG(out && w && bias);
     FVC_ARG(B >= 1 && Cin >= 1 && Cin <= 128 && Cout >= 1 && Cout <= 128 && (k == 1 || k == 3 || k == 5 || k == 7));
-    FVC_ARG(stride == 1 || stride == 2);
+    FVC_ARG(H >= 1 && W >= 1 && (stride == 1 || stride == 2));
     FVC_ARG(impl == FVC_IMPL_SIMT || impl == FVC_IMPL_TC || impl == FVC_IMPL_TC_FAST);
     FVC_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0) || transposed);
     cudaStream_t s = (cudaStream_t)stream;
-    ConvLayer L;
-    make_conv_layer(L, Cin, Cout, k, stride, transposed);
-    int Ho = transposed ? H * stride : H / stride, Wo = transposed ? W * stride : W / stride;
-    TmpPool tmp(s);
-    ActT in;
-    in.B = B; in.H = H; in.W = W; in.Cp = (impl != FVC_IMPL_SIMT && Cin <= 8) ? 8 : pad_c(Cin);   // narrow records for the input layers
-    in.parity = (!transposed && stride == 2) ? 1 : 0;
-    if (tmp.get(&in.p, act_bytes(B, H, W, in.Cp))) return FVC_ERR_CUDA;
-    int rc = launch_nchw_to_act(x, in, Cin, 0, s);
-    if (rc) return rc;
-    float* out_nhwc = nullptr;
-    if (tmp.get(&out_nhwc, (size_t)B * Ho * Wo * Cout * 4)) return FVC_ERR_CUDA;
-    Epilogue ep;
+    fvc_conv_op* op = new fvc_conv_op();
+    struct Guard {   // releases the half-built handle on every error return
+        fvc_conv_op* op;
+        ~Guard() { if (op) fvc_conv_op_destroy(op); }
+    } guard{op};
+    FVC_CUDA(cudaGetDevice(&op->device));
+    make_conv_layer(op->L, Cin, Cout, k, stride, transposed);
+    op->B = B; op->Cin = Cin; op->H = H; op->W = W; op->Cout = Cout; op->impl = impl;
+    op->Ho = transposed ? H * stride : H / stride;
+    op->Wo = transposed ? W * stride : W / stride;
+    op->in.B = B; op->in.H = H; op->in.W = W;
+    op->in.Cp = (impl != FVC_IMPL_SIMT && Cin <= 8) ? 8 : pad_c(Cin);   // narrow records for the input layers
+    op->in.parity = (!transposed && stride == 2) ? 1 : 0;
+    FVC_CUDA(cudaMalloc(&op->in.p, act_bytes(B, H, W, op->in.Cp)));
+    FVC_CUDA(cudaMemsetAsync(op->in.p, 0, act_bytes(B, H, W, op->in.Cp), s));   // padding channels stay zero
+    FVC_CUDA(cudaMalloc(&op->out_nhwc, (size_t)B * op->Ho * op->Wo * Cout * 4));
+    FVC_CUDA(cudaMalloc(&op->bias, (size_t)Cout * 4));
+    FVC_CUDA(cudaMemcpyAsync(op->bias, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, s));
+    Epilogue& ep = op->ep;
     memset(&ep, 0, sizeof(ep));
-    ep.bias = bias;
+    ep.bias = op->bias;
     ep.acc_scale = 1.f;
     ep.act = act;
-    ep.out_f32 = out_nhwc;
+    ep.out_f32 = op->out_nhwc;
     // test hook: FVC_CONV2D_VIA_ACT=1 (2: parity-planar) writes the result as an ACT record tensor, the way the layers
     // of the frame pipeline hand their outputs on (exercises the ACT / TMA-store epilogues), and converts it back
-    ActT via;
-    memset(&via, 0, sizeof(via));
     {
         const char* va = getenv("FVC_CONV2D_VIA_ACT");
         const int mode = va ? atoi(va) : 0;
         if (mode && impl != FVC_IMPL_SIMT) {
-            via.B = B; via.H = Ho; via.W = Wo; via.Cp = pad_c(Cout);
-            via.parity = (mode == 2 && Ho % 2 == 0 && Wo % 2 == 0 && !(transposed && stride == 2)) ? 1 : 0;
-            if (tmp.get(&via.p, act_bytes(B, Ho, Wo, via.Cp))) return FVC_ERR_CUDA;
-            FVC_CUDA(cudaMemsetAsync(via.p, 0, act_bytes(B, Ho, Wo, via.Cp), s));
+            ActT& via = op->via;
+            via.B = B; via.H = op->Ho; via.W = op->Wo; via.Cp = pad_c(Cout);
+            via.parity = (mode == 2 && op->Ho % 2 == 0 && op->Wo % 2 == 0 && !(transposed && stride == 2)) ? 1 : 0;
+            FVC_CUDA(cudaMalloc(&via.p, act_bytes(B, op->Ho, op->Wo, via.Cp)));
+            FVC_CUDA(cudaMemsetAsync(via.p, 0, act_bytes(B, op->Ho, op->Wo, via.Cp), s));
             ep.out_act = via;
             ep.out_f32 = nullptr;
         }
     }
+    int rc = 0;
     if (impl != FVC_IMPL_SIMT) {
-        if (!tc_supported(L, in.Cp)) {
+        if (!tc_supported(op->L, op->in.Cp)) {
             set_error("fvc_conv2d: shape not supported by the tcgen05 engine");
             return FVC_ERR_ARG;
         }
-        TcPlan* plan = nullptr;
-        rc = tc_plan_create(L, w, in, Ho, Wo, ep, &plan, s, impl == FVC_IMPL_TC_FAST);
-        if (rc) return rc;
-        rc = tc_plan_launch(plan, s);
-        if (rc == 0) rc = (cudaStreamSynchronize(s) == cudaSuccess) ? 0 : cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
-        tc_plan_destroy(plan);
-        if (rc) return rc;
-        if (via.p) return launch_act_to_nchw(via, Cout, y, s);
+        rc = tc_plan_create(op->L, w, op->in, op->Ho, op->Wo, ep, &op->plan, s, impl == FVC_IMPL_TC_FAST);
     } else {
-        SimtWeights sw;
-        rc = simt_pack_weights(L, w, in.Cp, std::max(pad_c(Cout), 32), &sw, s);
-        if (rc) return rc;
-        rc = launch_conv_simt(L, sw, in, Ho, Wo, ep, s);
-        cudaStreamSynchronize(s);
-        cudaFree(sw.w);
-        if (rc) return rc;
+        rc = simt_pack_weights(op->L, w, op->in.Cp, std::max(pad_c(Cout), 32), &op->sw, s);
     }
-    return launch_nhwc_to_nchw(out_nhwc, y, B, Cout, Ho, Wo, s);
+    if (rc) return rc;
+    guard.op = nullptr;
+    *out = op;
+    return 0;
+}
+
+int fvc_conv_op_run(fvc_conv_op* op, const float* x, float* y, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(op && x && y);
+    int dev = -1;
+    FVC_CUDA(cudaGetDevice(&dev));
+    if (dev != op->device) {
+        set_error("fvc_conv_op_run: the op was created on device %d, the current device is %d", op->device, dev);
+        return FVC_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = launch_nchw_to_act(x, op->in, op->Cin, 0, s);
+    if (rc) return rc;
+    if (op->plan) rc = tc_plan_launch(op->plan, s);
+    else rc = launch_conv_simt(op->L, op->sw, op->in, op->Ho, op->Wo, op->ep, s);
+    if (rc) return rc;
+    if (op->via.p) return launch_act_to_nchw(op->via, op->Cout, y, s);
+    return launch_nhwc_to_nchw(op->out_nhwc, y, op->B, op->Cout, op->Ho, op->Wo, s);
+}
+
+int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W, int Cout,
+               int k, int stride, int transposed, int act, int impl, void* stream) {
+    FVC_ARG(x && w && bias && y);
+    fvc_conv_op* op = nullptr;
+    int rc = fvc_conv_op_create(&op, w, bias, B, Cin, H, W, Cout, k, stride, transposed, act, impl, stream);
+    if (rc) return rc;
+    rc = fvc_conv_op_run(op, x, y, stream);
+    // the handle's buffers are plain allocations: wait for the work before releasing them
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess && rc == 0)
+        rc = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
+    fvc_conv_op_destroy(op);
+    return rc;
 }
 
 int fvc_gdn(const float* x, const float* beta, const float* gamma, float* y, int B, int C, int H, int W,

@@ -80,6 +80,7 @@ struct fvc_ctx {
     bool use_few = true;     // FVC_FEW=0 routes the 2-3 output-channel layers through the tensor-core engine
     bool gdn_fused = true;   // FVC_GDN_FUSED=0: (I)GDN as a separate 1x1 "norm" convolution launch (round-1 form)
     bool tail_fused = true;  // FVC_TAIL_FUSED=0: mvDecoder.deconv8 / warpnet.conv6 as their own 3x3 convolution launches
+    bool tail_fused_warpnet = true;
     float* taps_buf = nullptr;   // per-pixel partial products of a fused tail convolution, fp32 [B,H,W,<=28]
     double last_conv_seconds = -1.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
@@ -321,7 +322,7 @@ static int build_buffers(fvc_ctx* c) {
     A(c->alloc_act(&c->wc4u, H, W, 64, 0));
     A(c->alloc_act(&c->wc4u_r, H, W, 64, 0));
     A(c->alloc_act(&c->wt5, H, W, 64, 0));
-    if (!c->tail_fused) A(c->alloc_act(&c->wc5, H, W, 64, 0));   // else: stays in the SM (fused conv6)
+    if (!c->tail_fused_warpnet) A(c->alloc_act(&c->wc5, H, W, 64, 0));   // else: stays in the SM (fused conv6)
     A(c->alloc(&c->wres, (size_t)B * H * W * 3 * 4));
     A(c->alloc(&c->prediction, (size_t)B * 3 * H * W * 4));
     A(c->alloc_act(&c->residual, H, W, c->cp_narrow, 1));
@@ -364,7 +365,7 @@ static int build_buffers(fvc_ctx* c) {
     if (c->impl != FVC_IMPL_SIMT) A(c->alloc(&c->taps_buf, (size_t)B * H * W * 28 * 4));
     if (c->tail_fused) {   // geometry of the two tensors that stay in the SM (they shape never-launched plans)
         c->alias_act(&c->d[7], H, W, 128, 0, c->taps_buf);
-        c->alias_act(&c->wc5, H, W, 64, 0, c->taps_buf);
+        if (c->tail_fused_warpnet) c->alias_act(&c->wc5, H, W, 64, 0, c->taps_buf);
     }
 #undef A
     return 0;
@@ -730,7 +731,7 @@ static int run_motion_comp(fvc_ctx* c, const float* cur, const float* ref, cudaS
     PK("@k_upadd_act:half", launch_upadd_act(c->wc3, c->wc1, c->wc3u, c->wc3u_r, s));
     R(res_block(c, 4, c->wc3u_r, c->wc3u, c->wt4, c->wc4, no_act(), s));
     PK("@k_upadd_act:full", launch_upadd_act(c->wc4, c->wc0, c->wc4u, c->wc4u_r, s));
-    if (c->tail_fused) {
+    if (c->tail_fused_warpnet) {
         // ResBlock 5's conv2 (+ skip) -> conv6 (endecoder.py:294-295) in one kernel + the tap sum
         R(res_block(c, 5, c->wc4u_r, c->wc4u, c->wt5, c->wc5, no_act(), s, "warpnet.conv6"));
         ConvRt& t6 = c->conv["warpnet.conv6"];
@@ -886,8 +887,9 @@ fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl) {
 
     const char* gf0 = getenv("FVC_GDN_FUSED");
     c->gdn_fused = impl != FVC_IMPL_SIMT && !(gf0 && gf0[0] == '0');
-    const char* tf0 = getenv("FVC_TAIL_FUSED");
+    const char* tf0 = getenv("FVC_TAIL_FUSED");   // 0: off, 1 (default): mvDecoder.deconv8 and warpnet.conv6, 2: deconv8 only
     c->tail_fused = impl != FVC_IMPL_SIMT && !(tf0 && tf0[0] == '0');
+    c->tail_fused_warpnet = c->tail_fused && !(tf0 && tf0[0] == '2');
     if (build_layers(c) || build_buffers(c)) {
         fvc_ctx_destroy(c);
         return nullptr;
@@ -1256,7 +1258,7 @@ int64_t fvc_ctx_get_tensor(fvc_ctx* c, const char* name_c, float* out, int64_t c
         int rc = launch_nhwc_to_nchw(fi->second.p, out, B, fi->second.C, fi->second.h, fi->second.w, s);
         return rc ? rc : cnt;
     }
-    if (c->tail_fused && (n == "mvdec_d7" || n == "warpnet_c5")) {
+    if ((c->tail_fused && n == "mvdec_d7") || (c->tail_fused_warpnet && n == "warpnet_c5")) {
         set_error("%s is not materialised: it stays in the SM (fused tail convolution; FVC_TAIL_FUSED=0 restores it)", name_c);
         return FVC_ERR_STATE;
     }

@@ -5,7 +5,9 @@ function mirrors the reference op it replaces (same argument meaning, same resul
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
+import os
 
 import torch
 
@@ -13,7 +15,7 @@ from . import _lib
 from ._lib import (ACT_EXP, ACT_LRELU001, ACT_LRELU01, ACT_NONE, ACT_RELU, IMPL_SIMT, IMPL_TC, IMPL_TC_FAST, check, lib, ptr,
                    stream_ptr)
 
-__all__ = ["avg_pool2", "upsample2x_bilinear", "flow_warp", "conv2d", "conv_transpose2d", "gdn",
+__all__ = ["avg_pool2", "upsample2x_bilinear", "flow_warp", "conv2d", "conv_transpose2d", "conv_op_cache_clear", "gdn",
            "quant_bits_factorized", "quant_bits_laplace", "recon_losses", "eb_forward", "gaussian_forward",
            "pack_eb_params", "cdf_table_factorized", "cdf_table_laplace", "entropy_encode_factorized",
            "entropy_encode_laplace", "entropy_decode_factorized", "entropy_decode_laplace", "ACT_NONE", "ACT_RELU", "ACT_LRELU01", "ACT_LRELU001", "ACT_EXP", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_FAST"]
@@ -55,6 +57,50 @@ def flow_warp(im, flow):
     return out
 
 
+class _ConvOpCache:
+    """Handles of fvc_conv_op_* (packed weights + engine plan + staging tensors) kept across calls of conv2d /
+    conv_transpose2d, so a layer applied once per forward (entropy_models.py:160-190) packs its weights once.
+
+    An entry is keyed by the identity of the weight / bias memory and its version counter (in-place updates such as an
+    optimizer step bump it and the next call builds a new handle); the entry holds a reference to both tensors, so their
+    memory cannot be freed and handed to other tensors while the key is live."""
+
+    def __init__(self, capacity):
+        self.capacity = capacity
+        self.entries = collections.OrderedDict()
+
+    def _drop(self, entry):
+        torch.cuda.synchronize(entry["device"])        # the handle's buffers may still be in use by queued launches
+        lib().fvc_conv_op_destroy(entry["handle"])
+
+    def clear(self):
+        while self.entries:
+            self._drop(self.entries.popitem()[1])
+
+    def get(self, key, build):
+        e = self.entries.get(key)
+        if e is not None:
+            self.entries.move_to_end(key)
+            return e
+        e = build()
+        self.entries[key] = e
+        while len(self.entries) > self.capacity:
+            self._drop(self.entries.popitem(last=False)[1])
+        return e
+
+
+_conv_ops = _ConvOpCache(int(os.environ.get("FVC_CONV_OP_CACHE", "32")))
+
+
+def conv_op_cache_clear():
+    """Destroy every cached convolution handle (ops.conv2d / conv_transpose2d / torch.ops.fvc.conv2d)."""
+    _conv_ops.clear()
+
+
+def conv_op_cache_size():
+    return len(_conv_ops.entries)
+
+
 def _conv(x, weight, bias, stride, transposed, act, impl):
     x, weight = _cuda_f32(x, "x"), _cuda_f32(weight, "weight")
     B, Cin, H, W = x.shape
@@ -69,12 +115,38 @@ def _conv(x, weight, bias, stride, transposed, act, impl):
             raise ValueError("Conv2d weight must be [Cout,Cin,k,k]")
         Cout = weight.shape[0]
         Ho, Wo = H // stride, W // stride
-    if bias is None:
-        bias = torch.zeros(Cout, device=x.device, dtype=torch.float32)
-    bias = _cuda_f32(bias, "bias")
+    if bias is not None:
+        bias = _cuda_f32(bias, "bias")
     y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
-    check(lib().fvc_conv2d(ptr(x), ptr(weight), ptr(bias), ptr(y), B, Cin, H, W, Cout, k, stride, int(transposed),
-                           int(act), int(impl), stream_ptr()), "fvc_conv2d")
+    if _conv_ops.capacity <= 0:                        # FVC_CONV_OP_CACHE=0: one-shot call, nothing kept
+        b = bias if bias is not None else torch.zeros(Cout, device=x.device, dtype=torch.float32)
+        check(lib().fvc_conv2d(ptr(x), ptr(weight), ptr(b), ptr(y), B, Cin, H, W, Cout, k, stride, int(transposed),
+                               int(act), int(impl), stream_ptr()), "fvc_conv2d")
+        return y
+    try:
+        versions = (weight._version, None if bias is None else bias._version)
+    except RuntimeError:                               # inference tensors carry no version counter: do not cache
+        versions = None
+    if versions is None:
+        b = bias if bias is not None else torch.zeros(Cout, device=x.device, dtype=torch.float32)
+        check(lib().fvc_conv2d(ptr(x), ptr(weight), ptr(b), ptr(y), B, Cin, H, W, Cout, k, stride, int(transposed),
+                               int(act), int(impl), stream_ptr()), "fvc_conv2d")
+        return y
+    # the engine's planner reads FVC_* environment switches when a plan is built: they are part of the key
+    key = (x.device.index, weight.data_ptr(), None if bias is None else bias.data_ptr(), versions,
+           B, Cin, H, W, Cout, k, stride, bool(transposed), int(act), int(impl),
+           tuple(sorted(kv for kv in os.environ.items() if kv[0].startswith("FVC_"))))
+
+    def build():
+        b = bias if bias is not None else torch.zeros(Cout, device=x.device, dtype=torch.float32)
+        h = C.c_void_p()
+        check(lib().fvc_conv_op_create(C.byref(h), ptr(weight), ptr(b), B, Cin, H, W, Cout, k, stride, int(transposed),
+                                       int(act), int(impl), stream_ptr()), "fvc_conv_op_create")
+        return {"handle": h, "device": x.device, "weight": weight, "bias": bias}
+
+    with torch.cuda.device(x.device):
+        e = _conv_ops.get(key, build)
+        check(lib().fvc_conv_op_run(e["handle"], ptr(x), ptr(y), stream_ptr()), "fvc_conv_op_run")
     return y
 
 

@@ -79,6 +79,18 @@ FVC_API int fvc_flow_warp(const float* img, const float* flow, float* out, int B
 FVC_API int fvc_conv2d(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W,
                int Cout, int k, int stride, int transposed, int act, int impl, void* stream);
 
+/* The same convolution as a reusable handle, for callers that apply one layer many times (the reference's nn.Conv2d /
+ * nn.ConvTranspose2d modules outside VideoCompressor: entropy_models.py:160-190 hyper-prior stacks, one call per
+ * forward).  fvc_conv_op_create packs the weights and builds the engine plan once (the only step with a host
+ * synchronisation); fvc_conv_op_run converts x, launches and converts back, asynchronously on `stream`.  The handle
+ * copies the bias, owns its staging tensors and is specific to the input shape [B,Cin,H,W] and to the device it was
+ * created on; weights changed afterwards need a new handle.  Destroy only after the last run has finished. */
+typedef struct fvc_conv_op fvc_conv_op;
+FVC_API int fvc_conv_op_create(fvc_conv_op** out, const float* w, const float* bias, int B, int Cin, int H, int W,
+                               int Cout, int k, int stride, int transposed, int act, int impl, void* stream);
+FVC_API int fvc_conv_op_run(fvc_conv_op* op, const float* x, float* y, void* stream);
+FVC_API void fvc_conv_op_destroy(fvc_conv_op* op);
+
 /* GDN.forward — GDN.py:63-93.  beta: [C], gamma: [C,C] are the RAW parameters (the lower bounds
  * and the square-minus-pedestal reparametrisation of GDN.py:73-79 are applied inside). */
 FVC_API int fvc_gdn(const float* x, const float* beta, const float* gamma, float* y, int B, int C, int H, int W,

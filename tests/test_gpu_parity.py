@@ -976,6 +976,60 @@ def test_context_cache_is_bounded(dev, state_dict):
     m.release()
 
 
+def test_conv_op_handles_are_cached_and_follow_weight_updates(dev):
+    """ops.conv2d keeps the packed weights / plan of a layer across calls (fvc_conv_op_*): the same call twice reuses
+    one handle and returns identical bits; an in-place weight update (version bump) or a new input shape builds a new
+    handle whose result follows the new weights; the cache is bounded; the one-shot C entry point agrees bit for bit."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from fastvideocodec_b200 import ops
+    from fastvideocodec_b200._lib import check, lib, ptr, stream_ptr
+    ops.conv_op_cache_clear()
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn((1, 64, 16, 24), generator=g).to(dev)
+    w = (torch.randn((64, 64, 3, 3), generator=g) / 24.0).to(dev)
+    b = (torch.randn((64,), generator=g) * 0.1).to(dev)
+    y0 = ops.conv2d(x, w, b, 1, ops.ACT_RELU)
+    assert ops.conv_op_cache_size() == 1
+    x2 = x * 0.5
+    y1 = ops.conv2d(x2, w.detach(), b, 1, ops.ACT_RELU)           # detach(): same memory, same version -> same handle
+    assert ops.conv_op_cache_size() == 1
+    assert torch.equal(ops.conv2d(x, w, b, 1, ops.ACT_RELU), y0)
+    want1 = torch.relu(F.conv2d(x2.cpu(), w.cpu(), b.cpu(), padding=1))
+    assert (y1.cpu() - want1).abs().max().item() <= 1e-4 * max(1.0, want1.abs().max().item())
+    # the one-shot entry point (create + run + destroy): same bits
+    y_once = torch.empty_like(y0)
+    check(lib().fvc_conv2d(ptr(x), ptr(w), ptr(b), ptr(y_once), 1, 64, 16, 24, 64, 3, 1, 0, ops.ACT_RELU, ops.IMPL_TC,
+                           stream_ptr()), "fvc_conv2d")
+    assert torch.equal(y_once, y0)
+    # in-place update of the weights and of the bias: new handles, new results
+    w.mul_(-1.0)
+    y2 = ops.conv2d(x, w, b, 1, ops.ACT_RELU)
+    assert ops.conv_op_cache_size() == 2
+    want2 = torch.relu(F.conv2d(x.cpu(), w.cpu(), b.cpu(), padding=1))
+    assert (y2.cpu() - want2).abs().max().item() <= 1e-4 * max(1.0, want2.abs().max().item())
+    b.add_(1.0)
+    y3 = ops.conv2d(x, w, b, 1, ops.ACT_RELU)
+    want3 = torch.relu(F.conv2d(x.cpu(), w.cpu(), b.cpu(), padding=1))
+    assert (y3.cpu() - want3).abs().max().item() <= 1e-4 * max(1.0, want3.abs().max().item())
+    # another input shape: its own handle; the cache stays bounded
+    ops.conv2d(x[..., :16].contiguous(), w, b, 1, ops.ACT_RELU)
+    assert ops.conv_op_cache_size() == 4
+    cap = ops._conv_ops.capacity
+    try:
+        ops._conv_ops.capacity = 2
+        ops.conv2d(x[..., :8].contiguous(), w, b, 1, ops.ACT_RELU)
+        assert ops.conv_op_cache_size() == 2
+    finally:
+        ops._conv_ops.capacity = cap
+    # C ABI argument checks of the handle API
+    h = C.c_void_p()
+    assert lib().fvc_conv_op_create(C.byref(h), ptr(w), ptr(b), 1, 64, 16, 24, 64, 4, 1, 0, 0, ops.IMPL_TC, stream_ptr()) != 0
+    assert lib().fvc_conv_op_run(None, ptr(x), ptr(y0), stream_ptr()) != 0
+    ops.conv_op_cache_clear()
+    assert ops.conv_op_cache_size() == 0
+
+
 def test_subnet_module_forwards_match_oracle(model, state_dict, dev):
     """The drop-in module surface reference models.py classes call (sub-module forwards, motioncompensation,
     BitEstimator closures) against the oracle's restatement of each module, element-wise."""

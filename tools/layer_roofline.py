@@ -13,6 +13,7 @@ try:
 except Exception:
     pass
 sd = init_state_dict(0)
+COL = int(sys.argv[2]) if len(sys.argv) > 2 else 1   # which timing column of the input file
 
 
 def out_res(name):
@@ -50,7 +51,14 @@ for line in open(sys.argv[1]):
     f = line.split()
     if len(f) < 2 or f[0] in ("layer", "TOTAL"):
         continue
-    name, ms = f[0], float(f[1])
+    if f[0].startswith("@") or "#taps" in f[0]:   # frame kernels / tap sums: no MMA work
+        continue
+    try:
+        name, ms = f[0], float(f[COL])
+    except (ValueError, IndexError):
+        continue
+    if ms != ms:                              # "nan": the layer does not exist in this variant (fused away)
+        continue
     ho, wo, st, tr = out_res(name)
     if "#norm" in name:                       # GDN norm = 1x1 convolution C -> C of the squared activations
         C = sd[name.replace("#norm", "") + ".beta"].numel(); cin = cout = C; k = 1
