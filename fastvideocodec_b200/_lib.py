@@ -61,6 +61,11 @@ _SIGNATURES = {
     "fvc_entropy_decode_factorized": (_i, [C.c_void_p, _l, _l, _i, C.c_void_p, _i, _i, _f, C.c_void_p, _s]),
     "fvc_entropy_decode_laplace": (_i, [C.c_void_p, _l, _l, _f, _i, _i, _f, C.c_void_p, _s]),
     "fvc_entropy_stream_capacity": (_l, [_l, _i]),
+    "fvc_entropy_encode_indexed": (_i, [C.c_void_p, C.c_void_p, _l, C.c_void_p, _i, _i, C.c_void_p, C.c_void_p, _i,
+                                        C.c_void_p, _l, C.c_void_p, C.c_void_p, _s]),
+    "fvc_entropy_decode_indexed": (_i, [C.c_void_p, _l, _l, C.c_void_p, C.c_void_p, _i, _i, C.c_void_p, C.c_void_p, _i,
+                                        C.c_void_p, C.c_void_p, _s]),
+    "fvc_entropy_stream_capacity_indexed": (_l, [_l, _i]),
     "fvc_ctx_launch_count": (_l, [C.c_void_p]),
     "fvc_ctx_last_conv_seconds": (C.c_double, [C.c_void_p]),
     "fvc_ctx_profile_text": (C.c_char_p, [C.c_void_p]),

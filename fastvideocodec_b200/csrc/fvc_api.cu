@@ -376,6 +376,43 @@ int fvc_entropy_decode_laplace(const void* stream_in, int64_t nbytes, int64_t n,
                                       (cudaStream_t)stream);
 }
 
+int fvc_entropy_encode_indexed(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdf, int ntab,
+                               int cdf_stride, const int32_t* cdf_length, const int32_t* offset, int lane_len,
+                               void* stream_out, int64_t capacity, uint32_t* nbytes_out, uint32_t* err_out,
+                               void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(symbols && indexes && cdf && cdf_length && offset && stream_out && nbytes_out && err_out);
+    FVC_ARG(n >= 1 && ntab >= 1 && cdf_stride >= 2 && lane_len >= 1 && entropy_indexed_slot_words(lane_len) <= 65535);
+    FVC_ARG((int64_t)entropy_stream_capacity_indexed(n, lane_len) <= capacity);
+    cudaStream_t s = (cudaStream_t)stream;
+    TmpPool tmp(s);
+    uint32_t* lane_words = nullptr;
+    uint16_t* words = nullptr;
+    const int64_t nlanes = cdiv64(n, lane_len);
+    if (tmp.get(&words, (size_t)nlanes * entropy_indexed_slot_words(lane_len) * 2) || tmp.get(&lane_words, (size_t)nlanes * 4))
+        return FVC_ERR_CUDA;
+    FVC_CUDA(cudaMemsetAsync(err_out, 0, 12, s));
+    return launch_rans_encode_indexed(symbols, indexes, n, lane_len, cdf, ntab, cdf_stride, cdf_length, offset, words,
+                                      lane_words, (uint8_t*)stream_out, nbytes_out, err_out, s);
+}
+
+int fvc_entropy_decode_indexed(const void* stream_in, int64_t nbytes, int64_t n, const int32_t* indexes,
+                               const int32_t* cdf, int ntab, int cdf_stride, const int32_t* cdf_length,
+                               const int32_t* offset, int lane_len, int32_t* symbols_out, uint32_t* err_out,
+                               void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(stream_in && indexes && cdf && cdf_length && offset && symbols_out && err_out);
+    FVC_ARG(n >= 1 && ntab >= 1 && cdf_stride >= 2 && lane_len >= 1);
+    FVC_CUDA(cudaMemsetAsync(err_out, 0, 12, (cudaStream_t)stream));
+    return launch_rans_decode_indexed((const uint8_t*)stream_in, nbytes, n, lane_len, indexes, cdf, ntab, cdf_stride,
+                                      cdf_length, offset, symbols_out, err_out, (cudaStream_t)stream);
+}
+
+int64_t fvc_entropy_stream_capacity_indexed(int64_t n, int lane_len) {
+    if (n < 0 || lane_len < 1) return FVC_ERR_ARG;
+    return (int64_t)entropy_stream_capacity_indexed(n, lane_len);
+}
+
 int64_t fvc_entropy_stream_capacity(int64_t n, int lane_len) {
     if (n < 0 || lane_len < 1) return FVC_ERR_ARG;
     return (int64_t)entropy_stream_capacity(n, lane_len);

@@ -153,7 +153,7 @@ __global__ void k_rans_encode(const uint32_t* __restrict__ packed, int64_t n, in
 
 // container assembly: one block per lane (block 0 also writes the header)
 __global__ void k_rans_pack(const uint16_t* __restrict__ words, const uint32_t* __restrict__ lane_words, int64_t n,
-                            int L, uint8_t* __restrict__ out, uint32_t* __restrict__ total_bytes) {
+                            int L, int slot_words, uint8_t* __restrict__ out, uint32_t* __restrict__ total_bytes) {
     pdl_sync();
     const int nlanes = (int)((n + L - 1) / L);
     const int lane = blockIdx.x;
@@ -167,7 +167,7 @@ __global__ void k_rans_pack(const uint16_t* __restrict__ words, const uint32_t* 
     const uint32_t hdr = 16u + (((uint32_t)nlanes * 2u + 3u) & ~3u);
     uint16_t* payload = reinterpret_cast<uint16_t*>(out + hdr);
     const uint32_t nw = lane_words[lane];
-    const uint16_t* src = words + (int64_t)lane * (L + 2) + (L + 2 - nw);
+    const uint16_t* src = words + (int64_t)lane * slot_words + (slot_words - nw);
     for (uint32_t k = threadIdx.x; k < nw; k += blockDim.x) payload[off_s + k] = src[k];
     if (lane == 0) {
         uint32_t* h = reinterpret_cast<uint32_t*>(out);
@@ -263,6 +263,110 @@ __global__ void k_rans_decode_laplace(const uint8_t* __restrict__ stream, int64_
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Indexed-table coder: the model CompressAI's EntropyModel.compress / decompress hands its range coder
+// (reference entropy_models.py:80-93, 237-247 call it through entropy_bottleneck / gaussian_conditional): per element
+// an index into a set of quantised CDF tables (`_quantized_cdf` [ntab][stride], `_cdf_length`, `_offset`, written by
+// update()), symbols outside a table's range escaped through its last (tail-mass) bin followed by the raw value in
+// 4-bit bypass digits:
+//     v = symbol - offset[idx];  max = cdf_length[idx] - 2
+//     v < 0    -> raw = -2v - 1, v = max;      v >= max -> raw = 2 (v - max), v = max
+//     code v under the table; if v == max: nb = number of 4-bit digits of raw, coded as digits of 15 then the rest
+//     (while nb >= 15: 15, nb -= 15; then nb), then the nb digits of raw, least significant first.
+// Same lanes and container as above; a bypass digit d is the interval [d << 12, (d + 1) << 12).  One thread per lane.
+// err[0]: index outside [0, ntab); err[1]: empty interval (malformed table); err[2]: lane could not be opened.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rans_put(uint32_t& x, uint16_t* slot, int& w, uint32_t start, uint32_t freq) {
+    if ((uint64_t)x >= ((uint64_t)freq << 16)) {     // freq may be 2^16 (a one-symbol table): compare in 64 bits
+        slot[--w] = (uint16_t)(x & 0xffffu);
+        x >>= 16;
+    }
+    x = ((x / freq) << 16) + (x % freq) + start;
+}
+
+__global__ void k_rans_encode_indexed(const int32_t* __restrict__ symbols, const int32_t* __restrict__ indexes, int64_t n,
+                                      int L, int slot_words, const int32_t* __restrict__ cdf, int ntab, int stride,
+                                      const int32_t* __restrict__ cdf_len, const int32_t* __restrict__ offset,
+                                      uint16_t* __restrict__ words, uint32_t* __restrict__ lane_words,
+                                      unsigned int* __restrict__ err) {
+    const int64_t nlanes = (n + L - 1) / L;
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= nlanes) return;
+    const int64_t first = lane * L;
+    const int cnt = (int)min((int64_t)L, n - first);
+    uint16_t* slot = words + lane * (int64_t)slot_words;
+    int w = slot_words;
+    uint32_t x = RANS_L;
+    for (int k = cnt - 1; k >= 0; --k) {              // elements backwards, and inside an element its digits backwards
+        int idx = indexes[first + k];
+        if (idx < 0 || idx >= ntab) { atomicAdd(err, 1u); idx = 0; }
+        const int32_t* T = cdf + (size_t)idx * stride;
+        const int maxv = cdf_len[idx] - 2;
+        int v = symbols[first + k] - offset[idx];
+        uint32_t raw = 0;
+        if (v < 0) { raw = (uint32_t)(-2 * (int64_t)v - 1); v = maxv; }
+        else if (v >= maxv) { raw = (uint32_t)(2 * ((int64_t)v - maxv)); v = maxv; }
+        if (v == maxv) {
+            int nb = 0;
+            while (nb < 8 && (raw >> (nb * 4)) != 0) ++nb;
+            for (int j = nb - 1; j >= 0; --j) rans_put(x, slot, w, ((raw >> (j * 4)) & 15u) << 12, 1u << 12);
+            const int n15 = nb / 15, last = nb - 15 * n15;   // decode order: n15 digits of 15, then `last`
+            rans_put(x, slot, w, (uint32_t)last << 12, 1u << 12);
+            for (int j = 0; j < n15; ++j) rans_put(x, slot, w, 15u << 12, 1u << 12);
+        }
+        const uint32_t start = (uint32_t)T[v];
+        uint32_t freq = (uint32_t)T[v + 1] - start;
+        if ((int32_t)freq <= 0 || T[v + 1] > 65536) { atomicAdd(err + 1, 1u); freq = 1; }
+        rans_put(x, slot, w, start, freq);
+    }
+    slot[--w] = (uint16_t)(x & 0xffffu);
+    slot[--w] = (uint16_t)(x >> 16);
+    lane_words[lane] = (uint32_t)(slot_words - w);
+}
+
+__global__ void k_rans_decode_indexed(const uint8_t* __restrict__ stream, int64_t nbytes, int64_t n,
+                                      const int32_t* __restrict__ indexes, const int32_t* __restrict__ cdf, int ntab,
+                                      int stride, const int32_t* __restrict__ cdf_len, const int32_t* __restrict__ offset,
+                                      int32_t* __restrict__ symbols, unsigned int* __restrict__ err, int L) {
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= (int)((n + L - 1) / L)) return;
+    LaneReader rd;
+    int cnt = 0;
+    if (!rd.open(stream, nbytes, n, lane, L, cnt)) {
+        atomicAdd(err + 2, 1u);
+        return;
+    }
+    const int64_t first = (int64_t)lane * L;
+    for (int k = 0; k < cnt; ++k) {
+        int idx = indexes[first + k];
+        if (idx < 0 || idx >= ntab) { atomicAdd(err, 1u); idx = 0; }
+        const int32_t* T = cdf + (size_t)idx * stride;
+        const int maxv = cdf_len[idx] - 2;
+        const int32_t slot = (int32_t)(rd.x & 0xffffu);
+        int lo = 0, hi = maxv;                        // largest v with T[v] <= slot
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (T[mid] <= slot) lo = mid; else hi = mid - 1;
+        }
+        rd.advance((uint32_t)T[lo], (uint32_t)(T[lo + 1] - T[lo]));
+        int v = lo;
+        if (v == maxv) {
+            auto digit = [&]() {
+                const uint32_t d = (rd.x & 0xffffu) >> 12;
+                rd.advance(d << 12, 1u << 12);
+                return (int)d;
+            };
+            int d = digit(), nb = d;
+            while (d == 15) { d = digit(); nb += d; }
+            uint32_t raw = 0;
+            for (int j = 0; j < nb; ++j) raw |= (uint32_t)digit() << (4 * (j & 7));
+            v = (int)(raw >> 1);
+            if (raw & 1u) v = -v - 1; else v += maxv;
+        }
+        symbols[first + k] = v + offset[idx];
+    }
+}
+
 // bits = 8 * bytes, as floats, for the bpp bookkeeping (net.py:136: len(byte_stream) * 8)
 __global__ void k_bytes_to_bits(const uint32_t* __restrict__ nbytes, const unsigned int* __restrict__ err,
                                 float* __restrict__ bits) {
@@ -322,7 +426,7 @@ int launch_rans_encode(const uint32_t* packed, int64_t n, int L, uint16_t* words
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     FVC_CUDA(launch_pdl(k_rans_pack, (unsigned)nlanes, 128, 0, s, (const uint16_t*)words, (const uint32_t*)lane_words, n,
-                        L, out, total_bytes));
+                        L, L + 2, out, total_bytes));
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;
@@ -341,6 +445,42 @@ int launch_rans_decode_laplace(const uint8_t* stream, int64_t nbytes, int64_t n,
     FVC_ARG(n >= 1 && L >= 1);
     const int nl = (int)cdiv64(n, L);
     k_rans_decode_laplace<<<cdiv(nl, 32), 32, 0, s>>>(stream, nbytes, n, R, sigma, q_out, err, L);
+    g_launch_count++;
+    FVC_CHECK_LAUNCH();
+    return 0;
+}
+// indexed-table coder: 4-bit bypass digits grow the state by 4 bits each, a table symbol by at most 16: at most
+// (16 + 9 * 4) / 16 = 3.25 words per element
+int entropy_indexed_slot_words(int L) { return (13 * L + 3) / 4 + 3; }
+size_t entropy_stream_capacity_indexed(int64_t n, int L) {
+    const int64_t nlanes = cdiv64(std::max<int64_t>(n, 1), L);
+    return (size_t)(16 + ((nlanes * 2 + 3) & ~(int64_t)3) + 2 * nlanes * (int64_t)entropy_indexed_slot_words(L));
+}
+int launch_rans_encode_indexed(const int32_t* symbols, const int32_t* indexes, int64_t n, int L, const int32_t* cdf,
+                               int ntab, int stride, const int32_t* cdf_len, const int32_t* offset, uint16_t* words,
+                               uint32_t* lane_words, uint8_t* out, uint32_t* total_bytes, unsigned int* err,
+                               cudaStream_t s) {
+    FVC_ARG(n >= 1 && L >= 1 && entropy_indexed_slot_words(L) <= 65535 && ntab >= 1 && stride >= 2);
+    const int64_t nlanes = cdiv64(n, L);
+    FVC_ARG(nlanes <= 65535);
+    const int slot = entropy_indexed_slot_words(L);
+    k_rans_encode_indexed<<<(unsigned)cdiv64(nlanes, 32), 32, 0, s>>>(symbols, indexes, n, L, slot, cdf, ntab, stride,
+                                                                      cdf_len, offset, words, lane_words, err);
+    g_launch_count++;
+    FVC_CHECK_LAUNCH();
+    FVC_CUDA(launch_pdl(k_rans_pack, (unsigned)nlanes, 128, 0, s, (const uint16_t*)words, (const uint32_t*)lane_words, n,
+                        L, slot, out, total_bytes));
+    g_launch_count++;
+    FVC_CHECK_LAUNCH();
+    return 0;
+}
+int launch_rans_decode_indexed(const uint8_t* stream, int64_t nbytes, int64_t n, int L, const int32_t* indexes,
+                               const int32_t* cdf, int ntab, int stride, const int32_t* cdf_len, const int32_t* offset,
+                               int32_t* symbols, unsigned int* err, cudaStream_t s) {
+    FVC_ARG(n >= 1 && L >= 1 && ntab >= 1 && stride >= 2);
+    const int nl = (int)cdiv64(n, L);
+    k_rans_decode_indexed<<<cdiv(nl, 32), 32, 0, s>>>(stream, nbytes, n, indexes, cdf, ntab, stride, cdf_len, offset,
+                                                      symbols, err, L);
     g_launch_count++;
     FVC_CHECK_LAUNCH();
     return 0;

@@ -63,6 +63,15 @@ int bits_max_blocks();
 // R = mxrange (150): symbols s = q + R in [0, 2R-2]; tables are uint32 [C][2R] / [n][2R]; L = symbols per rANS lane
 size_t entropy_stream_capacity(int64_t n, int L);   // bytes
 size_t entropy_words_capacity(int64_t n, int L);    // 16-bit words of scratch
+int entropy_indexed_slot_words(int L);               // indexed-table coder: 16-bit words of scratch per lane
+size_t entropy_stream_capacity_indexed(int64_t n, int L);
+int launch_rans_encode_indexed(const int32_t* symbols, const int32_t* indexes, int64_t n, int L, const int32_t* cdf,
+                               int ntab, int stride, const int32_t* cdf_len, const int32_t* offset, uint16_t* words,
+                               uint32_t* lane_words, uint8_t* out, uint32_t* total_bytes, unsigned int* err,
+                               cudaStream_t s);
+int launch_rans_decode_indexed(const uint8_t* stream, int64_t nbytes, int64_t n, int L, const int32_t* indexes,
+                               const int32_t* cdf, int ntab, int stride, const int32_t* cdf_len, const int32_t* offset,
+                               int32_t* symbols, unsigned int* err, cudaStream_t s);
 int launch_cdf_table_factorized(FactorizedParams prm, int C, int R, uint32_t* table, cudaStream_t s);
 int launch_cdf_table_laplace(const float* sigma, int64_t n, int R, uint32_t* table, cudaStream_t s);
 int launch_sym_factorized(const float* x, int64_t n, int C, int R, const uint32_t* table, uint32_t* packed,

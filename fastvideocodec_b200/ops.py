@@ -18,7 +18,8 @@ from ._lib import (ACT_EXP, ACT_LRELU001, ACT_LRELU01, ACT_NONE, ACT_RELU, IMPL_
 __all__ = ["avg_pool2", "upsample2x_bilinear", "flow_warp", "conv2d", "conv_transpose2d", "conv_op_cache_clear", "gdn",
            "quant_bits_factorized", "quant_bits_laplace", "recon_losses", "eb_forward", "gaussian_forward",
            "pack_eb_params", "cdf_table_factorized", "cdf_table_laplace", "entropy_encode_factorized",
-           "entropy_encode_laplace", "entropy_decode_factorized", "entropy_decode_laplace", "ACT_NONE", "ACT_RELU", "ACT_LRELU01", "ACT_LRELU001", "ACT_EXP", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_FAST"]
+           "entropy_encode_laplace", "entropy_decode_factorized", "entropy_decode_laplace", "entropy_encode_indexed",
+           "entropy_decode_indexed", "ACT_NONE", "ACT_RELU", "ACT_LRELU01", "ACT_LRELU001", "ACT_EXP", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_FAST"]
 
 
 def _cuda_f32(t, name):
@@ -337,3 +338,57 @@ def entropy_decode_laplace(stream, sigma, mxrange=150, lane_len=8192):
     if int(err[2]):
         raise _lib.FvcError("entropy_decode_laplace: %d lanes could not be opened" % int(err[2]))
     return q
+
+
+def _cuda_i32(t, name, device=None):
+    if not torch.is_tensor(t):
+        raise TypeError("%s must be a tensor" % name)
+    if device is not None and t.device != device:
+        t = t.to(device)
+    if not t.is_cuda:
+        raise TypeError("%s must live on a CUDA device (libfvc_b200 has no CPU path)" % name)
+    return t.to(torch.int32).contiguous()
+
+
+def entropy_encode_indexed(symbols, indexes, quantized_cdf, cdf_length, offset, lane_len=8192):
+    """rANS-codes integer ``symbols`` under per-element tables ``quantized_cdf[indexes]`` with CompressAI's escape rule
+    for out-of-range values (fvc_entropy_encode_indexed; the coder behind EntropyModel.compress).  Returns bytes."""
+    sym = _cuda_i32(symbols, "symbols")
+    dev = sym.device
+    idx = _cuda_i32(indexes, "indexes", dev)
+    cdf, ln, off = _cuda_i32(quantized_cdf, "quantized_cdf", dev), _cuda_i32(cdf_length, "cdf_length", dev), _cuda_i32(offset, "offset", dev)
+    if idx.numel() != sym.numel() or cdf.dim() != 2 or ln.numel() != cdf.shape[0] or off.numel() != cdf.shape[0]:
+        raise ValueError("indexes must match symbols; quantized_cdf [ntab, stride] with one cdf_length / offset per table")
+    n = sym.numel()
+    cap = lib().fvc_entropy_stream_capacity_indexed(n, lane_len)
+    buf = torch.empty(cap, device=dev, dtype=torch.uint8)
+    nbytes = torch.zeros(1, device=dev, dtype=torch.int32)
+    err = torch.zeros(3, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        check(lib().fvc_entropy_encode_indexed(ptr(sym), ptr(idx), n, ptr(cdf), cdf.shape[0], cdf.shape[1], ptr(ln), ptr(off),
+                                               int(lane_len), ptr(buf), cap, ptr(nbytes), ptr(err), stream_ptr()),
+              "fvc_entropy_encode_indexed")
+    e = err.cpu().tolist()
+    if e[0] or e[1]:
+        raise _lib.FvcError("entropy_encode_indexed: %d indexes outside the table set, %d empty intervals (run update())"
+                            % (e[0], e[1]))
+    return bytes(buf[:int(nbytes.item())].cpu().numpy().tobytes())
+
+
+def entropy_decode_indexed(stream, indexes, quantized_cdf, cdf_length, offset, lane_len=8192):
+    """Inverse of entropy_encode_indexed: int32 symbols with the shape of ``indexes``."""
+    idx = _cuda_i32(indexes, "indexes")
+    dev = idx.device
+    cdf, ln, off = _cuda_i32(quantized_cdf, "quantized_cdf", dev), _cuda_i32(cdf_length, "cdf_length", dev), _cuda_i32(offset, "offset", dev)
+    st = _stream_tensor(stream, dev)
+    out = torch.empty(idx.shape, device=dev, dtype=torch.int32)
+    err = torch.zeros(3, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        check(lib().fvc_entropy_decode_indexed(ptr(st), len(stream), idx.numel(), ptr(idx), ptr(cdf), cdf.shape[0],
+                                               cdf.shape[1], ptr(ln), ptr(off), int(lane_len), ptr(out), ptr(err),
+                                               stream_ptr()), "fvc_entropy_decode_indexed")
+    e = err.cpu().tolist()
+    if e[0] or e[2]:
+        raise _lib.FvcError("entropy_decode_indexed: %d indexes outside the table set, %d lanes could not be opened"
+                            % (e[0], e[2]))
+    return out

@@ -149,6 +149,24 @@ FVC_API int fvc_entropy_decode_laplace(const void* stream_in, int64_t nbytes, in
                                        int lane_len, float* q_out, uint32_t* err_out, void* stream);
 FVC_API int64_t fvc_entropy_stream_capacity(int64_t n, int lane_len);
 
+/* Indexed-table coder: the model CompressAI's EntropyModel.compress / decompress codes under, which the reference's
+ * RecProbModel / MeanScaleHyperPriors call (entropy_models.py:80-93, 237-247 -> entropy_bottleneck.compress,
+ * gaussian_conditional.compress(x, indexes, means)).  CompressAI is an un-vendored dependency: its published
+ * encode_with_indexes rule is restated (parity unpinned): element i uses table indexes[i] of cdf [ntab][cdf_stride]
+ * (int32, 16-bit precision, cdf_length[t] valid entries, last bin = tail mass), v = symbols[i] - offset[t]; values outside
+ * [0, cdf_length[t] - 2) are escaped through the last bin followed by the raw value in 4-bit bypass digits.  Coder and
+ * container as above (rANS lanes, "FVR1"); symbols in the caller's order.  All pointers are device memory.
+ * err_out: device uint32[3] = indexes outside [0, ntab), empty intervals (malformed table), unreadable lanes. */
+FVC_API int fvc_entropy_encode_indexed(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdf,
+                                       int ntab, int cdf_stride, const int32_t* cdf_length, const int32_t* offset,
+                                       int lane_len, void* stream_out, int64_t capacity, uint32_t* nbytes_out,
+                                       uint32_t* err_out, void* stream);
+FVC_API int fvc_entropy_decode_indexed(const void* stream_in, int64_t nbytes, int64_t n, const int32_t* indexes,
+                                       const int32_t* cdf, int ntab, int cdf_stride, const int32_t* cdf_length,
+                                       const int32_t* offset, int lane_len, int32_t* symbols_out, uint32_t* err_out,
+                                       void* stream);
+FVC_API int64_t fvc_entropy_stream_capacity_indexed(int64_t n, int lane_len);
+
 /* ---------------------------------------------------------------------------------------------
  * Whole-path context: VideoCompressor.forward — net.py:70-220.
  * ------------------------------------------------------------------------------------------- */

@@ -150,3 +150,188 @@ def test_codec_round_trip_and_real_bits(dev, state_dict, size):
     with pytest.raises(_lib.FvcError):
         m.decompress(bad, fr[0])
     m.release()
+
+
+# ------------------------------------------------------------------------------------------------
+# the indexed-table coder and the CompressAI-side compress / decompress of entropy_models.py
+# (parity UNPINNED against CompressAI itself; checked against the oracle's restatement, oracle/compressai_oracle.py)
+# ------------------------------------------------------------------------------------------------
+def _scale_table(n=16, hi=64.0):
+    return np.exp(np.linspace(np.log(0.11), np.log(hi), n))
+
+
+@pytest.mark.parametrize("n,lane", [(1, 8192), (63, 16), (3000, 64), (20000, 8192)])
+def test_indexed_coder_byte_exact_and_round_trip(dev, n, lane):
+    from fastvideocodec_b200 import ops
+    from oracle import compressai_oracle as CA
+    st = _scale_table()
+    cdf, ln, off = CA.gaussian_tables(st)
+    rng = np.random.default_rng(100 + n)
+    idx = rng.integers(0, len(st), n)
+    sym = np.rint(rng.standard_normal(n) * st[idx]).astype(np.int64)
+    esc = rng.random(n) < 0.03                            # escapes: both signs, 1..8 bypass digits
+    sym[esc] = (rng.integers(1, 1 << 30, esc.sum()) * rng.choice([-1, 1], esc.sum())) >> rng.integers(0, 28, esc.sum())
+    if n >= 4:
+        sym[:4] = [off[idx[0]] - 1, off[idx[1]] + ln[idx[1]] - 2, off[idx[2]] + ln[idx[2]] - 3, off[idx[3]]]
+    t = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    got = ops.entropy_encode_indexed(t(sym), t(idx), t(cdf), t(ln), t(off), lane)
+    want = CA.encode_indexed(sym, idx, cdf, ln, off, lane)
+    assert got == want
+    back = ops.entropy_decode_indexed(got, t(idx), t(cdf), t(ln), t(off), lane)
+    assert back.dtype == torch.int32 and np.array_equal(back.cpu().numpy(), sym)
+    # a one-symbol table (freq = 2^16) codes for free and round-trips
+    cdf1 = np.asarray([[0, 65536, 0], [0, 40000, 65536]], dtype=np.int32)
+    ln1, off1 = np.asarray([2, 3], dtype=np.int32), np.asarray([0, 0], dtype=np.int32)
+    s1 = np.zeros(n, dtype=np.int64)
+    i1 = (np.arange(n) % 2).astype(np.int64)
+    g1 = ops.entropy_encode_indexed(t(s1), t(i1), t(cdf1), t(ln1), t(off1), lane)
+    assert g1 == CA.encode_indexed(s1, i1, cdf1, ln1, off1, lane)
+    assert np.array_equal(ops.entropy_decode_indexed(g1, t(i1), t(cdf1), t(ln1), t(off1), lane).cpu().numpy(), s1)
+
+
+def test_indexed_coder_errors(dev):
+    from fastvideocodec_b200 import ops
+    from fastvideocodec_b200._lib import FvcError
+    from oracle import compressai_oracle as CA
+    cdf, ln, off = CA.gaussian_tables(_scale_table(4, 8.0))
+    t = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    sym, idx = np.zeros(10, dtype=np.int64), np.zeros(10, dtype=np.int64)
+    bad = idx.copy()
+    bad[3] = 4
+    with pytest.raises(FvcError):                                  # index outside the table set
+        ops.entropy_encode_indexed(t(sym), t(bad), t(cdf), t(ln), t(off))
+    broken = cdf.copy()
+    broken[3, 5] = broken[3, 4]                                    # empty interval in the widest table
+    s2 = sym.copy()
+    s2[0] = off[3] + 4
+    with pytest.raises(FvcError):
+        ops.entropy_encode_indexed(t(s2), t(idx + 3), t(broken), t(ln), t(off))
+    good = ops.entropy_encode_indexed(t(sym), t(idx), t(cdf), t(ln), t(off))
+    with pytest.raises(FvcError):                                  # truncated container
+        ops.entropy_decode_indexed(good[:12], t(idx), t(cdf), t(ln), t(off))
+    with pytest.raises(FvcError):                                  # wrong element count
+        ops.entropy_decode_indexed(good, t(idx[:5]), t(cdf), t(ln), t(off))
+    with pytest.raises(ValueError):
+        ops.entropy_encode_indexed(t(sym), t(idx[:5]), t(cdf), t(ln), t(off))
+
+
+def _trained_like(eb, g):
+    C = eb.channels
+    with torch.no_grad():
+        for name, p in eb.named_parameters():
+            if "_matrix" in name or "_factor" in name:
+                p.add_(torch.randn(p.shape, generator=g) * 0.3)
+        med = torch.randn(C, generator=g) * 0.7
+        eb.quantiles[:, 0, 0] = med - 3.0 - torch.rand(C, generator=g) * 9
+        eb.quantiles[:, 0, 1] = med
+        eb.quantiles[:, 0, 2] = med + 3.0 + torch.rand(C, generator=g) * 14
+
+
+def test_recprob_update_compress_decompress(dev):
+    """RecProbModel.update / compress / decompress / get_actual_bits (entropy_models.py:43-48, 70-72, 80-94), factorized
+    branch and conditional-Gaussian branch (RPM outputs supplied by a stub network)."""
+    from fastvideocodec_b200.entropy_models import RecProbModel
+    from oracle import compressai_oracle as CA
+    g = torch.Generator().manual_seed(31)
+    C = 32
+
+    def rpm(prior_latent, hidden):
+        return prior_latent * 0.05 - 1.0, prior_latent * 0.9, hidden + 1
+
+    m = RecProbModel(C, rpm=rpm)
+    _trained_like(m.entropy_bottleneck, g)
+    with pytest.raises(ValueError):
+        m.entropy_bottleneck.compress(torch.zeros((1, C, 2, 2), device=dev))     # update() not run
+    m = m.to(dev).eval()
+    assert m.update(force=True) is True and m.update() is False
+    x = (torch.randn((2, C, 9, 14), generator=g) * 3).to(dev)
+    x[0, 0, 0, :4] = torch.tensor([500.0, -700.0, 40.0, -40.0])                  # escapes
+    m.set_RPM(False)
+    hidden = torch.zeros(1)
+    with torch.no_grad():
+        xh, lik, _, prior = m(x, hidden, training=False)
+        strings = m.compress(x)
+        assert isinstance(strings, list) and len(strings) == 2 and all(isinstance(s, bytes) for s in strings)
+        back = m.decompress(strings, x.shape[-2:])
+    assert torch.equal(back, xh)
+    # byte-exact against the oracle coder on the tables the module built (NCHW order, one string per batch element)
+    eb = m.entropy_bottleneck
+    cdf, ln, off = eb._quantized_cdf.cpu().numpy(), eb._cdf_length.cpu().numpy(), eb._offset.cpu().numpy()
+    med = eb.quantiles[:, 0, 1].detach().view(1, C, 1, 1)
+    sym = torch.round(x - med).long().cpu().numpy()
+    idx = np.broadcast_to(np.arange(C).reshape(1, C, 1, 1), sym.shape)
+    for b in range(2):
+        assert strings[b] == CA.encode_indexed(sym[b].reshape(-1), idx[b].reshape(-1), cdf, ln, off, eb.lane_len)
+    bits = float(m.get_actual_bits(strings))
+    assert bits == 8 * sum(len(s) for s in strings)
+    ideal = sum(CA.ideal_bits(sym[b].reshape(-1), idx[b].reshape(-1), cdf, ln, off) for b in range(2))
+    assert ideal <= bits <= ideal + 2 * (34 + 8 * 24)
+    # the table model is the likelihood model: actual bits track the (unclamped) estimate outside the escapes
+    est = float(-torch.log2(lik).sum())
+    assert abs(bits - est) <= 0.05 * est + 2000
+    # conditional-Gaussian branch
+    m.set_RPM(True)
+    with torch.no_grad():
+        xh, lik, hid, _ = m(x, hidden, training=False, prior_latent=prior)
+        strings = m.compress(x)
+        back = m.decompress(strings, x.shape[-2:])
+        assert torch.equal(back, xh)
+        x2, s2, h2, p2 = m.compress_slow(x, hidden, prior)
+        assert s2 == strings and torch.equal(x2, xh) and torch.equal(p2, torch.round(xh))
+        x3, h3, p3 = m.decompress_slow(s2, x.shape[-2:], hidden, prior)
+        assert torch.equal(x3, xh) and torch.equal(p3, p2) and m.enc_t > 0 and m.dec_t > 0
+    gc = m.gaussian_conditional
+    idx = CA.build_indexes(m.sigma.cpu(), gc.scale_table.cpu()).numpy()
+    sym = torch.round(x - m.mu).long().cpu().numpy()
+    cdf, ln, off = gc._quantized_cdf.cpu().numpy(), gc._cdf_length.cpu().numpy(), gc._offset.cpu().numpy()
+    assert strings[1] == CA.encode_indexed(sym[1].reshape(-1), idx[1].reshape(-1), cdf, ln, off, gc.lane_len)
+    # state_dict round trip keeps the tables (CompressAI layout)
+    from fastvideocodec_b200.entropy_models import RecProbModel as R2
+    m2 = R2(C, rpm=rpm)
+    m2.load_state_dict(m.state_dict())
+    assert torch.equal(m2.entropy_bottleneck._quantized_cdf, eb._quantized_cdf.cpu())
+    assert m2.update() is False                                   # tables came with the checkpoint
+
+
+@pytest.mark.parametrize("trick", [True, False])
+def test_meanscale_compress_decompress(dev, trick):
+    """MeanScaleHyperPriors.update / compress / decompress / compress_slow / decompress_slow / get_actual_bits
+    (entropy_models.py:194-197, 221-226, 237-324)."""
+    from fastvideocodec_b200.entropy_models import MeanScaleHyperPriors
+    g = torch.Generator().manual_seed(41)
+    C = 64
+    m = MeanScaleHyperPriors(C, entropy_trick=trick)
+    _trained_like(m.entropy_bottleneck, g)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.startswith("h_"):
+                p.copy_(torch.randn(p.shape, generator=g) * (0.04 if p.dim() == 4 else 0.1))
+    m = m.to(dev).eval()
+    assert m.update(force=True)
+    x = (torch.randn((2, C, 16, 24), generator=g) * 3).to(dev)
+    with torch.no_grad():
+        xh, (xl, zl) = m(x, training=False)
+        strings = m.compress(x)
+        assert len(strings) == 2 and len(strings[0]) == 2 and len(strings[1]) == 2
+        assert torch.equal(m.decompress(strings, x.shape[-2:]), xh)
+        bits = m.get_actual_bits(strings)
+        assert bits.shape == (2,) and bits.tolist() == [8.0 * (len(strings[0][b]) + len(strings[1][b])) for b in range(2)]
+        # code length against the ideal -log2 sum of the intervals actually coded (x under the Gaussian tables picked by
+        # build_indexes, escapes included; the random hyper-networks here make the model a poor fit, which is fine)
+        from oracle import compressai_oracle as CA
+        gc = m.gaussian_conditional
+        cdf, ln, off = gc._quantized_cdf.cpu().numpy(), gc._cdf_length.cpu().numpy(), gc._offset.cpu().numpy()
+        idx = CA.build_indexes(m.sigma.cpu(), gc.scale_table.cpu()).numpy()
+        sym = torch.round(x - m.mu).long().cpu().numpy()
+        for b in range(2):
+            ideal = CA.ideal_bits(sym[b].reshape(-1), idx[b].reshape(-1), cdf, ln, off)
+            nl = -(-sym[b].size // gc.lane_len)
+            assert ideal <= 8 * len(strings[0][b]) <= ideal + 34 * nl + 8 * (20 + 2 * nl) + 16 * nl
+            assert strings[0][b] == CA.encode_indexed(sym[b].reshape(-1), idx[b].reshape(-1), cdf, ln, off, gc.lane_len)
+        # the slow path recomputes everything from x on the encoder and from the strings alone on the decoder
+        x_hat, s, z_size = m.compress_slow(x, decode=True)
+        assert len(s[0]) == (1 if trick else 2) and tuple(z_size) == ((2, 16, 24) if trick else (16, 24))
+        back = m.decompress_slow(s, z_size)
+        assert back.shape == x.shape and torch.equal(back, x_hat)
+        assert (x_hat - xh).abs().max().item() <= 1e-3              # same model as the fast path
+        assert m.enc_t > 0 and m.dec_t > 0
