@@ -103,6 +103,8 @@ def conv_op_cache_size():
 
 
 def _conv(x, weight, bias, stride, transposed, act, impl):
+    # a non-contiguous weight / bias is copied per call: its memory identity means nothing, so it is never cached
+    cacheable = torch.is_tensor(weight) and weight.is_contiguous() and (bias is None or (torch.is_tensor(bias) and bias.is_contiguous()))
     x, weight = _cuda_f32(x, "x"), _cuda_f32(weight, "weight")
     B, Cin, H, W = x.shape
     k = weight.shape[-1]
@@ -119,7 +121,7 @@ def _conv(x, weight, bias, stride, transposed, act, impl):
     if bias is not None:
         bias = _cuda_f32(bias, "bias")
     y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
-    if _conv_ops.capacity <= 0:                        # FVC_CONV_OP_CACHE=0: one-shot call, nothing kept
+    if _conv_ops.capacity <= 0 or not cacheable:       # FVC_CONV_OP_CACHE=0: one-shot call, nothing kept
         b = bias if bias is not None else torch.zeros(Cout, device=x.device, dtype=torch.float32)
         check(lib().fvc_conv2d(ptr(x), ptr(weight), ptr(b), ptr(y), B, Cin, H, W, Cout, k, stride, int(transposed),
                                int(act), int(impl), stream_ptr()), "fvc_conv2d")
