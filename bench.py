@@ -354,6 +354,24 @@ def run_ours(args, rank, world, local_rank):
     h2d = GOP * BATCH * 3 * H * W * 4
     d2h = (GOP - 1) * 7 * 4
 
+    # the same call fed with the frames as the reference's loader holds them before ToTensor (uint8 HWC, dataset.py:68-75):
+    # a quarter of the upload, ToTensor on the device (extra information; `e2e` above stays the float32 contract)
+    u8_gops = [(g * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 1, 3, 4, 2).contiguous().pin_memory()
+               for g in host_gops[:max(1, min(n_local, args.steps))]]
+    model.gop_forward_host(u8_gops[0], want_recon=False)
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for s in range(args.steps):
+        model.gop_forward_host(u8_gops[s % len(u8_gops)], want_recon=False)
+    e5.record()
+    barrier()
+    t3 = torch.tensor([e4.elapsed_time(e5)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    e2e_u8 = {"value": frames_total / (float(t3) * 1e-3), "unit": "P-frames/s", "h2d_bytes_per_step": GOP * BATCH * 3 * H * W,
+              "d2h_bytes_per_step": d2h, "input": "uint8 [G,B,H,W,3] host frames, ToTensor on the device (fvc_gop_forward_host_u8)"}
+
     # ---- statistics: the one collective of the path ---------------------------------------------
     stats = summarize(reduce_stats(stats_vector(torch.cat(rows, 0))))
 
@@ -433,6 +451,7 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": "P-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "d2h_what": "the 7 scalars per P-frame only (eval.py reads metrics, not frames; "
                                     "models.py:376-383)"},
+                "e2e_u8_ingest": e2e_u8,
                 "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_base,
                 "parity": parity, "parity_stats": stats, "fast_mode": fast}

@@ -56,6 +56,12 @@ int fvc_upsample2x_bilinear(const float* x, float* y, int planes, int H, int W, 
     return launch_upsample2x_planar(x, y, planes, H, W, align_corners, scale, (cudaStream_t)stream);
 }
 
+int fvc_u8hwc_to_f32chw(const uint8_t* src, float* dst, int n, int H, int W, void* stream) {
+    NEED_DEVICE();
+    FVC_ARG(src && dst && n >= 0 && H >= 0 && W >= 0);
+    return launch_u8hwc_to_f32chw(src, dst, n, H, W, (cudaStream_t)stream);
+}
+
 int fvc_flow_warp(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream) {
     NEED_DEVICE();
     FVC_ARG(img && flow && out && B >= 0 && C >= 0 && H >= 2 && W >= 2);

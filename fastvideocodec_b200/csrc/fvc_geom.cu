@@ -70,6 +70,57 @@ __device__ __forceinline__ float warp_sample(const float* __restrict__ plane, in
 }
 
 // ----------------------------------------------------------------------------------------------
+// transforms.ToTensor() of the reference's frame ingest (dataset.py:75; models.py:425) on the device:
+// uint8 HWC [n,H,W,3] -> fp32 CHW [n,3,H,W], x / 255 (IEEE division: bit-identical to torchvision's .div(255)).
+// A thread converts 4 pixels = 12 bytes (three 32-bit loads) and writes one float4 per plane; the tail is scalar.
+// ----------------------------------------------------------------------------------------------
+__global__ void k_u8hwc_to_f32chw(const uint8_t* __restrict__ src, float* __restrict__ dst, int n, int64_t hw) {
+    pdl_sync();
+    const int64_t quads = hw >> 2;
+    const int img = blockIdx.y;
+    const uint8_t* s = src + (size_t)img * hw * 3;
+    float* d = dst + (size_t)img * hw * 3;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(s) & 3) == 0) && ((reinterpret_cast<uintptr_t>(d) & 15) == 0) && ((hw & 3) == 0);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+        uint8_t b[12];
+        if (aligned) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(s + q * 12);
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                b[k] = (uint8_t)(w0 >> (8 * k));
+                b[4 + k] = (uint8_t)(w1 >> (8 * k));
+                b[8 + k] = (uint8_t)(w2 >> (8 * k));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) b[k] = s[q * 12 + k];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 v = make_float4(b[c] / 255.0f, b[3 + c] / 255.0f, b[6 + c] / 255.0f, b[9 + c] / 255.0f);
+            if (aligned) *reinterpret_cast<float4*>(d + (size_t)c * hw + q * 4) = v;
+            else { float* o = d + (size_t)c * hw + q * 4; o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (hw & 3)) {          // up to 3 trailing pixels
+        const int64_t px = quads * 4 + threadIdx.x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[(size_t)c * hw + px] = s[px * 3 + c] / 255.0f;
+    }
+}
+int launch_u8hwc_to_f32chw(const uint8_t* src, float* dst, int n, int H, int W, cudaStream_t s) {
+    FVC_ARG(n >= 0 && n <= 65535 && H >= 0 && W >= 0);
+    const int64_t hw = (int64_t)H * W;
+    if (n == 0 || hw == 0) return 0;
+    dim3 grid((unsigned)std::min<int64_t>(std::max<int64_t>(cdiv64(hw >> 2, 256), 1), 148 * 8), (unsigned)n);
+    FVC_CUDA(launch_pdl(k_u8hwc_to_f32chw, grid, 256, 0, s, src, dst, n, hw));
+    g_launch_count++;
+    FVC_CHECK_LAUNCH();
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // avg_pool2d(2,2) on planar fp32
 // ----------------------------------------------------------------------------------------------
 __global__ void k_avg_pool2_planar(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W) {

@@ -6,6 +6,7 @@ namespace fvc {
 
 // ---- geometry / elementwise (fvc_geom.cu) ----------------------------------------------------
 int launch_avg_pool2_planar(const float* x, float* y, int planes, int H, int W, cudaStream_t s);
+int launch_u8hwc_to_f32chw(const uint8_t* src, float* dst, int n, int H, int W, cudaStream_t s);
 int launch_upsample2x_planar(const float* x, float* y, int planes, int H, int W, int align_corners, float scale,
                              cudaStream_t s);
 int launch_flow_warp_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W,

@@ -125,7 +125,8 @@ struct fvc_ctx {
     cudaStream_t copy_stream = nullptr;              // H2D of the GOP's frames, overlapped with the computation
     cudaEvent_t copy_fence = nullptr;
     std::vector<cudaEvent_t> copy_events;
-    int stage_G = 0;
+    int stage_G = 0, stage_G_u8 = 0;
+    uint8_t* stage_u8 = nullptr;          // fvc_gop_forward_host_u8: the uploaded uint8 HWC frames
     float* stage_frames = nullptr;
     float* stage_scalars = nullptr;
     // teacher forcing (tests / inspection): device fp32 NCHW tensors that replace the quantised latents
@@ -911,6 +912,7 @@ void fvc_ctx_destroy(fvc_ctx* c) {
         cudaEventDestroy(ev.second);
     }
     if (c->stage_frames) cudaFree(c->stage_frames);
+    if (c->stage_u8) cudaFree(c->stage_u8);
     if (c->stage_rec) cudaFree(c->stage_rec);
     if (c->stage_scalars) cudaFree(c->stage_scalars);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
@@ -1281,11 +1283,18 @@ int64_t fvc_ctx_get_tensor(fvc_ctx* c, const char* name_c, float* out, int64_t c
     return FVC_ERR_ARG;
 }
 
-int fvc_gop_forward_host(fvc_ctx* c, const float* frames_host, int G, float* recon_host, float* scalars_host,
-                         void* stream) {
-    FVC_ARG(c && frames_host && scalars_host && G >= 2);
+static int gop_forward_host_impl(fvc_ctx* c, const void* frames_host_any, bool u8, int G, float* recon_host,
+                                 float* scalars_host, void* stream) {
+    FVC_ARG(c && frames_host_any && scalars_host && G >= 2);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t fsz = (size_t)c->B * 3 * c->H * c->W;
+    const float* frames_host = u8 ? nullptr : static_cast<const float*>(frames_host_any);
+    const uint8_t* frames_u8 = u8 ? static_cast<const uint8_t*>(frames_host_any) : nullptr;
+    if (u8 && c->stage_G_u8 < G) {
+        if (c->stage_u8) cudaFree(c->stage_u8);
+        FVC_CUDA(cudaMalloc(&c->stage_u8, fsz * G));
+        c->stage_G_u8 = G;
+    }
     if (c->stage_G < G) {
         if (c->stage_frames) cudaFree(c->stage_frames);
         if (c->stage_rec) cudaFree(c->stage_rec);
@@ -1310,8 +1319,17 @@ int fvc_gop_forward_host(fvc_ctx* c, const float* frames_host, int G, float* rec
     FVC_CUDA(cudaEventRecord(c->copy_fence, s));
     FVC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_fence, 0));
     for (int i = 0; i < G; ++i) {
-        FVC_CUDA(cudaMemcpyAsync(c->stage_frames + (size_t)i * fsz, frames_host + (size_t)i * fsz, fsz * 4,
-                                 cudaMemcpyHostToDevice, c->copy_stream));
+        if (u8) {
+            // 1 byte per sample over PCIe; ToTensor (HWC -> CHW, / 255) on the device, on the copy stream as well
+            FVC_CUDA(cudaMemcpyAsync(c->stage_u8 + (size_t)i * fsz, frames_u8 + (size_t)i * fsz, fsz, cudaMemcpyHostToDevice,
+                                     c->copy_stream));
+            int rc = launch_u8hwc_to_f32chw(c->stage_u8 + (size_t)i * fsz, c->stage_frames + (size_t)i * fsz, c->B, c->H, c->W,
+                                            c->copy_stream);
+            if (rc) return rc;
+        } else {
+            FVC_CUDA(cudaMemcpyAsync(c->stage_frames + (size_t)i * fsz, frames_host + (size_t)i * fsz, fsz * 4,
+                                     cudaMemcpyHostToDevice, c->copy_stream));
+        }
         FVC_CUDA(cudaEventRecord(c->copy_events[i], c->copy_stream));
     }
     FVC_CUDA(cudaStreamWaitEvent(s, c->copy_events[0], 0));
@@ -1336,6 +1354,16 @@ int fvc_gop_forward_host(fvc_ctx* c, const float* frames_host, int G, float* rec
         return FVC_ERR_STATE;
     }
     return 0;
+}
+
+int fvc_gop_forward_host(fvc_ctx* c, const float* frames_host, int G, float* recon_host, float* scalars_host,
+                         void* stream) {
+    return gop_forward_host_impl(c, frames_host, false, G, recon_host, scalars_host, stream);
+}
+
+int fvc_gop_forward_host_u8(fvc_ctx* c, const uint8_t* frames_host_u8, int G, float* recon_host, float* scalars_host,
+                            void* stream) {
+    return gop_forward_host_impl(c, frames_host_u8, true, G, recon_host, scalars_host, stream);
 }
 
 }  // extern "C"

@@ -210,15 +210,21 @@ class VideoCompressor(nn.Module):
         return out
 
     def gop_forward_host(self, frames_host, want_recon=True):
-        """Closed-loop GOP from HOST frames [G,B,3,H,W] through fvc_gop_forward_host (models.py:368-383).
+        """Closed-loop GOP from HOST frames through fvc_gop_forward_host (models.py:368-383).
 
+        ``frames_host``: float32 [G,B,3,H,W] in [0,1] (what ``transforms.ToTensor()`` returns, dataset.py:75), or uint8
+        [G,B,H,W,3] (the decoded images before ToTensor: a quarter of the upload, converted on the device).
         Returns (recon_host [G-1,B,3,H,W] or None, scalars_host [G-1,7]).  H2D/D2H copies inside.
         """
-        if not (torch.is_tensor(frames_host) and frames_host.device.type == "cpu" and frames_host.dtype == torch.float32
-                and frames_host.dim() == 5 and frames_host.shape[2] == 3 and frames_host.is_contiguous()):
-            raise TypeError("frames_host must be a contiguous CPU float32 [G,B,3,H,W] tensor (pinned memory "
-                            "recommended: pageable memory makes the upload synchronous)")
-        G, B, _, H, W = frames_host.shape
+        ok = torch.is_tensor(frames_host) and frames_host.device.type == "cpu" and frames_host.dim() == 5 and frames_host.is_contiguous()
+        u8 = ok and frames_host.dtype == torch.uint8 and frames_host.shape[4] == 3
+        if not (u8 or (ok and frames_host.dtype == torch.float32 and frames_host.shape[2] == 3)):
+            raise TypeError("frames_host must be a contiguous CPU float32 [G,B,3,H,W] or uint8 [G,B,H,W,3] tensor (pinned "
+                            "memory recommended: pageable memory makes the upload synchronous)")
+        if u8:
+            G, B, H, W, _ = frames_host.shape
+        else:
+            G, B, _, H, W = frames_host.shape
         if G < 2:
             raise ValueError("a GOP needs the I-frame and at least one P-frame (G >= 2)")
         if H % 64 or W % 64:
@@ -230,9 +236,10 @@ class VideoCompressor(nn.Module):
             ctx = self._context(B, H, W, dev)
             rec = torch.empty((G - 1, B, 3, H, W), dtype=torch.float32, pin_memory=True) if want_recon else None
             sc = torch.empty((G - 1, 7), dtype=torch.float32, pin_memory=True)
-            check(lib().fvc_gop_forward_host(ctx.handle, C.c_void_p(frames_host.data_ptr()), G,
-                                             C.c_void_p(rec.data_ptr()) if want_recon else C.c_void_p(0),
-                                             C.c_void_p(sc.data_ptr()), stream_ptr()), "fvc_gop_forward_host")
+            fn = lib().fvc_gop_forward_host_u8 if u8 else lib().fvc_gop_forward_host
+            check(fn(ctx.handle, C.c_void_p(frames_host.data_ptr()), G,
+                     C.c_void_p(rec.data_ptr()) if want_recon else C.c_void_p(0),
+                     C.c_void_p(sc.data_ptr()), stream_ptr()), "fvc_gop_forward_host")
         self._last_ctx = ctx
         return rec, sc
 

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (ACT_EXP, ACT_LRELU001, ACT_LRELU01, ACT_NONE, ACT_RELU, IMPL_SIMT, IMPL_TC, IMPL_TC_FAST, check, lib, ptr,
                    stream_ptr)
 
-__all__ = ["avg_pool2", "upsample2x_bilinear", "flow_warp", "conv2d", "conv_transpose2d", "conv_op_cache_clear", "gdn",
+__all__ = ["avg_pool2", "upsample2x_bilinear", "to_tensor_u8", "flow_warp", "conv2d", "conv_transpose2d", "conv_op_cache_clear", "gdn",
            "quant_bits_factorized", "quant_bits_laplace", "recon_losses", "eb_forward", "gaussian_forward",
            "pack_eb_params", "cdf_table_factorized", "cdf_table_laplace", "entropy_encode_factorized",
            "entropy_encode_laplace", "entropy_decode_factorized", "entropy_decode_laplace", "entropy_encode_indexed",
@@ -45,6 +45,24 @@ def upsample2x_bilinear(x, align_corners=False, scale=1.0):
     check(lib().fvc_upsample2x_bilinear(ptr(x), ptr(y), B * Cc, H, W, int(bool(align_corners)), float(scale),
                                         stream_ptr()), "fvc_upsample2x_bilinear")
     return y
+
+
+def to_tensor_u8(frames_u8):
+    """transforms.ToTensor() on the device (dataset.py:75): uint8 [..., H, W, 3] -> float32 [..., 3, H, W] = x / 255."""
+    if not (torch.is_tensor(frames_u8) and frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.dim() >= 3
+            and frames_u8.shape[-1] == 3):
+        raise TypeError("frames_u8 must be a CUDA uint8 tensor [..., H, W, 3] (libfvc_b200 has no CPU path)")
+    src = frames_u8.contiguous()
+    H, W = src.shape[-3], src.shape[-2]
+    n = src.numel() // max(1, H * W * 3)
+    out = torch.empty(tuple(src.shape[:-3]) + (3, H, W), device=src.device, dtype=torch.float32)
+    with torch.cuda.device(src.device):
+        for i0 in range(0, n, 65535):
+            k = min(65535, n - i0)
+            check(lib().fvc_u8hwc_to_f32chw(C.c_void_p(src.data_ptr() + i0 * H * W * 3),
+                                            C.c_void_p(out.data_ptr() + i0 * H * W * 12), k, H, W, stream_ptr()),
+                  "fvc_u8hwc_to_f32chw")
+    return out
 
 
 def flow_warp(im, flow):

@@ -71,6 +71,10 @@ FVC_API int fvc_upsample2x_bilinear(const float* x, float* y, int planes, int H,
  * img: [B,C,H,W], flow: [B,2,H,W] (ch0 = x, ch1 = y) -> out: [B,C,H,W]. */
 FVC_API int fvc_flow_warp(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream);
 
+/* transforms.ToTensor() — the reference's frame ingest (dataset.py:75, models.py:425): uint8 HWC [n,H,W,3] ->
+ * fp32 CHW [n,3,H,W] in [0,1], x / 255 with IEEE division (bit-identical to torchvision).  Device pointers. */
+FVC_API int fvc_u8hwc_to_f32chw(const uint8_t* src, float* dst, int n, int H, int W, void* stream);
+
 /* nn.Conv2d(Cin,Cout,k,stride,padding=k//2) [transposed=0; weight [Cout,Cin,k,k]] or
  * nn.ConvTranspose2d(Cin,Cout,k,stride,padding=k//2,output_padding=stride-1)
  * [transposed=1; weight [Cin,Cout,k,k]], + bias, + activation.  stride in {1,2}.
@@ -201,6 +205,11 @@ FVC_API int64_t fvc_ctx_get_tensor(fvc_ctx* ctx, const char* name, float* out, i
  * copies results D2H and synchronises the stream before returning. */
 FVC_API int fvc_gop_forward_host(fvc_ctx* ctx, const float* frames_host, int G, float* recon_host, float* scalars_host,
                          void* stream);
+/* The same GOP call fed with the frames as the reference's loader holds them BEFORE transforms.ToTensor()
+ * (dataset.py:68-75: decoded image -> PIL -> ToTensor): frames_host_u8 [G,B,H,W,3], uint8, channel-interleaved.
+ * Uploads 1 byte per sample instead of 4 and applies ToTensor (HWC -> CHW, x / 255) on the device. */
+FVC_API int fvc_gop_forward_host_u8(fvc_ctx* ctx, const uint8_t* frames_host_u8, int G, float* recon_host,
+                                    float* scalars_host, void* stream);
 
 /* LSVC (reference models.py:1157-1411, non-attention "-128" variants: the same sub-networks as DVC) codes the
  * P-frames of a GOP in two phases (LSVC.forward, models.py:1344-1411):

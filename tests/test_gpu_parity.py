@@ -1288,3 +1288,37 @@ def test_lsvc_forward_matches_oracle_larger_frames(dev, state_dict):
         assert d.mean().item() <= 2e-3, (n, d.mean().item())
     assert (out[0].cpu() - want[0]).abs().mean().item() <= 2e-3
     m.release()
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 64), (3, 5, 7), (2, 1088, 1920), (1, 1, 1), (2, 17, 6)])
+def test_to_tensor_u8_bit_identical_to_torchvision_rule(dev, shape):
+    """fvc_u8hwc_to_f32chw = transforms.ToTensor() of the reference's ingest (dataset.py:75): HWC -> CHW, x / 255 in fp32
+    (IEEE division), bit for bit; aligned fast path, odd sizes (scalar tail) and unaligned views."""
+    from fastvideocodec_b200 import ops
+    n, H, W = shape
+    g = torch.Generator().manual_seed(n * 1000 + H + W)
+    u8 = torch.randint(0, 256, (n, H, W, 3), generator=g, dtype=torch.uint8)
+    want = u8.permute(0, 3, 1, 2).float().div(255)            # torchvision.transforms.functional.to_tensor
+    got = ops.to_tensor_u8(u8.to(dev))
+    assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    if H * W >= 8:                                            # unaligned source (offset by one pixel = 3 bytes)
+        flat = torch.cat([torch.zeros(3, dtype=torch.uint8), u8.reshape(-1)]).to(dev)
+        got2 = ops.to_tensor_u8(flat[3:].view(n, H, W, 3))
+        assert torch.equal(got2.cpu(), want)
+    with pytest.raises(TypeError):
+        ops.to_tensor_u8(u8)                                  # CPU tensor: no CPU path
+
+
+def test_gop_forward_host_uint8_frames_equal_float_frames(model, dev):
+    """fvc_gop_forward_host_u8: the GOP call fed with uint8 HWC frames gives exactly what the float32 call gives for
+    ToTensor() of the same frames (scalars and reconstructions bit for bit)."""
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    fr = synthetic_gop(128, 192, gop=4, gop_id=5)                               # [G,1,3,H,W] float
+    u8 = (fr * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 1, 3, 4, 2).contiguous()
+    as_float = u8.permute(0, 1, 4, 2, 3).float().div(255).contiguous()
+    rec_f, sc_f = model.gop_forward_host(as_float.pin_memory())
+    rec_u, sc_u = model.gop_forward_host(u8.pin_memory())
+    assert torch.equal(sc_f, sc_u) and torch.equal(rec_f, rec_u)
+    assert bool(torch.isfinite(sc_u).all()) and rec_u.shape == (3, 1, 3, 128, 192)
+    with pytest.raises(TypeError):
+        model.gop_forward_host(u8.permute(0, 1, 4, 2, 3))                       # uint8 but channel-planar / strided
