@@ -16,8 +16,9 @@ tables ``_quantized_cdf`` / ``_cdf_length`` / ``_offset`` from the learned densi
 The coder is the library's rANS-lane kernel over the same table / index / escape model CompressAI hands its range coder
 (``fvc_entropy_encode_indexed``); the byte strings are this library's "FVR1" containers, not CompressAI's rans64 format
 (sizes agree to within the per-lane state overhead; only ``len()`` and the round trip are used by the reference).
-Out of scope: the ``RPM`` / ``ConvLSTM`` recurrent prior networks (pass ``rpm=``), training-mode noise,
-``aux_loss`` / ``loss`` (training of the quantiles).
+``RPM`` / ``ConvLSTM`` (328-378, the recurrent prior network; pinned against the reference's own classes,
+tests/golden/rpm_128.npz) run their 3x3 convolutions on the tcgen05 engine.
+Out of scope: training-mode noise, ``aux_loss`` / ``loss`` (training of the quantiles).
 
 PARITY UNPINNED at this boundary: CompressAI is not available to check against; the algorithm follows its
 published ``EntropyBottleneck._logits_cumulative/_likelihood`` and ``GaussianConditional._likelihood``
@@ -316,12 +317,96 @@ def _estimate_bits_clamped(likelihoods):
     return torch.sum(torch.clamp(-1.0 * torch.log(likelihoods + 1e-5) / math.log(2.0), 0, 50))
 
 
+class _SplitConv(nn.Conv2d):
+    """nn.Conv2d(cin, cout, 3, 1, 1) evaluated on the tcgen05 engine, which takes at most 128 input and 128 output
+    channels per launch: wider layers (the 2C -> 4C gate convolution of the ConvLSTM, C -> 2C of RPM.conv8) run as
+    blocks of 128 output channels, each the fp32 sum over blocks of 128 input channels.  The weight blocks are cut once
+    per weight version, so the op-level handle cache (ops.conv2d) keeps their packed form."""
+
+    def __init__(self, cin, cout):
+        super().__init__(cin, cout, kernel_size=3, stride=1, padding=1)
+        self._blocks = None
+
+    def _weight_blocks(self):
+        key = (self.weight.data_ptr(), self.weight._version, self.bias.data_ptr(), self.bias._version)
+        if self._blocks is None or self._blocks[0] != key:
+            w, b = self.weight.detach(), self.bias.detach()
+            outs = []
+            for o in range(0, w.shape[0], 128):
+                ins = [w[o:o + 128, i:i + 128].contiguous() for i in range(0, w.shape[1], 128)]
+                outs.append((ins, b[o:o + 128].contiguous()))
+            self._blocks = (key, outs)
+        return self._blocks[1]
+
+    def forward(self, x, act=ops.ACT_NONE):
+        outs = []
+        for ins, b in self._weight_blocks():
+            if len(ins) == 1:
+                outs.append(ops.conv2d(x, ins[0], b, 1, act))
+                continue
+            y = None
+            for k, w in enumerate(ins):
+                part = ops.conv2d(x[:, 128 * k:128 * (k + 1)].contiguous(), w, b if k == 0 else None, 1, ops.ACT_NONE)
+                y = part if y is None else y + part
+            outs.append(torch.relu(y) if act == ops.ACT_RELU else y)
+            if act not in (ops.ACT_NONE, ops.ACT_RELU):
+                raise NotImplementedError("only ReLU is applied after a split-input convolution")
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
+
+class ConvLSTM(nn.Module):
+    """reference entropy_models.py:359-378: one 3x3 convolution of cat(x, h) to the four gates (j, i, f, o)."""
+
+    def __init__(self, channels=128, forget_bias=1.0, activation=torch.relu):
+        super().__init__()
+        self.conv = _SplitConv(2 * channels, 4 * channels)
+        self._forget_bias = forget_bias
+        self._activation = activation
+        self._channels = channels
+
+    def forward(self, x, state):
+        c, h = torch.split(state, self._channels, dim=1)
+        y = self.conv(torch.cat((x, h), dim=1).contiguous())
+        j, i, f, o = torch.split(y, self._channels, dim=1)
+        f = torch.sigmoid(f + self._forget_bias)
+        i = torch.sigmoid(i)
+        c = c * f + i * self._activation(j)
+        o = torch.sigmoid(o)
+        h = o * self._activation(c)
+        return h, torch.cat((c, h), dim=1)
+
+
+class RPM(nn.Module):
+    """reference entropy_models.py:328-357: the recurrent prior network of RecProbModel — four 3x3 conv + ReLU, the
+    ConvLSTM, three 3x3 conv + ReLU, conv C -> 2C + ReLU split into (sigma, mu).  Same parameter names as the reference
+    (``conv1..conv8``, ``lstm.conv``): its checkpoints load."""
+
+    def __init__(self, channels=128, act=torch.tanh):
+        super().__init__()
+        for i in range(1, 8):
+            setattr(self, "conv%d" % i, _SplitConv(channels, channels))
+        self.conv8 = _SplitConv(channels, 2 * channels)
+        self.channels = channels
+        self.lstm = ConvLSTM(channels)
+
+    def forward(self, x, hidden):
+        x = x.contiguous()
+        for i in range(1, 5):
+            x = getattr(self, "conv%d" % i)(x, ops.ACT_RELU)
+        x, hidden = self.lstm(x, hidden.to(x.device))
+        for i in range(5, 8):
+            x = getattr(self, "conv%d" % i)(x.contiguous(), ops.ACT_RELU)
+        sigma_mu = self.conv8(x, ops.ACT_RELU)
+        sigma, mu = torch.split(sigma_mu, self.channels, dim=1)
+        return sigma, mu, hidden
+
+
 class RecProbModel(nn.Module):
     """reference entropy_models.py:26-148 (forward / get_estimate_bits only).
 
-    ``RPM_flag=False``: factorized ``entropy_bottleneck``.  ``RPM_flag=True``: the recurrent prior network
-    (RPM + ConvLSTM) is out of scope; pass a module as ``rpm`` (called as ``rpm(prior_latent, rpm_hidden)`` ->
-    ``sigma, mu, rpm_hidden``) to use the conditional-Gaussian branch (entropy_models.py:58-63).
+    ``RPM_flag=False``: factorized ``entropy_bottleneck``.  ``RPM_flag=True``: the recurrent prior network ``RPM``
+    (entropy_models.py:328-378) supplies sigma / mu of the conditional-Gaussian branch (58-63); ``rpm=`` replaces it by
+    any callable ``rpm(prior_latent, rpm_hidden) -> (sigma, mu, rpm_hidden)``.
     """
 
     def __init__(self, channels, rpm=None):
@@ -330,7 +415,7 @@ class RecProbModel(nn.Module):
         self.entropy_bottleneck = EntropyBottleneck(channels)
         self.gaussian_conditional = GaussianConditional(None)
         self.sigma = self.mu = self.prior_latent = None
-        self.RPM = rpm
+        self.RPM = rpm if rpm is not None else RPM(channels)
         self.RPM_flag = False
 
     def set_RPM(self, RPM_flag):
@@ -339,8 +424,6 @@ class RecProbModel(nn.Module):
     def forward(self, x, rpm_hidden, training=None, prior_latent=None):
         if self.RPM_flag:
             assert prior_latent is not None, 'prior latent is none!'
-            if self.RPM is None:
-                raise NotImplementedError("the RPM/ConvLSTM prior network is outside the hot path; pass rpm=...")
             self.sigma, self.mu, rpm_hidden = self.RPM(prior_latent, rpm_hidden.to(x.device))
             self.sigma = torch.maximum(self.sigma, torch.FloatTensor([-7.0]).to(x.device))
             self.sigma = torch.exp(self.sigma) / 10
@@ -366,8 +449,6 @@ class RecProbModel(nn.Module):
         return torch.FloatTensor([len(b''.join(string)) * 8]).squeeze(0)
 
     def _rpm_params(self, prior_latent, rpm_hidden):
-        if self.RPM is None:
-            raise NotImplementedError("the RPM/ConvLSTM prior network is outside the hot path; pass rpm=...")
         sigma, mu, rpm_hidden = self.RPM(prior_latent, rpm_hidden.to(prior_latent.device))
         sigma = torch.maximum(sigma, torch.FloatTensor([-7.0]).to(sigma.device))
         return torch.exp(sigma) / 10, mu, rpm_hidden

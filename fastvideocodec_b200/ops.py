@@ -380,6 +380,8 @@ def entropy_encode_indexed(symbols, indexes, quantized_cdf, cdf_length, offset, 
     if idx.numel() != sym.numel() or cdf.dim() != 2 or ln.numel() != cdf.shape[0] or off.numel() != cdf.shape[0]:
         raise ValueError("indexes must match symbols; quantized_cdf [ntab, stride] with one cdf_length / offset per table")
     n = sym.numel()
+    if n == 0:                                          # nothing to code: the empty string round-trips
+        return b""
     cap = lib().fvc_entropy_stream_capacity_indexed(n, lane_len)
     buf = torch.empty(cap, device=dev, dtype=torch.uint8)
     nbytes = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -400,6 +402,10 @@ def entropy_decode_indexed(stream, indexes, quantized_cdf, cdf_length, offset, l
     idx = _cuda_i32(indexes, "indexes")
     dev = idx.device
     cdf, ln, off = _cuda_i32(quantized_cdf, "quantized_cdf", dev), _cuda_i32(cdf_length, "cdf_length", dev), _cuda_i32(offset, "offset", dev)
+    if idx.numel() == 0:
+        if len(stream):
+            raise _lib.FvcError("entropy_decode_indexed: a non-empty stream for zero symbols")
+        return torch.empty(idx.shape, device=dev, dtype=torch.int32)
     st = _stream_tensor(stream, dev)
     out = torch.empty(idx.shape, device=dev, dtype=torch.int32)
     err = torch.zeros(3, device=dev, dtype=torch.int32)

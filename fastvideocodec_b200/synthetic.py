@@ -135,3 +135,17 @@ def synthetic_gop(height: int, width: int, gop: int = 10, gop_id: int = 0, batch
         f = f + 0.01 * torch.randn(f.shape, generator=g)
         frames.append(f.clamp(0, 1))
     return torch.stack(frames, 0).contiguous()
+
+
+def init_rpm_state_dict(channels: int = 128, seed: int = 0):
+    """Seeded weights with the state_dict layout of the reference's RPM prior network (entropy_models.py:328-378):
+    ``conv1..conv7`` C->C, ``conv8`` C->2C, ``lstm.conv`` 2C->4C, all 3x3; PyTorch's default conv init range."""
+    g = torch.Generator().manual_seed(int(seed))
+    sd = OrderedDict()
+    C = int(channels)
+    shapes = [("conv%d" % i, C, C) for i in range(1, 8)] + [("conv8", 2 * C, C), ("lstm.conv", 4 * C, 2 * C)]
+    for name, cout, cin in shapes:
+        bound = 1.0 / math.sqrt(cin * 9)
+        sd[name + ".weight"] = (torch.rand((cout, cin, 3, 3), generator=g) * 2 - 1) * bound * 1.7
+        sd[name + ".bias"] = (torch.rand((cout,), generator=g) * 2 - 1) * bound
+    return sd

@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference):
 
-    python -m oracle.gen_golden_r2 [real] [hd] [l6] [entropy]
+    python -m oracle.gen_golden_r2 [real] [hd] [l6] [entropy] [rpm]
 
 Writes
   tests/golden/spynet_real.npz      : the reference's own pretrained SpyNet weights, levels 1-4
@@ -18,6 +18,8 @@ Writes
   tests/golden/pframe_L6_256.npz    : one P-frame at 256x256 of the reference class with ``self.L`` patched to 6
                                       (endecoder.py:318-319; moduleBasic extended with MEBasic(modelL5), (modelL6)),
                                       weights init_state_dict(0, spynet_levels=6, spynet_gain=1.8)
+  tests/golden/entropy_tables.npz   : float CDF tables of the calrealbits branch as the reference builds them
+  tests/golden/rpm_128.npz          : two recurrent steps of the reference's RPM / ConvLSTM prior network (entropy_models.py:328-378)
 """
 from __future__ import annotations
 
@@ -159,11 +161,35 @@ def gen_entropy():
     np.savez_compressed(os.path.join(GOLD, "entropy_tables.npz"), **_np(d))
 
 
+def gen_rpm():
+    """tests/golden/rpm_128.npz: the reference's own RPM / ConvLSTM classes (entropy_models.py:328-378, imported with the
+    compressai / torchac import stubs of ref_shim) run for two recurrent steps on CPU with
+    init_rpm_state_dict(128, seed 7).  Only inputs and outputs are stored; the weights are regenerated from the seed."""
+    from fastvideocodec_b200.synthetic import init_rpm_state_dict
+    ref_shim.load_reference_models()
+    with ref_shim._cwd(ref_shim.REF_ROOT):
+        import entropy_models as REM
+    C = 128
+    rpm = REM.RPM(C).eval()
+    sd = init_rpm_state_dict(C, 7)
+    assert list(rpm.state_dict().keys()) == list(sd.keys())
+    rpm.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(77)
+    x0 = torch.round(torch.randn((2, C, 9, 14), generator=g) * 3)          # prior latents are rounded latents
+    x1 = torch.round(torch.randn((2, C, 9, 14), generator=g) * 3)
+    h0 = torch.randn((2, 2 * C, 9, 14), generator=g) * 0.5
+    with torch.no_grad():
+        s0, m0, h1 = rpm(x0, h0)
+        s1, m1, h2 = rpm(x1, h1)
+    d = dict(x0=x0, x1=x1, h0=h0, sigma0=s0, mu0=m0, h1=h1, sigma1=s1, mu1=m1, h2=h2)
+    np.savez_compressed(os.path.join(GOLD, "rpm_128.npz"), **{k: (v if isinstance(v, np.ndarray) else v.numpy()) for k, v in d.items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    what = sys.argv[1:] or ["real", "l6", "hd", "entropy"]
+    what = sys.argv[1:] or ["real", "l6", "hd", "entropy", "rpm"]
     if "real" in what:
         gen_real()
     if "l6" in what:
@@ -172,6 +198,8 @@ def main():
         gen_hd()
     if "entropy" in what:
         gen_entropy()
+    if "rpm" in what:
+        gen_rpm()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -213,6 +213,12 @@ def test_indexed_coder_errors(dev):
         ops.entropy_decode_indexed(good, t(idx[:5]), t(cdf), t(ln), t(off))
     with pytest.raises(ValueError):
         ops.entropy_encode_indexed(t(sym), t(idx[:5]), t(cdf), t(ln), t(off))
+    # zero symbols: the empty string, both ways
+    empty = torch.zeros(0, dtype=torch.int32, device=dev)
+    assert ops.entropy_encode_indexed(empty, empty, t(cdf), t(ln), t(off)) == b""
+    assert ops.entropy_decode_indexed(b"", empty, t(cdf), t(ln), t(off)).numel() == 0
+    with pytest.raises(FvcError):
+        ops.entropy_decode_indexed(good, empty, t(cdf), t(ln), t(off))
 
 
 def _trained_like(eb, g):

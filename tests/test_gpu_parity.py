@@ -1322,3 +1322,44 @@ def test_gop_forward_host_uint8_frames_equal_float_frames(model, dev):
     assert bool(torch.isfinite(sc_u).all()) and rec_u.shape == (3, 1, 3, 128, 192)
     with pytest.raises(TypeError):
         model.gop_forward_host(u8.permute(0, 1, 4, 2, 3))                       # uint8 but channel-planar / strided
+
+
+def test_rpm_prior_network_matches_reference(dev):
+    """entropy_models.RPM / ConvLSTM (reference entropy_models.py:328-378) on the tcgen05 engine — 128-channel 3x3
+    convolutions, the 256 -> 512 gate convolution and conv8 128 -> 256 as 128-channel blocks — against two recurrent
+    steps of the reference's own classes (tests/golden/rpm_128.npz, oracle/gen_golden_r2.py rpm)."""
+    from conftest import load_golden
+    from fastvideocodec_b200 import ops
+    from fastvideocodec_b200.entropy_models import RPM, RecProbModel
+    from fastvideocodec_b200.synthetic import init_rpm_state_dict
+    gold = load_golden("rpm_128.npz")
+    rpm = RPM(128)
+    sd = init_rpm_state_dict(128, 7)
+    assert list(rpm.state_dict().keys()) == list(sd.keys())      # the generator asserts the same against the reference class
+    rpm.load_state_dict(sd, strict=True)
+    rpm = rpm.to(dev).eval()
+    ops.conv_op_cache_clear()
+
+    def close(a, b, what):
+        err = (a.cpu() - b).abs().max().item()
+        assert err <= 1e-4 * max(1.0, b.abs().max().item()), (what, err)
+
+    with torch.no_grad():
+        s0, m0, h1 = rpm(gold["x0"].to(dev), gold["h0"])                 # hidden may arrive on the CPU (reference: .to(x.device))
+        n_handles = ops.conv_op_cache_size()
+        s1, m1, h2 = rpm(gold["x1"].to(dev), h1)
+    assert ops.conv_op_cache_size() == n_handles == 7 + 2 + 8            # conv1-7, conv8 (2 blocks), lstm (4 x 2 blocks): reused
+    for got, name in ((s0, "sigma0"), (m0, "mu0"), (h1, "h1"), (s1, "sigma1"), (m1, "mu1"), (h2, "h2")):
+        close(got, gold[name], name)
+    # inside RecProbModel: the conditional-Gaussian branch driven by the network (entropy_models.py:58-63)
+    m = RecProbModel(128)
+    m.RPM.load_state_dict(sd)
+    m = m.to(dev).eval()
+    m.set_RPM(True)
+    x = (gold["x1"] + 0.3).to(dev)
+    with torch.no_grad():
+        xh, lik, hid, prior = m(x, gold["h0"], training=False, prior_latent=gold["x0"].to(dev))
+    close(m.sigma, torch.exp(torch.clamp(gold["sigma0"], min=-7.0)) / 10, "RecProbModel.sigma")
+    close(hid, gold["h1"], "RecProbModel.hidden")
+    assert torch.equal(prior, torch.round(x)) and bool(((lik > 0) & (lik <= 1)).all())
+    ops.conv_op_cache_clear()

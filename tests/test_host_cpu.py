@@ -267,8 +267,8 @@ def test_entropy_models_surface():
     assert torch.allclose(bits, torch.tensor([6.0, 6.0]))
     assert em.get_scale_table().shape == (64,) and abs(float(em.get_scale_table()[0]) - 0.11) < 1e-6
     m.set_RPM(True)
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 8, 2, 2), torch.zeros(1), prior_latent=torch.zeros(1, 8, 2, 2))
+    with pytest.raises(TypeError):                       # the RPM network runs on the CUDA engine only: no CPU path
+        m(torch.zeros(1, 8, 2, 2), torch.zeros(1, 16, 2, 2), prior_latent=torch.zeros(1, 8, 2, 2))
     m.train()
     m.set_RPM(False)
     with pytest.raises(NotImplementedError):
@@ -333,3 +333,32 @@ def test_entropy_models_load_compressai_layout_state_dict():
     g2 = GaussianConditional(None)
     g2.load_state_dict(sd, strict=True)
     assert g2.scale_table.shape == (64,)
+
+
+def test_entropy_models_range_coding_surface_and_rpm_layout():
+    """the reference-facing methods exist with the reference's signatures, and RPM / ConvLSTM carry the
+    reference's parameter names and shapes (entropy_models.py:328-378)."""
+    import inspect
+    from fastvideocodec_b200.entropy_models import ConvLSTM, MeanScaleHyperPriors, RPM, RecProbModel
+    from fastvideocodec_b200.synthetic import init_rpm_state_dict
+    for cls, names in ((RecProbModel, ["update", "compress", "decompress", "compress_slow", "decompress_slow",
+                                       "get_actual_bits", "get_estimate_bits", "set_RPM"]),
+                       (MeanScaleHyperPriors, ["update", "compress", "decompress", "compress_slow", "decompress_slow",
+                                               "get_actual_bits", "get_estimate_bits"])):
+        for n in names:
+            assert callable(getattr(cls, n)), (cls, n)
+    assert list(inspect.signature(RecProbModel.compress_slow).parameters) == ["self", "x", "rpm_hidden", "prior_latent"]
+    assert list(inspect.signature(RecProbModel.decompress_slow).parameters) == ["self", "string", "shape", "rpm_hidden", "prior_latent"]
+    assert list(inspect.signature(MeanScaleHyperPriors.compress_slow).parameters) == ["self", "x", "decode"]
+    assert list(inspect.signature(MeanScaleHyperPriors.decompress_slow).parameters) == ["self", "string", "shape"]
+    rpm = RPM(32)
+    sd = rpm.state_dict()
+    assert list(sd) == list(init_rpm_state_dict(32))
+    assert sd["conv8.weight"].shape == (64, 32, 3, 3) and sd["lstm.conv.weight"].shape == (128, 64, 3, 3)
+    assert isinstance(rpm.lstm, ConvLSTM) and isinstance(RecProbModel(8).RPM, RPM)
+    m = RecProbModel(8)
+    assert float(m.get_actual_bits([b"abc", b"de"])) == 40.0
+    assert MeanScaleHyperPriors(8).get_actual_bits(([b"abc", b"d"], [b"e", b""])).tolist() == [32.0, 8.0]
+    assert m.update(force=True) is True and m.entropy_bottleneck._quantized_cdf.shape[0] == 8
+    with pytest.raises(TypeError):
+        m.compress(torch.zeros((1, 8, 4, 4)))           # CPU tensors: the coder has no CPU path
