@@ -291,8 +291,14 @@ def run_ours(args, rank, world, local_rank):
     model = model.to(dev).eval()
     impl_name = {0: "simt", 1: "tc", 2: "tc-fast"}[model.impl]
 
-    # each rank codes its own GOPs (GOP g seeded 1234+g; rank r owns g = r mod world): weak scaling
+    # each rank codes its own GOPs (GOP g seeded 1234+g; rank r owns g = r mod world): weak scaling.
+    # --total-gops T (configs[2]: "64 GOPs x 10 frames"): the T GOPs are dealt round-robin (gop.shard_gops), every rank
+    # times its share, the job time is the slowest rank's: strong scaling.
     n_local = 2
+    strong = args.total_gops > 0
+    if strong:
+        from fastvideocodec_b200 import shard_gops
+        args.steps = len(shard_gops(args.total_gops, rank, world))
     host_gops = [synthetic_gop(H, W, gop=GOP, gop_id=rank + i * world, batch=BATCH).contiguous().pin_memory()
                  for i in range(n_local)]                      # [G,B,3,H,W] each
     dev_gops = [g.to(dev) for g in host_gops]
@@ -332,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t)
-    frames_total = world * args.steps * (GOP - 1) * BATCH
+    frames_total = (args.total_gops if strong else world * args.steps) * (GOP - 1) * BATCH
     value = frames_total / (ms_max * 1e-3)
 
     # ---- end to end: host frames -> metrics on host -----------------------------------------
@@ -440,13 +446,14 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "P-frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"tc": "f16 hi/lo pairs x3 MMAs (fp32 accumulate)", "tc-fast": "f16 x1 MMA (fp32 accumulate)",
+                "warmup": args.warmup, "ms_per_step": ms_max / max(1, args.steps), "higher_is_better": True,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": {"tc": "f16 hi/lo pairs x3 MMAs (fp32 accumulate)", "tc-fast": "f16 x1 MMA (fp32 accumulate)",
                                                   "simt": "f32"}[impl_name],
                 "data": "synthetic",
                 "config": {"workload": CONFIGS[args.config][3] + (" (%d views per rank)" % BATCH if args.config == "multiview" else ""),
                            "engine": impl_name, "l2": "per-frame working set (GBs of activations) exceeds the 126 MB L2",
-                           "parallelism": "gop-sharded x%d, no data-path collective" % world},
+                           "parallelism": "gop-sharded x%d, no data-path collective" % world,
+                           **({"total_gops": args.total_gops, "steps_are": "GOPs of rank 0's share"} if strong else {})},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": "P-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "d2h_what": "the 7 scalars per P-frame only (eval.py reads metrics, not frames; "
@@ -466,6 +473,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="hd", choices=sorted(CONFIGS))
+    ap.add_argument("--total-gops", type=int, default=0,
+                    help="strong-scaling form (configs[2]): this many GOPs in total, dealt round-robin to the ranks; "
+                         "overrides --steps")
     ap.add_argument("--precision", default="exact", choices=["exact", "fast"],
                     help="exact: fp16 hi/lo pairs, 3 MMAs per product (element-level parity; the headline); "
                          "fast: 1 fp16 MMA per product (metric-level parity)")
