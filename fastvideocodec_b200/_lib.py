@@ -48,6 +48,8 @@ _SIGNATURES = {
     "fvc_gop_forward_host": (_i, [C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, _s]),
     "fvc_gop_forward_host_u8": (_i, [C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, _s]),
     "fvc_u8hwc_to_f32chw": (_i, [C.c_void_p, _f, _i, _i, _i, _s]),
+    "fvc_iframe_forward": (_i, [C.c_void_p, _f, _f, _f, _s]),
+    "fvc_iframe_decode_bitstreams": (_i, [C.c_void_p, C.c_void_p, _l, C.c_void_p, _l, _f, _s]),
     "fvc_lsvc_mv_forward": (_i, [C.c_void_p, _f, _f, _f, _f, _s]),
     "fvc_lsvc_mc_res_forward": (_i, [C.c_void_p, _f, _f, _f, _f, _f, _f, _f, _s]),
     "fvc_decode_from_latents": (_i, [C.c_void_p, _f, _f, _f, _f, _s]),

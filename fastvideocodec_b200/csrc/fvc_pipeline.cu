@@ -783,13 +783,21 @@ static int run_res_decoder(fvc_ctx* c, cudaStream_t s) {
 // 1300-1331) with the motion field in c->mv_hat.  sums: 3 loss partial sums reduced with `loss_scale`,
 // bits_feature, bits_z in c->scalars[0..4].
 static int forward_mc_res(fvc_ctx* c, const float* cur, const float* ref, float* recon_out, double loss_scale,
-                          int clip_mse, cudaStream_t s) {
+                          int clip_mse, cudaStream_t s, bool intra = false) {
     const int B = c->B, H = c->H, W = c->W;
     int rc;
     int nb_z = 0, nb_f = 0;
     const int maxb = bits_max_blocks();
 #define R(expr) do { rc = (expr); if (rc) return rc; } while (0)
-    R(run_motion_comp(c, cur, ref, s));
+    if (intra) {
+        // intra frame: no reference, the prediction is zero and the "residual" is the frame itself
+        const size_t n = (size_t)B * 3 * H * W * 4;
+        FVC_CUDA(cudaMemsetAsync(c->prediction, 0, n, s));
+        FVC_CUDA(cudaMemsetAsync(c->warpframe, 0, n, s));
+        PK("@k_nchw_to_act:intra", launch_nchw_to_act(cur, c->residual, 3, 0, s));
+    } else {
+        R(run_motion_comp(c, cur, ref, s));
+    }
     // ---- residual encoder (analysis.py:44-48) ---------------------------------------------------
     R(run_conv_gdn(c, "resEncoder.conv1", "resEncoder.gdn1", c->residual, c->r_raw[0], c->r_sq[0], c->r[0], s));
     R(run_conv_gdn(c, "resEncoder.conv2", "resEncoder.gdn2", c->r[0], c->r_raw[1], c->r_sq[1], c->r[1], s));
@@ -1054,6 +1062,71 @@ int fvc_pframe_forward(fvc_ctx* c, const float* cur, const float* ref, float* re
         c->last_conv_seconds = tot;
     }
     return rc;
+}
+
+/* Intra frame through the residual branch alone ("hyperprior image codec from the same conv engine"):
+ * y = resEncoder(x), z = respriorEncoder(|y|), sigma = respriorDecoder(round z), x_hat = clamp(resDecoder(round y)),
+ * i.e. VideoCompressor.forward (net.py:86-116) with a zero prediction and no motion branch.  The reference has no
+ * learned intra codec (models.py:412-429 shells out to bpgenc / bpgdec); this reuses its modules and weights. */
+int fvc_iframe_forward(fvc_ctx* c, const float* frame, float* recon_out, float* scalars_out, void* stream) {
+    FVC_ARG(c && frame && recon_out && scalars_out);
+    if (fvc_ctx_missing_params(c) != 0) {
+        set_error("fvc_iframe_forward: %d parameters not set", fvc_ctx_missing_params(c));
+        return FVC_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = c->B, H = c->H, W = c->W;
+    int64_t before = g_launch_count;
+    c->conv_event_used = 0;
+    int rc = forward_mc_res(c, frame, nullptr, recon_out, 1.0 / ((double)B * 3 * H * W), 0, s, true);
+    if (rc) return rc;
+    FVC_CUDA(cudaMemsetAsync(c->scalars + 5, 0, 4, s));   // no motion stream
+    if (c->realbits)
+        for (int k = 0; k < 2 && !rc; ++k) rc = launch_bytes_to_bits(c->stream_bytes + k, c->ent_err, c->scalars + 3 + k, s);
+    if (!rc) rc = launch_finalize_scalars(c->scalars, (float)((double)B * H * W), scalars_out, c->sat_count, s);
+    c->launches += g_launch_count - before;
+    return rc;
+}
+
+/* Decoder of fvc_iframe_forward's two streams (fvc_ctx_get_bitstream 0 and 1). */
+int fvc_iframe_decode_bitstreams(fvc_ctx* c, const void* feat_stream, int64_t feat_bytes, const void* z_stream,
+                                 int64_t z_bytes, float* recon_out, void* stream) {
+    FVC_ARG(c && feat_stream && z_stream && recon_out);
+    if (fvc_ctx_missing_params(c) != 0) {
+        set_error("fvc_iframe_decode_bitstreams: %d parameters not set", fvc_ctx_missing_params(c));
+        return FVC_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t before = g_launch_count;
+    c->conv_event_used = 0;
+    int rc = ensure_entropy_buffers(c);
+    const int R = c->mxrange, L = c->rans_L;
+    const size_t n = (size_t)c->B * 3 * c->H * c->W * 4;
+    int nloss = 0;
+    if (!rc) rc = launch_cdf_table_factorized(be_params(c->be_z), 64, R, c->cdf_tab_z, s);
+    if (!rc) rc = launch_rans_decode_factorized((const uint8_t*)z_stream, z_bytes, latent_count(c, 1), L, 64, R, c->cdf_tab_z, c->z, c->ent_err, s);
+    if (!rc) rc = launch_nhwc_to_act(c->z, c->z_hat, 64, 0, s);
+    if (!rc) rc = run_prior_decoder(c, s);
+    if (!rc) rc = launch_rans_decode_laplace((const uint8_t*)feat_stream, feat_bytes, latent_count(c, 0), L, R, c->sigma, c->feature, c->ent_err, s);
+    if (!rc) rc = launch_nhwc_to_act(c->feature, c->feat_hat, 96, 0, s);
+    if (!rc) rc = run_res_decoder(c, s);
+    if (rc) return rc;
+    FVC_CUDA(cudaMemsetAsync(c->prediction, 0, n, s));
+    FVC_CUDA(cudaMemsetAsync(c->warpframe, 0, n, s));
+    // clamp(0 + recon_res, 0, 1); the distortion sums (against the zero prediction) are discarded
+    rc = launch_recon_losses(c->prediction, c->prediction, c->warpframe, c->recon_res, 1, c->B, c->H * c->W, recon_out,
+                             c->loss_partials, &nloss, s, 0);
+    c->launches += g_launch_count - before;
+    if (rc) return rc;
+    unsigned int err[3] = {0, 0, 0};
+    FVC_CUDA(cudaMemcpyAsync(err, c->ent_err, 12, cudaMemcpyDeviceToHost, s));
+    FVC_CUDA(cudaStreamSynchronize(s));
+    if (err[2]) {
+        set_error("fvc_iframe_decode_bitstreams: %u lanes could not be opened (wrong container, size or geometry)", err[2]);
+        cudaMemsetAsync(c->ent_err, 0, 12, s);
+        return FVC_ERR_ARG;
+    }
+    return 0;
 }
 
 /* LSVC two-phase use of the path (reference models.py:1344-1411): phase A on a batch of frames against their

@@ -311,6 +311,82 @@ class VideoCompressor(nn.Module):
         self._last_ctx = ctx
         return recon
 
+    # ---- intra frames ------------------------------------------------------------------------
+    def _iframe_call(self, frame):
+        if self.training:
+            raise NotImplementedError("training-mode forward is outside the B200 inference hot path; call .eval()")
+        if not (torch.is_tensor(frame) and frame.is_cuda and frame.dtype == torch.float32 and frame.dim() == 4 and frame.shape[1] == 3):
+            raise TypeError("frame must be a CUDA float32 [B,3,H,W] tensor")
+        B, _, H, W = frame.shape
+        if H % 64 or W % 64:
+            raise ValueError("H and W must be multiples of 64 (got %dx%d)" % (H, W))
+        x = frame.contiguous()
+        with torch.cuda.device(x.device):
+            ctx = self._context(B, H, W, x.device)
+            if bool(self.calrealbits) != ctx.realbits:
+                check(lib().fvc_ctx_set_realbits(ctx.handle, int(bool(self.calrealbits)), int(self.mxrange)),
+                      "fvc_ctx_set_realbits")
+                ctx.realbits = bool(self.calrealbits)
+            recon = torch.empty_like(x)
+            scalars = torch.empty(7, device=x.device, dtype=torch.float32)
+            check(lib().fvc_iframe_forward(ctx.handle, ptr(x), ptr(recon), ptr(scalars), stream_ptr()), "fvc_iframe_forward")
+        self._last_ctx = ctx
+        return recon, scalars
+
+    def iframe_forward(self, frame):
+        """Intra coding of a frame on the device, for the place where the reference shells out to bpgenc / bpgdec
+        (I_compression, models.py:412-429): the residual branch of ``forward`` (net.py:86-116) applied to the frame
+        itself (zero prediction, no motion branch), same weights and kernels.  Returns ``(clipped_recon, mse,
+        bpp_feature, bpp_z, bpp)``; honours ``calrealbits``."""
+        recon, s = self._iframe_call(frame)
+        return recon, s[0], s[3], s[4], s[6]
+
+    def i_codec(self, frame):
+        """``I_compression``-shaped wrapper (models.py:412-429: ``(Y1_com, bpp, psnr)``) for
+        ``parallel_compression(..., i_codec=model.i_codec)``."""
+        recon, mse, _, _, bpp = self.iframe_forward(frame)
+        psnr = 10.0 * torch.log10(1.0 / mse)
+        return recon, bpp, psnr
+
+    def iframe_compress(self, frame):
+        """``iframe_forward`` with real entropy coding: ``({"feature", "z"} -> bytes, clipped_recon, scalars[7])``."""
+        old = self.calrealbits
+        self.calrealbits = True
+        try:
+            recon, scalars = self._iframe_call(frame)
+        finally:
+            self.calrealbits = old
+        ctx = self._last_ctx
+        streams = {}
+        with torch.cuda.device(frame.device):
+            for k, name in enumerate(self.STREAMS[:2]):
+                n = check(lib().fvc_ctx_get_bitstream(ctx.handle, k, C.c_void_p(0), 0, stream_ptr()), "fvc_ctx_get_bitstream")
+                buf = (C.c_ubyte * max(n, 1))()
+                check(lib().fvc_ctx_get_bitstream(ctx.handle, k, buf, n, stream_ptr()), "fvc_ctx_get_bitstream")
+                streams[name] = bytes(buf[:n])
+        return streams, recon, scalars
+
+    def iframe_decompress(self, streams, shape, device=None):
+        """Decoder of ``iframe_compress``: the two byte streams -> the same clamped reconstruction, bit for bit.
+        ``shape`` = (B, 3, H, W)."""
+        import numpy as np
+        B, _, H, W = shape
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        with torch.cuda.device(dev):
+            ctx = self._context(B, H, W, dev)
+            check(lib().fvc_ctx_set_realbits(ctx.handle, int(ctx.realbits), int(self.mxrange)), "fvc_ctx_set_realbits")
+            dev_streams = []
+            for name in self.STREAMS[:2]:
+                raw = streams[name]
+                pad = (-len(raw)) % 4
+                dev_streams.append(torch.from_numpy(np.frombuffer(raw + b"\0" * pad, dtype=np.uint8).copy()).to(dev))
+            recon = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
+            f, z = dev_streams
+            check(lib().fvc_iframe_decode_bitstreams(ctx.handle, ptr(f), len(streams["feature"]), ptr(z), len(streams["z"]),
+                                                     ptr(recon), stream_ptr()), "fvc_iframe_decode_bitstreams")
+        self._last_ctx = ctx
+        return recon
+
     def force_latents(self, B, H, W, device, quant_mv=None, z_hat=None, feat_hat=None):
         """Teacher forcing for tests: the next forwards on the (B,H,W) context use these quantised latents (CUDA fp32
         NCHW; the caller keeps them alive) instead of their own quantiser outputs; all None = free running."""

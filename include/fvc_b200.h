@@ -211,6 +211,18 @@ FVC_API int fvc_gop_forward_host(fvc_ctx* ctx, const float* frames_host, int G, 
 FVC_API int fvc_gop_forward_host_u8(fvc_ctx* ctx, const uint8_t* frames_host_u8, int G, float* recon_host,
                                     float* scalars_host, void* stream);
 
+/* Intra frame on the device.  The reference codes frame 0 of a GOP by shelling out to bpgenc / bpgdec
+ * through temporary JPEG files (I_compression, models.py:412-429: external binaries, no learned intra codec).  This is
+ * the replacement the survey proposes, "a hyperprior image codec from the same conv engine": the residual branch of
+ * VideoCompressor.forward (net.py:86-116: resEncoder, respriorEncoder, respriorDecoder, resDecoder, both bit
+ * estimators) applied to the frame itself, i.e. the P-frame forward with a zero prediction and no motion branch; same
+ * weights, same kernels.  scalars_out[7] keeps the P-frame layout: mse, mean(x^2), mean(x^2), bpp_feature, bpp_z, 0, bpp.
+ * With fvc_ctx_set_realbits the two latents are entropy-coded (streams 0 and 1 of fvc_ctx_get_bitstream) and
+ * fvc_iframe_decode_bitstreams reproduces recon_out from them bit for bit. */
+FVC_API int fvc_iframe_forward(fvc_ctx* ctx, const float* frame, float* recon_out, float* scalars_out, void* stream);
+FVC_API int fvc_iframe_decode_bitstreams(fvc_ctx* ctx, const void* feat_stream, int64_t feat_bytes, const void* z_stream,
+                                         int64_t z_bytes, float* recon_out, void* stream);
+
 /* LSVC (reference models.py:1157-1411, non-attention "-128" variants: the same sub-networks as DVC) codes the
  * P-frames of a GOP in two phases (LSVC.forward, models.py:1344-1411):
  *   phase A: opticFlow + mv_codec on ALL frames at once against their ORIGINAL reference frames

@@ -383,6 +383,29 @@ def pframe_forward(sd, cur, ref, levels=4, capture=False):
     return out
 
 
+def iframe_forward(sd, x, capture=False):
+    """Intra frame through the residual branch of VideoCompressor.forward (net.py:86-116) with a zero prediction: the
+    composition behind fvc_iframe_forward (the reference itself codes I-frames with bpgenc / bpgdec,
+    models.py:412-429, so this pins the library's composition of the reference's own modules, not a reference path).
+    Returns (clipped, mse, bpp_feature, bpp_z, bpp)."""
+    feature = analysis(sd, x)
+    z = analysis_prior(sd, feature)
+    z_hat = torch.round(z)
+    sigma = synthesis_prior(sd, z_hat)
+    feat_hat = torch.round(feature)
+    recon = synthesis(sd, feat_hat)
+    clipped = recon.clamp(0.0, 1.0)
+    mse = torch.mean((recon - x).pow(2))
+    bits_feature, _ = laplace_bits(feat_hat, sigma)
+    bits_z, _ = factorized_bits(sd, "bitEstimator_z", z_hat)
+    B, _, H, W = x.shape
+    den = B * H * W
+    out = (clipped, mse, bits_feature / den, bits_z / den, (bits_feature + bits_z) / den)
+    if capture:
+        return out, dict(feature=feature, z=z, z_hat=z_hat, sigma=sigma, feat_hat=feat_hat, recon_res=recon)
+    return out
+
+
 def lsvc_forward(sd, x, layers, parents, ref_index, levels=4):
     """LSVC.forward in eval mode (128-channel, non-attention variants) — models.py:1344-1411.  ``layers``,
     ``parents``, ``ref_index`` are the reference's GOP graph (models.py:683-728, 923-949)."""

@@ -1363,3 +1363,87 @@ def test_rpm_prior_network_matches_reference(dev):
     close(hid, gold["h1"], "RecProbModel.hidden")
     assert torch.equal(prior, torch.round(x)) and bool(((lik > 0) & (lik <= 1)).all())
     ops.conv_op_cache_clear()
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 192), (2, 64, 64), (1, 1088, 1920)])
+def test_iframe_codec_matches_oracle_and_round_trips(dev, state_dict, shape):
+    """SURVEY 8f N4 — fvc_iframe_forward: a frame coded by the residual branch alone (net.py:86-116 with a zero
+    prediction), against the oracle's composition of the same reference modules (O.iframe_forward):
+      free run      : pre-round latents, quantised latents (count / +-1 / tie rule), rates
+      teacher forced: with the oracle's latents, the reconstruction within 1e-3 everywhere
+      real coding   : iframe_compress -> iframe_decompress reproduces the encoder's reconstruction bit for bit."""
+    from fastvideocodec_b200 import VideoCompressor
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    B, H, W = shape
+    x = synthetic_gop(H, W, gop=1 + B, gop_id=17)[1:1 + B, 0].contiguous()
+    want, cap = O.iframe_forward(state_dict, x, capture=True)
+    m = VideoCompressor()
+    m.load_state_dict(state_dict)
+    m = m.to(dev).eval()
+    xd = x.to(dev)
+    with torch.no_grad():
+        recon, mse, bpp_f, bpp_z, bpp = m.iframe_forward(xd)
+    for name in ("feature", "z", "sigma"):
+        got = m.get_intermediate(name).cpu()
+        tol = 5e-4 if name != "sigma" else 2e-3        # sigma = exp(.) of a network of the (possibly flipped) z_hat
+        if name != "sigma" or torch.equal(m.get_intermediate("z_hat").cpu(), cap["z_hat"]):
+            err = (got - cap[name]).abs().max().item()
+            assert err <= tol * max(1.0, cap[name].abs().max().item()), (name, err)
+    nf = check_latent("feat_hat", m.get_intermediate("feat_hat").cpu(), cap["feat_hat"], cap["feature"])
+    nz = check_latent("z_hat", m.get_intermediate("z_hat").cpu(), cap["z_hat"], cap["z"])
+    if nf == 0 and nz == 0:
+        assert (recon.cpu() - want[0]).abs().max().item() <= 1e-3
+        for got, ref in ((mse, want[1]), (bpp_f, want[2]), (bpp_z, want[3]), (bpp, want[4])):
+            assert abs(float(got) - float(ref)) <= 2e-4 * abs(float(ref)), (float(got), float(ref))
+    else:
+        assert abs(float(bpp) - float(want[4])) <= 5e-3 * float(want[4])
+    # teacher forced: the oracle's quantised latents in, reconstruction everywhere
+    m.force_latents(B, H, W, dev, z_hat=cap["z_hat"].to(dev), feat_hat=cap["feat_hat"].to(dev))
+    with torch.no_grad():
+        recon_f = m.iframe_forward(xd)[0]
+    m.force_latents(B, H, W, dev)
+    assert (recon_f.cpu() - want[0]).abs().max().item() <= 1e-3
+    assert (m.get_intermediate("recon_res").cpu() - cap["recon_res"]).abs().max().item() <= 5e-4 * max(1.0, cap["recon_res"].abs().max().item())
+    # real entropy coding and the decoder
+    with torch.no_grad():
+        streams, rec_enc, sc = m.iframe_compress(xd)
+        assert set(streams) == {"feature", "z"} and torch.equal(rec_enc, recon)
+        rec_dec = m.iframe_decompress(streams, (B, 3, H, W))
+    assert torch.equal(rec_dec, rec_enc)
+    real_bpp = 8.0 * (len(streams["feature"]) + len(streams["z"])) / (B * H * W)
+    assert abs(float(sc[6]) - real_bpp) <= 1e-6 * real_bpp and float(sc[5]) == 0.0
+    assert float(bpp) <= real_bpp <= 1.01 * float(bpp) + 8.0 * 160 / (B * H * W)
+    # the I_compression-shaped hook
+    with torch.no_grad():
+        y, b, p = m.i_codec(xd)
+    assert torch.equal(y, recon) and abs(float(p) - 10 * math.log10(1 / float(mse))) <= 1e-3
+    # a P-frame after the intra frame on the same context is unaffected by the intra call
+    if B == 1 and H <= 256:
+        fr = synthetic_gop(H, W, gop=2, gop_id=3)[:, 0]
+        with torch.no_grad():
+            a = m(fr[1:2].to(dev), fr[0:1].to(dev))
+            m.iframe_forward(xd)
+            b2 = m(fr[1:2].to(dev), fr[0:1].to(dev))
+        assert all(torch.equal(u, v) for u, v in zip(a, b2))
+    with pytest.raises(TypeError):
+        m.iframe_forward(x)
+    m.release()
+
+
+def test_parallel_compression_with_device_i_codec(model, dev):
+    """models.py:258-262 / 412-429: ``parallel_compression(..., compressI=True)`` with the device intra codec in the place
+    of the bpgenc / bpgdec shell-out: frame 0 is replaced by its intra reconstruction, its bpp / PSNR lead the lists, and
+    the P-frames are predicted from it."""
+    from fastvideocodec_b200 import parallel_compression
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    model.r = 1024
+    data = synthetic_gop(64, 128, gop=3, gop_id=2)[:, 0].to(dev)
+    with torch.no_grad():
+        rec0, bpp0, psnr0 = model.i_codec(data[0:1])
+        out = parallel_compression(None, model, data.clone(), compressI=True, i_codec=model.i_codec)
+        p1 = model(data[1:2], rec0)
+    assert len(out) == 11 and len(out[6]) == 3                     # I + 2 P PSNRs
+    assert abs(out[6][0] - float(psnr0)) <= 1e-4
+    assert torch.equal(out[0][0:1], p1[0])                          # first P-frame predicted from the intra recon
+    want_bpp = (float(bpp0) + float(p1[7])) / 2                     # running mean over the first two entries is inside out[3]
+    assert out[3] > 0 and math.isfinite(out[3]) and want_bpp > 0

@@ -5,6 +5,7 @@ run everywhere (no GPU, no reference needed).  ``test_live_reference_*`` additio
 reference when the checkout is present (build container only).
 """
 import math
+import os
 
 import pytest
 import torch
@@ -169,3 +170,25 @@ def test_oracle_matches_reference_hd_gop_first_frame(state_dict, golden_hd_gop10
     assert ((out[0] - want).abs() > 2e-5).float().mean().item() <= 1e-3     # u16 steps; tie flips perturb locally
     for i in range(7):
         assert abs(float(out[1 + i]) - g["rows"][0, i].item()) <= 1e-4 * abs(g["rows"][0, i].item()), i
+
+
+def test_oracle_iframe_composition_matches_reference_modules(state_dict):
+    """O.iframe_forward composes the residual branch (net.py:86-105) on the frame itself; its pieces are
+    checked here against the live reference's own modules (resEncoder, respriorEncoder, respriorDecoder, resDecoder)."""
+    if not os.path.isdir(ref_shim.REF_ROOT):
+        pytest.skip("reference checkout not present")
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    model = ref_shim.build_reference_model(state_dict)
+    x = synthetic_gop(64, 128, gop=2, gop_id=9)[1:2, 0].contiguous()
+    out, cap = O.iframe_forward(state_dict, x, capture=True)
+    with torch.no_grad():
+        feature = model.resEncoder(x)
+        z = model.respriorEncoder(feature)
+        sigma = model.respriorDecoder(torch.round(z))
+        recon = model.resDecoder(torch.round(feature))
+    for got, ref, name in ((cap["feature"], feature, "feature"), (cap["z"], z, "z"), (cap["sigma"], sigma, "sigma"),
+                           (cap["recon_res"], recon, "recon")):
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-5 * max(1.0, ref.abs().max().item()), (name, err)
+    assert torch.equal(out[0], cap["recon_res"].clamp(0, 1))
+    assert abs(float(out[4]) - float(out[2]) - float(out[3])) <= 1e-6 * float(out[4])
