@@ -336,7 +336,7 @@ static int entropy_encode_common(bool laplace, const float* x, const float* sigm
     TmpPool tmp(s);
     uint32_t *packed = nullptr, *lane_words = nullptr;
     uint16_t* words = nullptr;
-    if (tmp.get(&packed, (size_t)n * 4) || tmp.get(&words, entropy_words_capacity(n, L) * 2) ||
+    if (tmp.get(&packed, (size_t)n * 8) || tmp.get(&words, entropy_words_capacity(n, L) * 2) ||
         tmp.get(&lane_words, (size_t)cdiv64(n, L) * 4))
         return FVC_ERR_CUDA;
     FVC_CUDA(cudaMemsetAsync(err_out, 0, 12, s));

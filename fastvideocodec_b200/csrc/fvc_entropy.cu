@@ -83,9 +83,19 @@ __global__ void k_cdf_table_laplace(const float* __restrict__ sigma, int64_t n, 
 }
 
 // ----------------------------------------------------------------------------------------------
-// phase 1: symbol -> (start, freq), packed start | freq << 16   (freq <= 65536 - (Lp - 2) fits 16 bits)
+// phase 1: symbol -> two words: start | freq << 16 (freq <= 65536 - (Lp - 2) fits 16 bits), floor((2^32 - 1) / freq)
 // err[0] counts symbols outside [-R, R-2] (torchac check_input_bounds would raise), err[1] empty intervals
 // ----------------------------------------------------------------------------------------------
+// Exact x / freq, x % freq for x < 2^32, 1 <= freq <= 2^16 from m = floor((2^32 - 1) / freq) = 2^32 / freq - e,
+// 0 < e <= 1: mulhi(x, m) = floor(x / freq - x e / 2^32) and x e / 2^32 < 1, so the estimate is the quotient or one
+// less: one upward correction, never a downward one.  m depends on the symbol only, not on the coder state.
+__device__ __forceinline__ uint32_t rans_rcp(uint32_t freq) { return 0xffffffffu / freq; }
+__device__ __forceinline__ void rans_divmod(uint32_t x, uint32_t freq, uint32_t rcp, uint32_t& q, uint32_t& r) {
+    q = __umulhi(x, rcp);
+    r = x - q * freq;
+    if (r >= freq) { ++q; r -= freq; }
+}
+
 __device__ __forceinline__ int symbol_of(float x, int R, unsigned int* err) {
     int s = (int)rintf(x) + R;                       // net.py:76/91/100 round, then x + mxrange
     if (s < 0 || s > 2 * R - 2) {
@@ -103,7 +113,7 @@ __global__ void k_sym_factorized(const float* __restrict__ x, int64_t n, int C, 
         const int c = (int)(i % C);
         const int s = symbol_of(x[i], R, err);
         const uint32_t start = table[(size_t)c * Lp + s], end = table[(size_t)c * Lp + s + 1];
-        packed[i] = start | ((end - start) << 16);
+        reinterpret_cast<uint2*>(packed)[i] = make_uint2(start | ((end - start) << 16), rans_rcp(end - start));
     }
 }
 __global__ void k_sym_laplace(const float* __restrict__ x, const float* __restrict__ sigma, int64_t n, int R,
@@ -118,7 +128,7 @@ __global__ void k_sym_laplace(const float* __restrict__ x, const float* __restri
             atomicAdd(err + 1, 1u);
             end = start + 1;
         }
-        packed[i] = start | ((end - start) << 16);
+        reinterpret_cast<uint2*>(packed)[i] = make_uint2(start | ((end - start) << 16), rans_rcp(end - start));
     }
 }
 
@@ -137,14 +147,21 @@ __global__ void k_rans_encode(const uint32_t* __restrict__ packed, int64_t n, in
     uint16_t* slot = words + lane * (int64_t)(L + 2);
     int w = L + 2;                                    // write cursor (exclusive)
     uint32_t x = RANS_L;
+    // The state update is a serial chain over the lane's symbols and this thread issues in order: everything that does
+    // not depend on the state was done in phase 1 (interval and the reciprocal m = floor((2^32 - 1) / freq) that turns
+    // the division into a multiply-high), the next symbol's record is fetched while this one is coded.
+    const uint2* rec = reinterpret_cast<const uint2*>(packed) + first;
+    uint2 p = cnt > 0 ? rec[cnt - 1] : make_uint2(0x10000u, 0xffffffffu);
     for (int k = cnt - 1; k >= 0; --k) {              // rANS codes backwards, decodes forwards
-        const uint32_t p = packed[first + k];
-        const uint32_t start = p & 0xffffu, freq = p >> 16;
+        const uint32_t start = p.x & 0xffffu, freq = p.x >> 16, rcur = p.y;
+        if (k > 0) p = rec[k - 1];
         if (x >= (freq << 16)) {                      // x_max = ((RANS_L >> 16) << 16) * freq
             slot[--w] = (uint16_t)(x & 0xffffu);
             x >>= 16;
         }
-        x = ((x / freq) << 16) + (x % freq) + start;
+        uint32_t q, r;
+        rans_divmod(x, freq, rcur, q, r);
+        x = (q << 16) + r + start;
     }
     slot[--w] = (uint16_t)(x & 0xffffu);
     slot[--w] = (uint16_t)(x >> 16);
@@ -281,7 +298,9 @@ __device__ __forceinline__ void rans_put(uint32_t& x, uint16_t* slot, int& w, ui
         slot[--w] = (uint16_t)(x & 0xffffu);
         x >>= 16;
     }
-    x = ((x / freq) << 16) + (x % freq) + start;
+    uint32_t q, r;
+    rans_divmod(x, freq, rans_rcp(freq), q, r);       // the reciprocal does not depend on the state: off the chain
+    x = (q << 16) + r + start;
 }
 
 __global__ void k_rans_encode_indexed(const int32_t* __restrict__ symbols, const int32_t* __restrict__ indexes, int64_t n,

@@ -138,7 +138,7 @@ struct fvc_ctx {
     // real entropy coding (calrealbits, net.py:123-138 / 155-168 / 183-195): allocated on first use
     int realbits = 0, mxrange = 150, rans_L = 8192;
     uint32_t *cdf_tab_mv = nullptr, *cdf_tab_z = nullptr;   // [C][2R] integer CDFs of the two BitEstimators
-    uint32_t* sym_packed = nullptr;                          // start | freq << 16 per symbol (largest latent)
+    uint32_t* sym_packed = nullptr;                          // 2 words per symbol: start | freq << 16, reciprocal (largest latent)
     uint16_t* rans_words = nullptr;
     uint32_t* rans_lane_words = nullptr;
     uint8_t* stream[3] = {nullptr, nullptr, nullptr};        // 0: feature, 1: z, 2: mv
@@ -580,7 +580,7 @@ static int ensure_entropy_buffers(fvc_ctx* c) {
     const int R = c->mxrange, L = c->rans_L;
     const int64_t nmax = latent_count(c, 2);
     if (c->alloc(&c->cdf_tab_mv, (size_t)128 * 2 * R * 4) || c->alloc(&c->cdf_tab_z, (size_t)64 * 2 * R * 4) ||
-        c->alloc(&c->sym_packed, (size_t)nmax * 4) || c->alloc(&c->rans_words, entropy_words_capacity(nmax, L) * 2) ||
+        c->alloc(&c->sym_packed, (size_t)nmax * 8) || c->alloc(&c->rans_words, entropy_words_capacity(nmax, L) * 2) ||
         c->alloc(&c->rans_lane_words, (size_t)cdiv64(nmax, L) * 4) || c->alloc(&c->stream_bytes, 16) ||
         c->alloc(&c->ent_err, 16))
         return FVC_ERR_CUDA;
@@ -602,18 +602,20 @@ static int encode_factorized(fvc_ctx* c, int which, const float* x, cudaStream_t
     const BitEstRt& be = which == 1 ? c->be_z : c->be_mv;
     uint32_t* tab = which == 1 ? c->cdf_tab_z : c->cdf_tab_mv;
     const int64_t n = latent_count(c, which);
-    PK(which == 1 ? "@entropy_encode:z" : "@entropy_encode:mv", launch_cdf_table_factorized(be_params(be), be.C, c->mxrange, tab, s));
+    PK(which == 1 ? "@entropy_model:z" : "@entropy_model:mv", launch_cdf_table_factorized(be_params(be), be.C, c->mxrange, tab, s));
     rc = launch_sym_factorized(x, n, be.C, c->mxrange, tab, c->sym_packed, c->ent_err, s);
     if (rc) return rc;
-    return launch_rans_encode(c->sym_packed, n, c->rans_L, c->rans_words, c->rans_lane_words, c->stream[which],
-                              c->stream_bytes + which, s);
+    PK(which == 1 ? "@rans_encode:z" : "@rans_encode:mv",
+       launch_rans_encode(c->sym_packed, n, c->rans_L, c->rans_words, c->rans_lane_words, c->stream[which], c->stream_bytes + which, s));
+    return 0;
 }
 static int encode_laplace(fvc_ctx* c, cudaStream_t s) {
     int rc;
     const int64_t n = latent_count(c, 0);
-    PK("@entropy_encode:feature", launch_sym_laplace(c->feature, c->sigma, n, c->mxrange, c->sym_packed, c->ent_err, s));
-    return launch_rans_encode(c->sym_packed, n, c->rans_L, c->rans_words, c->rans_lane_words, c->stream[0],
-                              c->stream_bytes + 0, s);
+    PK("@entropy_model:feature", launch_sym_laplace(c->feature, c->sigma, n, c->mxrange, c->sym_packed, c->ent_err, s));
+    PK("@rans_encode:feature",
+       launch_rans_encode(c->sym_packed, n, c->rans_L, c->rans_words, c->rans_lane_words, c->stream[0], c->stream_bytes + 0, s));
+    return 0;
 }
 
 // mvDecoder (synthesis_mv.py:71-79): c->quant_mv (ACT) -> c->mv_hat (fp32 NHWC2)
@@ -896,6 +898,13 @@ fvc_ctx* fvc_ctx_create(int B, int H, int W, int levels, int impl) {
 
     const char* gf0 = getenv("FVC_GDN_FUSED");
     c->gdn_fused = impl != FVC_IMPL_SIMT && !(gf0 && gf0[0] == '0');
+    // symbols per rANS lane of the real entropy coder: a lane is one serial chain (~85 ns per symbol), so the coder's
+    // time is proportional to it, and each lane costs 32 bits of final state: 8192 -> +0.1 % size, 3 x 0.8 ms per 1080p
+    // frame; 2048 -> +0.4 %, 3 x 0.2 ms.  Encoder and decoder must agree (the container records it).
+    if (const char* rl = getenv("FVC_RANS_L")) {
+        const int v = atoi(rl);
+        if (v >= 64 && v <= 16384) c->rans_L = v;
+    }
     const char* tf0 = getenv("FVC_TAIL_FUSED");   // 0: off, 1 (default): mvDecoder.deconv8 and warpnet.conv6, 2: deconv8 only
     c->tail_fused = impl != FVC_IMPL_SIMT && !(tf0 && tf0[0] == '0');
     c->tail_fused_warpnet = c->tail_fused && !(tf0 && tf0[0] == '2');
