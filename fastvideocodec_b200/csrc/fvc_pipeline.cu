@@ -123,6 +123,11 @@ struct fvc_ctx {
     float* scalars = nullptr;                        // device [7] (internal copy)
     float *stage_cur = nullptr, *stage_ref = nullptr, *stage_rec = nullptr;  // GOP driver staging
     cudaStream_t copy_stream = nullptr;              // H2D of the GOP's frames, overlapped with the computation
+    // real entropy coding runs beside the rest of the frame: the coders are serial chains on a handful of warps (0.8 ms
+    // each at 1080p) whose inputs are final when they are launched and whose outputs are only read after the frame
+    cudaStream_t ent_stream = nullptr;
+    cudaEvent_t ent_fork = nullptr, ent_done = nullptr;
+    bool ent_pending = false;
     cudaEvent_t copy_fence = nullptr;
     std::vector<cudaEvent_t> copy_events;
     int stage_G = 0, stage_G_u8 = 0;
@@ -596,9 +601,36 @@ static FactorizedParams be_params(const BitEstRt& be) {
     for (int i = 0; i < 11; ++i) prm.p[i] = be.p[i];
     return prm;
 }
+// The coder's stream: everything queued on `main` so far (the coder's inputs) happens before what follows on it.
+static int ent_fork(fvc_ctx* c, cudaStream_t main, cudaStream_t* out) {
+    static const bool side = !(getenv("FVC_ENT_STREAM") && getenv("FVC_ENT_STREAM")[0] == '0');
+    if (!side) { *out = main; return 0; }
+    if (!c->ent_stream) {
+        FVC_CUDA(cudaStreamCreateWithFlags(&c->ent_stream, cudaStreamNonBlocking));
+        FVC_CUDA(cudaEventCreateWithFlags(&c->ent_fork, cudaEventDisableTiming));
+        FVC_CUDA(cudaEventCreateWithFlags(&c->ent_done, cudaEventDisableTiming));
+    }
+    FVC_CUDA(cudaEventRecord(c->ent_fork, main));
+    FVC_CUDA(cudaStreamWaitEvent(c->ent_stream, c->ent_fork, 0));
+    c->ent_pending = true;
+    *out = c->ent_stream;
+    return 0;
+}
+// `main` continues only after the coders queued so far have finished (before their byte counts / streams are read and
+// before the next frame overwrites their inputs)
+static int ent_join(fvc_ctx* c, cudaStream_t main) {
+    if (!c->ent_pending) return 0;
+    FVC_CUDA(cudaEventRecord(c->ent_done, c->ent_stream));
+    FVC_CUDA(cudaStreamWaitEvent(main, c->ent_done, 0));
+    c->ent_pending = false;
+    return 0;
+}
 // which = 1 (z) or 2 (mv): x is the pre-round latent, fp32 NHWC
-static int encode_factorized(fvc_ctx* c, int which, const float* x, cudaStream_t s) {
+static int encode_factorized(fvc_ctx* c, int which, const float* x, cudaStream_t main) {
     int rc;
+    cudaStream_t s;
+    rc = ent_fork(c, main, &s);
+    if (rc) return rc;
     const BitEstRt& be = which == 1 ? c->be_z : c->be_mv;
     uint32_t* tab = which == 1 ? c->cdf_tab_z : c->cdf_tab_mv;
     const int64_t n = latent_count(c, which);
@@ -609,8 +641,11 @@ static int encode_factorized(fvc_ctx* c, int which, const float* x, cudaStream_t
        launch_rans_encode(c->sym_packed, n, c->rans_L, c->rans_words, c->rans_lane_words, c->stream[which], c->stream_bytes + which, s));
     return 0;
 }
-static int encode_laplace(fvc_ctx* c, cudaStream_t s) {
+static int encode_laplace(fvc_ctx* c, cudaStream_t main) {
     int rc;
+    cudaStream_t s;
+    rc = ent_fork(c, main, &s);
+    if (rc) return rc;
     const int64_t n = latent_count(c, 0);
     PK("@entropy_model:feature", launch_sym_laplace(c->feature, c->sigma, n, c->mxrange, c->sym_packed, c->ent_err, s));
     PK("@rans_encode:feature",
@@ -859,6 +894,8 @@ static int forward(fvc_ctx* c, const float* cur, const float* ref, float* recon_
     if (rc) return rc;
     rc = launch_reduce_partials(c->bits_partials + 2 * bits_max_blocks(), nb_mv, 1, 1.0, c->scalars + 5, s);
     if (rc) return rc;
+    rc = ent_join(c, s);
+    if (rc) return rc;
     if (c->realbits) {   // total_bits = real_bits (net.py:147-149, 172-174, 200-202): 8 x bytes of the three streams
         for (int k = 0; k < 3 && !rc; ++k) rc = launch_bytes_to_bits(c->stream_bytes + k, c->ent_err, c->scalars + 3 + k, s);
         if (rc) return rc;
@@ -935,6 +972,9 @@ void fvc_ctx_destroy(fvc_ctx* c) {
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
     if (c->copy_fence) cudaEventDestroy(c->copy_fence);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ent_fork) cudaEventDestroy(c->ent_fork);
+    if (c->ent_done) cudaEventDestroy(c->ent_done);
+    if (c->ent_stream) cudaStreamDestroy(c->ent_stream);
     delete c;
 }
 
@@ -1090,6 +1130,8 @@ int fvc_iframe_forward(fvc_ctx* c, const float* frame, float* recon_out, float* 
     int rc = forward_mc_res(c, frame, nullptr, recon_out, 1.0 / ((double)B * 3 * H * W), 0, s, true);
     if (rc) return rc;
     FVC_CUDA(cudaMemsetAsync(c->scalars + 5, 0, 4, s));   // no motion stream
+    rc = ent_join(c, s);
+    if (rc) return rc;
     if (c->realbits)
         for (int k = 0; k < 2 && !rc; ++k) rc = launch_bytes_to_bits(c->stream_bytes + k, c->ent_err, c->scalars + 3 + k, s);
     if (!rc) rc = launch_finalize_scalars(c->scalars, (float)((double)B * H * W), scalars_out, c->sat_count, s);
@@ -1154,6 +1196,7 @@ int fvc_lsvc_mv_forward(fvc_ctx* c, const float* cur, const float* ref, float* m
     int rc = forward_mv(c, cur, ref, &nb_mv, s);
     if (!rc) rc = launch_reduce_partials(c->bits_partials + 2 * bits_max_blocks(), nb_mv, 1, 1.0, bits_mv_out, s);
     if (!rc) rc = launch_nhwc_to_nchw(c->mv_hat, mv_hat_out, c->B, 2, c->H, c->W, s);
+    if (!rc) rc = ent_join(c, s);
     c->launches += g_launch_count - before;
     return rc;
 }
@@ -1171,6 +1214,7 @@ int fvc_lsvc_mc_res_forward(fvc_ctx* c, const float* cur, const float* ref, cons
     const size_t n = (size_t)c->B * 3 * c->H * c->W;
     int rc = launch_nchw_to_nhwc(mv_hat, c->mv_hat, c->B, 2, c->H, c->W, s);
     if (!rc) rc = forward_mc_res(c, cur, ref, com_out, 1.0, 1, s);   // sums (not means) of the squared errors
+    if (!rc) rc = ent_join(c, s);
     if (!rc) {
         FVC_CUDA(cudaMemcpyAsync(mc_out, c->prediction, n * 4, cudaMemcpyDeviceToDevice, s));
         FVC_CUDA(cudaMemcpyAsync(warp_out, c->warpframe, n * 4, cudaMemcpyDeviceToDevice, s));
