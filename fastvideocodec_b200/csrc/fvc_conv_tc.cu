@@ -109,6 +109,9 @@ struct alignas(64) TcParams {
     int o_nseg;       // 64-byte pieces of the hi half of an output record (Cp / 32); the lo half follows
     uint32_t stg_bytes;
     Epilogue ep;
+    int nab;          // number of partial buffers: 1 << nab_log2, or 3 (fused GDN / tail kernels: two buffers hold less
+                      // than the three chains of a 3x3 tile, four do not fit beside the second MMA's accumulators).
+                      // Last member: the offsets of everything above stay what the default kernels were tuned with
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -625,7 +628,7 @@ __device__ __forceinline__ void gdn_tile_epilogue(const TcParams& P, const float
         const uint64_t d0 = make_desc(0, 1024u, 2u);      // K-major SWIZZLE_128B, 8-row groups 1024 B apart
         for (int s = 0; s < P.S; ++s) {
             const uint32_t a_hi = stgA + (uint32_t)(s * 2) * 16384u, a_lo = a_hi + 16384u;
-            const uint32_t dcol = tmem_base + 2u * (uint32_t)P.CT + (uint32_t)(s * N);
+            const uint32_t dcol = tmem_base + (uint32_t)(P.nab * P.CT) + (uint32_t)(s * N);
             const uint32_t aa[3] = {a_hi, a_hi, a_lo};    // x tiles [g_hi][g_lo][g_hi] of the packed stream
 #pragma unroll
             for (int t = 0; t < 3; ++t)
@@ -641,7 +644,7 @@ __device__ __forceinline__ void gdn_tile_epilogue(const TcParams& P, const float
     tc_fence_after();
     // ---- 3. normalise and store ---------------------------------------------------------------------------------
     e16* rec_out = ok ? ep.out_act.p + act_pixel_offset(ep.out_act, b, oy, ox) : nullptr;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2u * (uint32_t)P.CT + colbase;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(P.nab * P.CT) + colbase;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         uint32_t d[16];
@@ -745,7 +748,7 @@ __device__ __forceinline__ void tap_stage_issue(const TcParams& P, const float* 
         mbar_wait(bar_gw, 0);                             // weight tiles resident (completes once per kernel)
         const uint64_t d0 = make_desc(0, 1024u, 2u);
         for (int s = 0; s < P.S; ++s) {
-            const uint32_t dcol = tmem_base + 2u * (uint32_t)P.CT + (uint32_t)(s * 32);
+            const uint32_t dcol = tmem_base + (uint32_t)(P.nab * P.CT) + (uint32_t)(s * 32);
             uint32_t first = 0u;
             // stream order: per segment [w_hi][w_lo] (against y_hi), then per segment [w_hi] (against y_lo)
             for (int t = 0; t < 3 * nseg; ++t) {
@@ -783,7 +786,7 @@ __device__ __forceinline__ void tap_finish(const TcParams& P, int b, int sub, in
     {
         const int share = 1024 / N;                        // 16 (N = 64) or 8 (N = 128) columns per thread
         const int c0 = (cA >> 5) * share;                  // first column of this thread
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2u * (uint32_t)P.CT + (uint32_t)(s0 * 32 + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(P.nab * P.CT) + (uint32_t)(s0 * 32 + c0);
         float* dst = ok ? ep.tap_out + (((size_t)b * P.Hout + oy) * P.Wout + ox) * (size_t)ep.tap_cq : nullptr;
         for (int q0 = 0; q0 < share; q0 += 8) {
             uint32_t d[8];
@@ -1000,6 +1003,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
             const uint32_t so0 = (uint32_t)s_first * sstep, do0 = (uint32_t)s_first * N;
             const uint32_t so1 = (uint32_t)(s_first + TC_ISSUERS) * sstep, do1 = (uint32_t)(s_first + TC_ISSUERS) * N;
             const uint32_t nabs = (uint32_t)P.nab_log2, nabm = (1u << nabs) - 1u;
+            // fused GDN / tail kernels may run a ring of three buffers; every other instantiation keeps the mask
+            // arithmetic (and its exact code: ptxas' allocation of the skip-connection variant is fragile)
+            const bool nab3 = (GDN || TAP) && P.nab == 3;
             while (cur.valid(ntiles)) {
                 const TcSub& sb = P.sub[cur.sub];
                 const TcPass& ps = P.pass[sb.pass_first + cur.pass];
@@ -1020,9 +1026,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     // sub-tiles) are issued per loop iteration; per-tile loop control would dominate otherwise
                     while (t < ntaps) {
                         const int t0 = t, t1 = min(t + gtaps, ntaps);
-                        const uint32_t pb = gg & nabm;
+                        uint32_t pb = gg & nabm, rph = (gg >> nabs) & 1u;
+                        if constexpr (GDN || TAP) {
+                            if (nab3) { const uint32_t q3 = gg / 3u; pb = gg - 3u * q3; rph = q3 & 1u; }
+                        }
                         { const long long c0 = dbg_on ? clock64() : 0;
-                          mbar_wait(bar_aempty + 8 * pb, ((gg >> nabs) & 1u) ^ 1u);
+                          mbar_wait(bar_aempty + 8 * pb, rph ^ 1u);
                           if (dbg_on) w_aempty += clock64() - c0; }
                         tc_fence_after();
                         const uint32_t dcol = tmem_u + pb * CT;
@@ -1073,9 +1082,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                                 if (lead) tc_commit_t<PAIR>(bar_afull + 8 * gpb);
                                 ++gg;
                             }
-                            gpb = gg & nabm;
+                            uint32_t rph;
+                            if constexpr (GDN || TAP) {
+                                if (nab3) { const uint32_t q3 = gg / 3u; gpb = gg - 3u * q3; rph = q3 & 1u; }
+                                else { gpb = gg & nabm; rph = (gg >> nabs) & 1u; }
+                            } else {
+                                gpb = gg & nabm;
+                                rph = (gg >> nabs) & 1u;
+                            }
                             { const long long c0 = dbg_on ? clock64() : 0;
-                              mbar_wait(bar_aempty + 8 * gpb, ((gg >> nabs) & 1u) ^ 1u);
+                              mbar_wait(bar_aempty + 8 * gpb, rph ^ 1u);
                               if (dbg_on) w_aempty += clock64() - c0; }
                             tc_fence_after();
                             gdcol = tmem_u + gpb * CT;
@@ -1138,6 +1154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
         const uint32_t colbase = (uint32_t)part * (uint32_t)(NCH * 8);
         constexpr bool PARK = NCH >= 6;
         const uint32_t nabs = (uint32_t)P.nab_log2, nabm = (1u << nabs) - 1u;
+        const bool nab3 = (GDN || TAP) && P.nab == 3;
         const uint32_t aempty_l = PAIR ? mapa_u32(bar_aempty, 0) : bar_aempty;   // the leader's issuers wait on it
         uint32_t gg = 0;
         float run[NCH * 8];
@@ -1177,11 +1194,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 }
             }
             for (int g = 0; g < ng; ++g, ++gg) {
-                const uint32_t pb = gg & nabm;
+                uint32_t pb, rph;
+                if constexpr (GDN || TAP) {
+                    if (nab3) { const uint32_t q3 = gg / 3u; pb = gg - 3u * q3; rph = q3 & 1u; }
+                    else { pb = gg & nabm; rph = (gg >> nabs) & 1u; }
+                } else {
+                    pb = gg & nabm;
+                    rph = (gg >> nabs) & 1u;
+                }
 #ifdef FVC_TC_ACCDBG
                 const long long c0 = adbg ? clock64() : 0;
 #endif
-                mbar_wait_sleep(bar_afull + 8 * pb, (gg >> nabs) & 1u, P.acc_sleep_ns);
+                mbar_wait_sleep(bar_afull + 8 * pb, rph, P.acc_sleep_ns);
                 tc_fence_after();
 #ifdef FVC_TC_ACCDBG
                 const long long c1 = adbg ? clock64() : 0;
@@ -1661,9 +1685,13 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
     // partial-accumulator buffers: 4 when they fit the 512 TMEM columns (the MMA issuers then run up to a whole
     // tile ahead of an epilogue), else 2
     P.nab_log2 = (4 * P.CT <= 512 && env_int("FVC_TC_NAB", 4) >= 4 && !gdn && !tap) ? 2 : 1;
+    P.nab = 1 << P.nab_log2;
+    // fused GDN / tail kernels: a third buffer when it fits beside the second MMA's accumulators (a 3x3 tile of 64-channel
+    // records is three chains: with two buffers the issuers stall on the tile's own epilogue)
+    if ((gdn || tap) && 3 * P.CT + (gdn ? SX * 64 : SX * 32) <= 512 && env_int("FVC_TC_NAB3", 1) != 0) P.nab = 3;
     uint32_t cols = 32;
     // fused GDN / tail: the second MMA's accumulators (S x 64 / S x 32 columns) live behind the two partial buffers
-    while (cols < (uint32_t)((1 << P.nab_log2) * P.CT + (gdn ? SX * 64 : (tap ? SX * 32 : 0)))) cols <<= 1;
+    while (cols < (uint32_t)(P.nab * P.CT + (gdn ? SX * 64 : (tap ? SX * 32 : 0)))) cols <<= 1;
     P.tmem_cols = cols;
     P.tiles_x = pair ? cdiv(cdiv(P.Wq, 8 * SX), 2) : cdiv(P.Wq, 8 * SX);
     P.tiles_y = cdiv(P.Hq, 16);
