@@ -598,7 +598,13 @@ __device__ __forceinline__ void gdn_tile_epilogue(const TcParams& P, const float
     uint32_t satm = 0;
     // ---- 1. x in place, squares into the A-operand staging tile ------------------------------------------------
 #pragma unroll
-    for (int i = 0; i < 32; ++i) run[i] = fmaf(run[i], ep.acc_scale, bias_s[cA + i]);
+    for (int i = 0; i < 32; i += 4) {   // bias as 16-byte shared-memory loads (cA is a multiple of 32)
+        const float4 bq = *reinterpret_cast<const float4*>(bias_s + cA + i);
+        run[i] = fmaf(run[i], ep.acc_scale, bq.x);
+        run[i + 1] = fmaf(run[i + 1], ep.acc_scale, bq.y);
+        run[i + 2] = fmaf(run[i + 2], ep.acc_scale, bq.z);
+        run[i + 3] = fmaf(run[i + 3], ep.acc_scale, bq.w);
+    }
     {
         const int row = th * 8 + tw;
         const uint32_t sw = (uint32_t)(row & 7);
@@ -650,7 +656,12 @@ __device__ __forceinline__ void gdn_tile_epilogue(const TcParams& P, const float
         uint32_t d[16];
         tc_ld16(taddr + 16 * j, d);
         tc_wait_ld();
-        float y[16];
+        float y[16], gb[16];
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+            const float4 bq = *reinterpret_cast<const float4*>(gbeta_s + cA + 16 * j + q);
+            gb[q] = bq.x; gb[q + 1] = bq.y; gb[q + 2] = bq.z; gb[q + 3] = bq.w;
+        }
 #pragma unroll
         for (int q = 0; q < 16; q += 2) {
             // x as the unfused path read it back from its hi/lo record
@@ -660,8 +671,8 @@ __device__ __forceinline__ void gdn_tile_epilogue(const TcParams& P, const float
             e2f2(h, h0, h1);
             e2f2(ep_pack2(x0 - h0, x1 - h1), l0, l1);
             const float r0 = h0 + l0, r1 = h1 + l1;
-            const float n0 = fmaf(__uint_as_float(d[q]), ep.gdn_scale, gbeta_s[cA + 16 * j + q]);
-            const float n1 = fmaf(__uint_as_float(d[q + 1]), ep.gdn_scale, gbeta_s[cA + 16 * j + q + 1]);
+            const float n0 = fmaf(__uint_as_float(d[q]), ep.gdn_scale, gb[q]);
+            const float n1 = fmaf(__uint_as_float(d[q + 1]), ep.gdn_scale, gb[q + 1]);
             y[q] = ep.gdn_inverse ? r0 * sqrtf(n0) : r0 / sqrtf(n0);
             y[q + 1] = ep.gdn_inverse ? r1 * sqrtf(n1) : r1 / sqrtf(n1);
         }
@@ -712,12 +723,22 @@ __device__ __forceinline__ void tap_stage_issue(const TcParams& P, const float* 
                     ld_global_nc_v8(rec_res + ep.res_act.Cp + cA + 16 * j, rl);
                 }
             }
+            // bias as four 16-byte shared-memory loads (cA is a multiple of 32); the activation is selected once per
+            // 16 channels; LeakyReLU as max(w, 0.1 w): the same bits as the select, one instruction less
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                float w = fmaf(run[16 * j + q], ep.acc_scale, bias_s[cA + 16 * j + q]);
-                if (ep.act == FVC_ACT_RELU) w = fmaxf(w, 0.f);
-                else if (ep.act == FVC_ACT_LRELU01) w = w > 0.f ? w : w * 0.1f;
-                v[q] = w;
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 bq = *reinterpret_cast<const float4*>(bias_s + cA + 16 * j + 4 * q4);
+                v[4 * q4 + 0] = fmaf(run[16 * j + 4 * q4 + 0], ep.acc_scale, bq.x);
+                v[4 * q4 + 1] = fmaf(run[16 * j + 4 * q4 + 1], ep.acc_scale, bq.y);
+                v[4 * q4 + 2] = fmaf(run[16 * j + 4 * q4 + 2], ep.acc_scale, bq.z);
+                v[4 * q4 + 3] = fmaf(run[16 * j + 4 * q4 + 3], ep.acc_scale, bq.w);
+            }
+            if (ep.act == FVC_ACT_RELU) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
+            } else if (ep.act == FVC_ACT_LRELU01) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], v[q] * 0.1f);
             }
             if (RES) {
 #pragma unroll
@@ -1214,6 +1235,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pb * P.CT + colbase;
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
+                    if constexpr (GDN || TAP) {
+                        // first chain of a tile: straight into the running sums (these kernels' tiles are one to three
+                        // chains; the generic path's copy costs 32 moves per thread and tile)
+                        if (g == 0) {
+                            tc_ld8(taddr + i * 8, reinterpret_cast<uint32_t*>(run + i * 8));
+                            tc_wait_ld();
+                            continue;
+                        }
+                    }
                     float v[8];
                     // At most two TMEM loads in flight: the address of load i carries a (zero) dependency on
                     // the sums of chunk i-2.  Unconstrained, ptxas issues 4+ loads back to back and then
