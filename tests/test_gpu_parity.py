@@ -1264,6 +1264,30 @@ def test_fused_tails_match_separate_convolutions(dev, state_dict, monkeypatch):
     print("launches fused %d vs separate %d" % (a[4], b[4]))
 
 
+def test_three_partial_buffers_bit_identical_to_two(dev, state_dict, monkeypatch):
+    """The fused GDN / tail kernels rotate THREE partial-accumulator buffers in TMEM (FVC_TC_NAB3, default on): buffering
+    depth only, the chains and their order are unchanged -> every output bit-identical to the two-buffer ring, also over
+    partial tiles and several tiles per CTA (the ring index is g mod 3, its phase bit flips every third chain)."""
+    from fastvideocodec_b200 import VideoCompressor
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    res = {}
+    for (H, W, gid) in ((192, 320, 8), (448, 704, 9)):
+        fr = synthetic_gop(H, W, gop=2, gop_id=gid).to(dev)
+        for nab3 in ("1", "0"):
+            monkeypatch.setenv("FVC_TC_NAB3", nab3)
+            m = VideoCompressor()
+            m.load_state_dict(state_dict)
+            m = m.to(dev).eval()
+            m.impl = _impls()[-1][1]
+            with torch.no_grad():
+                out = m(fr[1], fr[0])
+            res[nab3] = (out, [m.get_intermediate(n) for n in ("mv_hat", "warpnet_res", "feature", "recon_res")])
+            m.release()
+        a, b = res["1"], res["0"]
+        assert torch.equal(a[0][0], b[0][0]) and all(float(x) == float(y) for x, y in zip(a[0][1:], b[0][1:]))
+        assert all(torch.equal(x, y) for x, y in zip(a[1], b[1]))
+
+
 def test_lsvc_forward_matches_oracle_larger_frames(dev, state_dict):
     """LSVC tree GOP (models.py:1344-1411) at 192x320 with 6 P-frames (three tree layers: batches of 6 / 2 / 4) against
     the oracle's restatement (pinned to the unmodified reference at 64x64): bpp / losses within 0.5 %, frames of the
