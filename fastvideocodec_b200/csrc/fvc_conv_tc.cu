@@ -390,7 +390,10 @@ struct PassIter {
 // loads (residual) of a batch of chunks are all issued before any of them is consumed and before the
 // batch's stores, so a thread pays one memory round trip per batch instead of one per chunk
 // (ncu: the per-chunk version was stall_long_sb-bound and starved the MMA pipe).
-template <int NCH, bool RES, bool STG = false>
+// LEAN: the instantiation for the common layer shape (ACT outputs only, no activation beyond ReLU / LeakyReLU(0.1), additive
+// skip only): the rarely used branches are compiled out, the kernel's code shrinks (instruction fetch is a visible stall
+// of the epilogue-bound layers, ncu)
+template <int NCH, bool RES, bool STG = false, bool LEAN = false>
 __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __restrict__ bias_s, const float* run,
                                               int b, int sub, int ty, int tx, int th, int tw, uint32_t colbase,
                                               uint32_t stg) {
@@ -501,10 +504,10 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
                 } else if (act == FVC_ACT_LRELU01) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) w[q] = w[q] > 0.f ? w[q] : w[q] * 0.1f;
-                } else if (act == FVC_ACT_EXP) {
+                } else if (!LEAN && act == FVC_ACT_EXP) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) w[q] = expf(w[q]);
-                } else if (act == FVC_ACT_LRELU001) {
+                } else if (!LEAN && act == FVC_ACT_LRELU001) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) w[q] = w[q] > 0.f ? w[q] : w[q] * 0.01f;
                 }
@@ -519,7 +522,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
                         r[2 * q] = a0 + b0;
                         r[2 * q + 1] = a1 + b1;
                     }
-                    if (ep.res_mode == 0) {
+                    if (LEAN || ep.res_mode == 0) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) w[q] += r[q];
                     } else if (ep.res_mode == 1) {   // GDN.py:88-93: x / sqrt(beta + gamma . x^2)
@@ -530,12 +533,12 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
                         for (int q = 0; q < 8; ++q) w[q] = r[q] * sqrtf(w[q]);
                     }
                 }
-                if (ep.res_f32) {
+                if (!LEAN && ep.res_f32) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         if (c0 + q < Cout) w[q] += ep.res_f32[pixC + c0 + q];
                 }
-                if (ep.out_f32) {
+                if (!LEAN && ep.out_f32) {
                     if ((Cout & 7) == 0) {
                         // 8 channels = one 32-byte sector per store
                         if (c0 < Cout) st_global_v8(ep.out_f32 + pixC + c0, reinterpret_cast<const uint32_t*>(w));
@@ -563,7 +566,7 @@ __device__ __forceinline__ void tile_epilogue(const TcParams& P, const float* __
                 if (ep.out_act.p && c0 < ep.out_act.Cp) ep_store8_packed(rec_out, ep.out_act.Cp, c0, v, false, satm, wlo);
                 if (ep.out_act_relu.p && c0 < ep.out_act_relu.Cp) ep_store8_packed(rec_relu, ep.out_act_relu.Cp, c0, v, true, satm, wlo);
             }
-            if (ep.out_act_sq.p && c0 < ep.out_act_sq.Cp) {   // squares for the following (I)GDN
+            if (!LEAN && ep.out_act_sq.p && c0 < ep.out_act_sq.Cp) {   // squares for the following (I)GDN
 #pragma unroll
                 for (int q = 0; q < PAIR * 8; ++q) v[q] = v[q] * v[q] * ep.sq_scale;
                 if (PAIR == 2) ep_store16_packed(rec_sq, ep.out_act_sq.Cp, c0, v, false, satm, wlo);
@@ -839,6 +842,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
     constexpr bool STG = MODE == 1;    // TMA-store epilogue
     constexpr bool GDN = MODE == 2;    // fused (I)GDN epilogue
     constexpr bool TAP = MODE == 3;    // fused 3x3 tail convolution (tap-split second MMA)
+    constexpr bool LEAN = MODE == 4;   // MODE 0 with the rare epilogue branches compiled out (tile_epilogue)
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: SWIZZLE_128B atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1305,12 +1309,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                         for (int i = 0; i < NCH / 2; ++i)
 #pragma unroll
                             for (int q = 0; q < 8; ++q) run[i * 8 + q] = run[2 * i * 8 + q] + run[(2 * i + 1) * 8 + q];
-                        tile_epilogue<NCH / 2, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase >> 1, stg);
+                        tile_epilogue<NCH / 2, RES, false, LEAN>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase >> 1, stg);
                     } else {
-                        tile_epilogue<NCH, RES, STG>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
+                        tile_epilogue<NCH, RES, STG, LEAN>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
                     }
                 } else {
-                    tile_epilogue<NCH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
+                    tile_epilogue<NCH, RES, false, LEAN>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
                 }
             } else {
                 // 48/64 running sums + the epilogue state do not fit 96 registers (ncu: spill reloads
@@ -1323,7 +1327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
 #pragma unroll
                 for (int i = NH; i < NCH; ++i) tc_st8(taddr + i * 8, reinterpret_cast<const uint32_t*>(run + i * 8));
                 tc_wait_st();
-                tile_epilogue<NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
+                tile_epilogue<NH, RES, false, LEAN>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase, stg);
 #pragma unroll
                 for (int i = NH; i < NCH; ++i) {
                     tc_ld8(taddr + i * 8, reinterpret_cast<uint32_t*>(run + (i - NH) * 8));
@@ -1335,7 +1339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant
                     if (PAIR) mbar_arrive_cluster(aempty_l + 8 * pb);
                     else mbar_arrive(bar_aempty + 8 * pb);
                 }
-                tile_epilogue<NCH - NH, RES>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase + NH * 8, stg);
+                tile_epilogue<NCH - NH, RES, false, LEAN>(P, bias_s, run, b, sub, ty, tx, th, tw, colbase + NH * 8, stg);
             }
             if (STG && stg) {
                 // generic-proxy writes of the staging blocks -> visible to the async proxy; then one lane issues the
@@ -1479,6 +1483,7 @@ __global__ void k_tc_pack(const float* __restrict__ w, e16* __restrict__ out, co
 // host: plan
 // ----------------------------------------------------------------------------------------------
 struct TcPlan {
+    bool lean = false;     // the layer qualifies for the LEAN instantiation (k_conv_tc<.., 4>)
     unsigned long long* dbg = nullptr;
     TcParams P;
     e16* wstream = nullptr;
@@ -1969,6 +1974,9 @@ int tc_plan_create(const ConvLayer& L, const float* w_ref, ActT in, int Hout, in
         if (cudaMalloc(&plan->dbg, 64) == cudaSuccess) cudaMemset(plan->dbg, 0, 64);
         P.dbg = plan->dbg;
     }
+    plan->lean = env_int("FVC_TC_LEAN", 1) != 0 && !gdn && !tap && !tmast && ep.out_act.p && !ep.out_f32 && !ep.res_f32 &&
+                 !ep.out_act_sq.p && (ep.act == FVC_ACT_NONE || ep.act == FVC_ACT_RELU || ep.act == FVC_ACT_LRELU01) &&
+                 (!ep.res_act.p || ep.res_mode == 0);
     plan->smem = 1024 + (size_t)npb * P.patch_bytes + (size_t)P.stg_bytes + (size_t)nst * P.stage_bytes + 1024;
     int ntiles = P.B * P.nsub * P.tiles_y * P.tiles_x;
     plan->grid = pair ? 2 * std::max(1, std::min(ntiles, sms / 2)) : std::max(1, std::min(ntiles, sms));
@@ -2033,6 +2041,7 @@ static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
         }
         if (plan->P.tap) return tc_launch_t3<NCH, RES, false, 3>(plan, s);
     }
+    if (plan->lean) return plan->P.pair ? tc_launch_t3<NCH, RES, true, 4>(plan, s) : tc_launch_t3<NCH, RES, false, 4>(plan, s);
     return plan->P.pair ? tc_launch_t3<NCH, RES, true>(plan, s) : tc_launch_t3<NCH, RES, false>(plan, s);
 }
 
