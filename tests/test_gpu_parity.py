@@ -1288,6 +1288,30 @@ def test_three_partial_buffers_bit_identical_to_two(dev, state_dict, monkeypatch
         assert all(torch.equal(x, y) for x, y in zip(a[1], b[1]))
 
 
+def test_lean_kernels_bit_identical_to_generic(dev, state_dict, monkeypatch):
+    """Most layers run a LEAN instantiation of the convolution kernel (k_conv_tc<.., 4>: the epilogue branches they never
+    take are compiled out, FVC_TC_LEAN, default on).  Same arithmetic in the same order: every tensor of the frame is
+    bit-identical to the generic kernels', in both precision modes."""
+    from fastvideocodec_b200 import VideoCompressor
+    from fastvideocodec_b200.synthetic import synthetic_gop
+    fr = synthetic_gop(320, 448, gop=2, gop_id=10).to(dev)
+    names = ("estmv", "mvfeature", "mv_hat", "prediction", "feature", "z", "sigma", "recon_res")
+    for precision in ("exact", "fast"):
+        res = {}
+        for lean in ("1", "0"):
+            monkeypatch.setenv("FVC_TC_LEAN", lean)
+            m = VideoCompressor(precision=precision)
+            m.load_state_dict(state_dict)
+            m = m.to(dev).eval()
+            with torch.no_grad():
+                out = m(fr[1], fr[0])
+            res[lean] = (out, [m.get_intermediate(n) for n in names])
+            m.release()
+        a, b = res["1"], res["0"]
+        assert torch.equal(a[0][0], b[0][0]) and all(float(x) == float(y) for x, y in zip(a[0][1:], b[0][1:])), precision
+        assert all(torch.equal(x, y) for x, y in zip(a[1], b[1])), precision
+
+
 def test_lsvc_forward_matches_oracle_larger_frames(dev, state_dict):
     """LSVC tree GOP (models.py:1344-1411) at 192x320 with 6 P-frames (three tree layers: batches of 6 / 2 / 4) against
     the oracle's restatement (pinned to the unmodified reference at 64x64): bpp / losses within 0.5 %, frames of the
