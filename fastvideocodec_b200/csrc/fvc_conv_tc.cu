@@ -2041,7 +2041,9 @@ static int tc_launch_t2(TcPlan* plan, cudaStream_t s) {
         }
         if (plan->P.tap) return tc_launch_t3<NCH, RES, false, 3>(plan, s);
     }
-    if (plan->lean) return plan->P.pair ? tc_launch_t3<NCH, RES, true, 4>(plan, s) : tc_launch_t3<NCH, RES, false, 4>(plan, s);
+    if constexpr (NCH >= 2 && NCH <= 6) {   // the accumulator widths the frame's lean layers use (compile time: 16 kernels)
+        if (plan->lean) return plan->P.pair ? tc_launch_t3<NCH, RES, true, 4>(plan, s) : tc_launch_t3<NCH, RES, false, 4>(plan, s);
+    }
     return plan->P.pair ? tc_launch_t3<NCH, RES, true>(plan, s) : tc_launch_t3<NCH, RES, false>(plan, s);
 }
 
